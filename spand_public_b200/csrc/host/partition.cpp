@@ -1,0 +1,241 @@
+#include "partition.hpp"
+
+#include <algorithm>
+#include <cassert>
+#include <cstdint>
+#include <cstdio>
+#include <limits>
+#include <numeric>
+#include <stdexcept>
+
+// METIS as shipped in the CUDA toolkit's static library: 64-bit idx_t (the reference wants
+// the 32-bit build, src/partition.cpp:53; arrays are widened at this boundary instead).
+extern "C" {
+int METIS_SetDefaultOptions(int64_t* options);
+int METIS_ComputeVertexSeparator(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* options,
+                                 int64_t* sepsize, int64_t* part);
+}
+
+namespace spand {
+
+namespace {
+
+// Graph without self loops (src/partition.cpp:21-39)
+void graph_csc(const SpMat& A, std::vector<int>& colptr, std::vector<int>& rowval) {
+    int n = A.rows;
+    colptr.assign(n + 1, 0);
+    rowval.clear();
+    rowval.reserve(A.nnz());
+    for (int j = 0; j < n; j++) {
+        for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++)
+            if (A.rowind[k] != j) rowval.push_back(A.rowind[k]);
+        colptr[j + 1] = (int)rowval.size();
+    }
+}
+
+// src/partition.cpp:51-97 (vertex-separator branch only; Tree::partition hard-wires
+// use_vertex_sep = true, src/tree.cpp:318)
+void separator_metis(const std::vector<int>& colptr, const std::vector<int>& rowval, const std::vector<int>& dofs,
+                     std::vector<int>& parts) {
+    int size = (int)dofs.size();
+    if (size == 0) return;
+    std::vector<int64_t> xadj(size + 1, 0), adj;
+    for (int i = 0; i < size; i++) {
+        int g = dofs[i];
+        for (int k = colptr[g]; k < colptr[g + 1]; k++) {
+            int nb = rowval[k];
+            if (nb == g) continue;
+            auto it = std::lower_bound(dofs.begin(), dofs.end(), nb);
+            if (it != dofs.end() && *it == nb) adj.push_back((int64_t)(it - dofs.begin()));
+        }
+        xadj[i + 1] = (int64_t)adj.size();
+    }
+    int64_t options[64];
+    if (METIS_SetDefaultOptions(options) != 1) throw std::runtime_error("METIS_SetDefaultOptions failed");
+    int64_t nv = size, sepsize = 0;
+    std::vector<int64_t> p64(size, 0);
+    if (adj.empty()) adj.push_back(0);
+    int rc = METIS_ComputeVertexSeparator(&nv, xadj.data(), adj.data(), nullptr, options, &sepsize, p64.data());
+    if (rc != 1) throw std::runtime_error("METIS_ComputeVertexSeparator failed");
+    for (int i = 0; i < size; i++) parts[i] = (int)p64[i];
+}
+
+// src/partition.cpp:139-210
+void separator_geo(const std::vector<int>& colptr, const std::vector<int>& rowval, const std::vector<int>& dofs,
+                   std::vector<int>& parts, const DenseMat& X, std::vector<int>& invp) {
+    int N = (int)dofs.size();
+    if (N == 0) return;
+    int bestdim = -1;
+    double maxrange = -1.0;
+    for (int d = 0; d < X.rows; d++) {
+        double maxi = std::numeric_limits<double>::lowest(), mini = std::numeric_limits<double>::max();
+        for (int g : dofs) {
+            double x = X(d, g);
+            maxi = std::max(maxi, x);
+            mini = std::min(mini, x);
+        }
+        if (maxi - mini > maxrange) {
+            bestdim = d;
+            maxrange = maxi - mini;
+        }
+    }
+    // Median coordinate = value at rank N/2 (the reference sorts the dofs; only this value is used)
+    std::vector<double> xs(N);
+    for (int i = 0; i < N; i++) xs[i] = X(bestdim, dofs[i]);
+    std::nth_element(xs.begin(), xs.begin() + N / 2, xs.end());
+    double midv = xs[N / 2];
+    for (int g : dofs) {
+        invp[g] = -1;
+        for (int k = colptr[g]; k < colptr[g + 1]; k++) invp[rowval[k]] = -1;
+    }
+    for (int i = 0; i < N; i++) {
+        int g = dofs[i];
+        invp[g] = i;
+        parts[i] = (X(bestdim, g) < midv) ? 0 : 1;
+    }
+    for (int i = 0; i < N; i++) {
+        if (parts[i] == 0) continue;
+        int g = dofs[i];
+        for (int k = colptr[g]; k < colptr[g + 1]; k++) {
+            int in = invp[rowval[k]];
+            if (in == -1) continue;
+            if (parts[in] == 0) {
+                parts[i] = 2;
+                break;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+std::vector<ClusterID> partition_modifiedND(const SpMat& A, int nlevels, const DenseMat* Xcoo, bool verb) {
+    int N = A.rows;
+    bool geo = (Xcoo != nullptr);
+    if (verb) printf(geo ? "Geometric MND partitioning & ordering\n" : "Algebraic MND partitioning & ordering\n");
+    std::vector<int> colptr, rowval;
+    graph_csc(A, colptr, rowval);
+    std::vector<int> parttmp(N), scratch(N + 1);
+    std::vector<std::vector<int>> doms(1, std::vector<int>(N));
+    std::iota(doms[0].begin(), doms[0].end(), 0);
+    SepID top(nlevels - 1, 0);
+    std::vector<ClusterID> part(N, ClusterID(top, top, top));
+    for (int depth = 0; depth < nlevels - 1; depth++) {
+        int level = nlevels - depth - 1;
+        int nseps = 1 << depth;
+        std::vector<std::vector<int>> newdoms(2 * nseps);
+        long sepmin = N, sepmax = 0, septot = 0;
+        for (int sep = 0; sep < nseps; sep++) {
+            SepID idself(level, sep);
+            std::vector<int> dofs = doms[sep];
+            std::sort(dofs.begin(), dofs.end());
+            if (geo) separator_geo(colptr, rowval, dofs, parttmp, *Xcoo, scratch);
+            else separator_metis(colptr, rowval, dofs, parttmp);
+            SepID idleft(level - 1, 2 * sep), idright(level - 1, 2 * sep + 1);
+            for (size_t i = 0; i < dofs.size(); i++) {
+                ClusterID& p = part[dofs[i]];
+                int side = parttmp[i];
+                if (side == 0 || side == 1) {
+                    const SepID& idside = (side == 0 ? idleft : idright);
+                    if (p.self == idself) p.self = idside;
+                    if (p.l == idself) p.l = idside;
+                    if (p.r == idself) p.r = idside;
+                } else if (side == 2) {
+                    if (p.self == idself) {
+                        p.l = idleft;
+                        p.r = idright;
+                    }
+                }
+            }
+            long nnewsep = 0;
+            for (int g : dofs) {
+                const ClusterID& p = part[g];
+                if (p.self == idleft || p.l == idleft || p.r == idleft) newdoms[2 * sep].push_back(g);
+                if (p.self == idright || p.l == idright || p.r == idright) newdoms[2 * sep + 1].push_back(g);
+                if (p.self == idself && p.l == idleft && p.r == idright) nnewsep++;
+            }
+            sepmin = std::min(sepmin, nnewsep);
+            sepmax = std::max(sepmax, nnewsep);
+            septot += nnewsep;
+        }
+        doms.swap(newdoms);
+        if (verb)
+            printf("  Depth %2d: (%5d separators, [%5ld %5ld], mean %6.1f)\n", depth + 1, nseps, sepmin, sepmax,
+                   (double)septot / nseps);
+    }
+    return part;
+}
+
+Ordering build_ordering(const SpMat& A, int nlevels, const DenseMat* Xcoo, bool verb) {
+    if (A.rows != A.cols) throw std::runtime_error("partition: matrix must be square");
+    if (nlevels <= 0) throw std::runtime_error("partition: nlevels must be > 0");
+    if (Xcoo && Xcoo->cols != A.rows) throw std::runtime_error("partition: coordinates must be dim x N");
+    Ordering o;
+    int N = A.rows;
+    o.N = N;
+    o.nlevels = nlevels;
+    o.part = partition_modifiedND(A, nlevels, Xcoo, verb);
+    // Ordering: identity, then L stable sorts by progressively merged ClusterIDs (tree.cpp:344-352)
+    o.perm.resize(N);
+    std::iota(o.perm.begin(), o.perm.end(), 0);
+    std::vector<ClusterID> merged = o.part;
+    auto cmp = [&merged](int i, int j) { return merged[i] < merged[j]; };
+    std::stable_sort(o.perm.begin(), o.perm.end(), cmp);
+    for (int lvl = 1; lvl < nlevels; lvl++) {
+        for (auto& c : merged) c = merge_if(c, lvl);
+        std::stable_sort(o.perm.begin(), o.perm.end(), cmp);
+    }
+    // Leaf clusters = maximal runs of equal ClusterID (tree.cpp:360-370)
+    o.levels.assign(nlevels, {});
+    int order = 0;
+    for (int k = 0; k < N;) {
+        const ClusterID& id = o.part[o.perm[k]];
+        int knext = k + 1;
+        while (knext < N && o.part[o.perm[knext]] == id) knext++;
+        ClusterNode c;
+        c.start = k;
+        c.size = knext - k;
+        c.level = id.self.lvl;
+        c.order = order++;
+        c.sparsify = (id.l.lvl == 0 && id.r.lvl == 0);
+        c.parent = -1;
+        c.child_begin = c.child_end = 0;
+        c.id = id;
+        o.levels[0].push_back(c);
+        k = knext;
+    }
+    // Hierarchy (tree.cpp:381-415)
+    for (int lvl = 1; lvl < nlevels; lvl++) {
+        auto& prev = o.levels[lvl - 1];
+        size_t begin = 0;
+        while (begin < prev.size() && prev[begin].level < lvl) begin++;
+        for (size_t k = begin; k < prev.size();) {
+            if (prev[k].level < lvl) throw std::runtime_error("partition: hierarchy is not sorted by level");
+            ClusterID idp = merge_if(prev[k].id, lvl);
+            ClusterNode p;
+            p.start = prev[k].start;
+            p.size = 0;
+            p.child_begin = (int)k;
+            while (k < prev.size() && merge_if(prev[k].id, lvl) == idp) {
+                p.size += prev[k].size;
+                prev[k].parent = (int)o.levels[lvl].size();
+                k++;
+            }
+            p.child_end = (int)k;
+            p.level = idp.self.lvl;
+            p.order = order++;
+            p.sparsify = (idp.l.lvl == lvl && idp.r.lvl == lvl);
+            p.parent = -1;
+            p.id = idp;
+            o.levels[lvl].push_back(p);
+        }
+    }
+    o.norders = order;
+    if (verb) {
+        printf("Hierarchy numbers (# of cluster at each level of the cluster-hierarchy)\n");
+        for (int lvl = 0; lvl < nlevels; lvl++) printf("%3d %9zu\n", lvl, o.levels[lvl].size());
+    }
+    return o;
+}
+
+}  // namespace spand
