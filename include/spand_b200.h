@@ -1,0 +1,104 @@
+/* spand_b200.h — C ABI of the B200-native spaND factorization path.
+ *
+ * This is the drop-in boundary: every entry point replaces one public member of the reference's
+ * spaND::Tree (include/tree.h, citations relative to /root/reference) or one free function taking a
+ * Tree (include/is.h). Plain pointers and sizes only; all matrices are CSC with int32 indices and
+ * FP64 values; vectors are host pointers unless the name says _device. Return value 0 = success,
+ * 1 = "Error: Non-SPD Pivot" (src/tree.cpp:587-590), 2 = "Error: Singular Pivot" (src/tree.cpp:625-628),
+ * -1 = any other failure (message via spand_last_error). There is no CPU fallback: calls that need the
+ * GPU fail with -1 when no CUDA device is present.
+ */
+#ifndef SPAND_B200_H
+#define SPAND_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spand_tree spand_tree;
+
+/* enums of include/spaND.h:19-21 */
+enum { SPAND_SPD = 0, SPAND_SYM = 1, SPAND_GEN = 2 };
+enum { SPAND_LLT = 0, SPAND_PLU = 3 };
+
+/* Tree::Tree(int lvl)                               include/tree.h:170, src/tree.cpp:86-113 */
+spand_tree* spand_create(int nlevels);
+void spand_destroy(spand_tree* t);
+const char* spand_last_error(spand_tree* t);
+
+/* Tree::set_tol / set_skip / set_symm_kind / set_scaling_kind / set_use_geo / set_verb / set_use_sparsify
+ *                                                   include/tree.h:133-147, src/tree.cpp:114-131 */
+int spand_set_tol(spand_tree* t, double tol);
+int spand_set_skip(spand_tree* t, int skip);
+int spand_set_symm_kind(spand_tree* t, int kind);
+int spand_set_scaling_kind(spand_tree* t, int kind);
+int spand_set_use_geo(spand_tree* t, int geo);
+int spand_set_verb(spand_tree* t, int verb);
+int spand_set_use_sparsify(spand_tree* t, int use);
+int spand_set_device(spand_tree* t, int device);
+/* Tree::set_Xcoo — dim x N, column-major; copied (the reference borrows the pointer, tree.h:56) */
+int spand_set_coords(spand_tree* t, int dim, int N, const double* X);
+/* test hook: stop after (level, phase) with phase 0=eliminate 1=scale 2=sparsify 3=merge; -1 = off */
+int spand_set_stop(spand_tree* t, int level, int phase);
+
+/* Tree::partition(SpMat&)                           include/tree.h:176, src/tree.cpp:306-419
+ * A: symmetric pattern (values ignored). */
+int spand_partition(spand_tree* t, int N, const int* colptr, const int* rowind);
+/* the returned vector<ClusterID>, natural ordering; each array has N entries */
+int spand_get_partition(spand_tree* t, int* self_lvl, int* self_sep, int* l_lvl, int* l_sep, int* r_lvl, int* r_sep);
+/* Tree::get_assembly_perm                           include/tree.h:152 */
+int spand_get_perm(spand_tree* t, int* perm);
+int spand_get_N(spand_tree* t);
+
+/* Tree::assemble(SpMat&)                            include/tree.h:182, src/tree.cpp:505-575
+ * Builds the dense blocks and uploads them to HBM. May be called again to restart from the same partition. */
+int spand_assemble(spand_tree* t, int N, const int* colptr, const int* rowind, const double* val);
+
+/* Tree::factorize()                                 include/tree.h:186, src/tree.cpp:1447-1551 */
+int spand_factorize(spand_tree* t);
+
+/* Tree::solve(VectorXd&) — in place                 include/tree.h:192, src/tree.cpp:1610-1635 */
+int spand_solve(spand_tree* t, double* x);
+int spand_solve_device(spand_tree* t, double* x_device);
+
+/* cg(A, rhs, x, precond, iters, tol, verb)          include/is.h:12, src/is.cpp:39-121
+ * returns the iteration count of the reference (i+1) or a negative error; x is the initial guess / result */
+int spand_cg(spand_tree* t, int N, const int* colptr, const int* rowind, const double* val, const double* rhs,
+             double* x, int iters, double tol, int verb, double* seconds);
+
+/* Tree::nnz / get_stop / get_nlevels                include/tree.h:158-160 */
+long long spand_nnz(spand_tree* t);
+int spand_get_stop(spand_tree* t);
+int spand_get_nlevels(spand_tree* t);
+
+/* write_stats triple (order id, original size, final size) for every hierarchy cluster
+ *                                                   include/tree.h:242-251, src/tree.cpp:44-57 */
+int spand_num_clusters(spand_tree* t);
+int spand_get_stats(spand_tree* t, int* id, int* size, int* rank);
+
+/* Tree::log / Tree::tprof                           include/tree.h:163-165, include/util.h:262-401
+ * spand_log_fields() doubles per level, see spand_log_field_name(i) */
+int spand_log_fields(void);
+const char* spand_log_field_name(int i);
+int spand_get_log(spand_tree* t, double* out);
+/* device time of the last factorize(), CUDA events on the factorization stream, seconds */
+double spand_factorize_seconds(spand_tree* t);
+long long spand_kernel_launches(spand_tree* t);
+long long spand_arena_bytes(spand_tree* t);
+
+/* Tree::get_trailing_mat                            include/tree.h:153, src/tree.cpp:1730-1763
+ * permuted ordering, CSC; call with null pointers to get nnz first */
+int spand_trailing(spand_tree* t, int* colptr, int* rowind, double* val);
+
+/* host utilities of src/util.cpp used by the drivers */
+void spand_util_random(int size, int seed, double* out);              /* util.cpp:549-558 */
+void spand_util_linspace_nd(int n, int dim, double* out);             /* util.cpp:488-517 */
+int spand_util_neglapl(int n, int d, int* colptr, int* rowind, double* val); /* mats/neglapl_d_n.mm generator */
+int spand_util_aniso(int n, int* colptr, int* rowind, double* val);  /* config C5, SURVEY.md 8(d) */
+int spand_util_mm_read(const char* fn, int* rows, int* cols, int* colptr, int* rowind, double* val); /* mmio.hpp:160 */
+int spand_util_mm_read_dense(const char* fn, int* rows, int* cols, double* out);                      /* mmio.hpp:225 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

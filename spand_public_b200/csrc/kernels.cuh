@@ -1,0 +1,135 @@
+// Device task descriptors + launchers for the spaND factorization hot path on sm_100a.
+//
+// One launcher = one variable-size batch over all clusters / edges of a level. Which reference
+// BLAS/LAPACK call each batch replaces (citations relative to /root/reference):
+//   launch_potrf_step   LAPACKE_dpotrf    src/util.cpp:158-165   <- potf_cluster  src/tree.cpp:582
+//   launch_trsm_step    cblas_dtrsm       src/util.cpp:256-274   <- trsm_potf_edgeIn/Out src/tree.cpp:640-663
+//   launch_gemm         cblas_dgemm/dsyrk src/util.cpp:122-156   <- gemm_edges    src/tree.cpp:748-793
+//   launch_rrqr         assemble_Asn + LAPACKE_dgeqp3 + choose_rank + scatter
+//                                         src/tree.cpp:1189-1224, 1292-1347, 1004-1046; src/util.cpp:383-452
+//   launch_copy         update_edges block copy + setZero           src/tree.cpp:1133-1184
+//   launch_trsv / launch_gemv / launch_house / launch_xcopy
+//                       Scaling*/Gemm*/Orthogonal/Merge ::fwd/bwd   src/operations.cpp:31-208
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace spand {
+
+constexpr int NB = 64;  // block size of the right-looking blocked POTRF / TRSM
+
+struct PotrfTask {
+    double* A;  // n x n, column-major, lower triangle referenced
+    int ld, n;
+};
+
+enum TrsmMode {
+    TRSM_RLT = 0,  // B (m x n) <- B T^-T, T lower n x n      (out-edge of an LLT pivot)
+    TRSM_LLN = 1,  // B (n x m) <- T^-1 B, T lower n x n      (in-edge of an LLT / PLU pivot)
+    TRSM_RUN = 2,  // B (m x n) <- B T^-1, T upper n x n      (out-edge of a PLU pivot)
+};
+
+struct TrsmTask {
+    double* B;
+    const double* T;
+    int ldb, ldt;
+    int m;  // free dimension of B
+    int n;  // triangle dimension
+};
+
+struct GemmContrib {
+    const double* A;  // m x k, column-major
+    const double* B;  // NT: n x k (used transposed);  NN: k x n
+    int lda, ldb, k;
+};
+
+enum GemmFlags { GEMM_LOWER = 1, GEMM_ZERO_INIT = 2, GEMM_NN = 4 };
+
+struct GemmTask {
+    double* C;  // m x n, C = (ZERO_INIT ? 0 : C) - sum_c A_c op(B_c)
+    int ldc, m, n;
+    int c0, nc;  // contributions [c0, c0 + nc), applied in this order (deterministic)
+    int flags;
+};
+
+struct QrSrc {
+    double* blk;     // the edge block
+    int ld;
+    int nbr;         // neighbour cluster id: its current size is the free dimension of the block
+    int transposed;  // 0: in-edge  A[s,n] (rows x w);  1: out-edge A[n,s] (w x rows)
+};
+
+struct QrTask {
+    int cluster;
+    int rows;     // current size of the cluster (it has not been sparsified before)
+    int src0, nsrc;
+    double* W;    // scratch: rows x maxcols (+ norms)
+    int maxcols;
+    double* V;    // out: rows x rank Householder vectors (unit diagonal implicit), ld = rows
+    double* tau;  // out: rank
+    int* ipiv;    // scratch: 2 * maxcols
+};
+
+struct CopyTask {
+    const double* src;  // nullptr => identity block
+    double* dst;
+    int lds, ldd, rows, cols;
+};
+
+struct TrsvTask {
+    const double* T;
+    double* x;
+    int ld, n;
+};
+
+struct GemvContrib {
+    const double* A;
+    const double* x;
+    int lda, k;  // fwd: A is m x k, y -= A x ;  bwd (trans): A is k x m, y -= A^T x
+};
+
+struct GemvTask {
+    double* y;
+    int m, c0, nc;
+};
+
+struct HouseTask {
+    const double* V;
+    const double* tau;
+    double* x;
+    int rows, rank;
+};
+
+struct XCopyTask {
+    const double* src;
+    double* dst;
+    int n;
+};
+
+// All launchers are asynchronous on `st`. `err` is a device int: bit 0 = non-SPD pivot.
+void launch_potrf_step(const PotrfTask* t, int nt, int j0, int* err, cudaStream_t st);
+void launch_trsm_step(int mode, const TrsmTask* t, int nt, int j0, int max_m, cudaStream_t st);
+// tile_prefix: nt + 1 exclusive prefix of ceil(m/64)*ceil(n/64); total_tiles = tile_prefix[nt]
+void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const int* tile_prefix, int total_tiles,
+                       cudaStream_t st);
+void launch_gemm_small(const GemmTask* t, int nt, const GemmContrib* c, cudaStream_t st);
+// csize: device array of current cluster sizes (read for neighbours, written with the rank)
+void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, cudaStream_t st);
+void launch_copy(const CopyTask* t, int nt, cudaStream_t st);
+void launch_trsv(const TrsvTask* t, int nt, int trans, cudaStream_t st);
+void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, cudaStream_t st);
+void launch_house(const HouseTask* t, int nt, int trans, cudaStream_t st);
+void launch_xcopy(const XCopyTask* t, int nt, cudaStream_t st);
+void launch_fill(double* p, size_t n, double v, cudaStream_t st);
+
+// PCG building blocks (src/is.cpp:39-121)
+void launch_spmv(int n, const int* rowptr, const int* colind, const double* val, const double* x, double* y,
+                 cudaStream_t st);
+void launch_dot(int n, const double* a, const double* b, double* out, cudaStream_t st);  // out must be zeroed
+void launch_axpy(int n, double alpha, const double* x, double* y, cudaStream_t st);      // y += alpha x
+void launch_xpay(int n, const double* x, double beta, double* y, cudaStream_t st);       // y = x + beta y
+void launch_gather(int n, const int* idx, const double* src, double* dst, cudaStream_t st);   // dst[i] = src[idx[i]]
+void launch_scatter(int n, const int* idx, const double* src, double* dst, cudaStream_t st);  // dst[idx[i]] = src[i]
+
+}  // namespace spand
