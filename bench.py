@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 spaND factorization path.
+
+One "step" = one numerical factorization (Tree::factorize, reference src/tree.cpp:1447-1551) of the
+configuration BASELINE.json quotes its metric on: the synthetic 3-D 7-point Laplacian 128^3
+(2 097 152 dofs), tol 1e-2, 16 levels, geometric modified ND (config C4). Blocks are already assembled
+in HBM when the timed region starts (`value`); `e2e` times assemble (host CSC -> dense blocks -> HBM)
++ factorize + one solve with host vectors through the C ABI.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c4|c3|c2|c1|n,d,L,tol]
+
+N > 1 (torchrun): every rank factorizes its own replica of the problem on its own GPU (no collective on
+the data path; sub-tree sharding over NCCL is not built yet), `value` = all dofs
+factorized by all ranks / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIGS = {
+    # name: (n, d, nlevels, tol, description)
+    "c1": (32, 2, 5, 1e-2, "2D Laplacian 32^2 (mats/neglapl_2_32.mm), tol 1e-2, 5 levels"),
+    "c2": (30, 3, 8, 1e-2, "3D Laplacian 30^3 (mats/neglapl_3_30.mm), tol 1e-2, 8 levels"),
+    "c3": (1024, 2, 14, 1e-3, "2D Laplacian 1024^2, tol 1e-3, 14 levels"),
+    "c4": (128, 3, 16, 1e-2, "3D Laplacian 128^3, tol 1e-2, 16 levels"),
+    "s64": (64, 3, 13, 1e-2, "3D Laplacian 64^3, tol 1e-2, 13 levels"),
+    "s48": (48, 3, 12, 1e-2, "3D Laplacian 48^3, tol 1e-2, 12 levels"),
+}
+
+
+def parse_config(name):
+    if name in CONFIGS:
+        return CONFIGS[name]
+    n, d, L, tol = name.split(",")
+    return (int(n), int(d), int(L), float(tol), f"{d}D Laplacian {n}^{d}, tol {tol}, {L} levels")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def measure_fp64_peak(torch, dev):
+    """DGEMM ceiling (cuBLAS 8192^3, best of 5): MEASURED_PEAKS.json holds no FP64 figure."""
+    try:
+        a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        best = 1e9
+        for _ in range(6):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            torch.matmul(a, b)
+            e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e) * 1e-3)
+        del a, b
+        torch.cuda.empty_cache()
+        return 2 * 8192**3 / best / 1e12
+    except Exception:
+        return None
+
+
+def flops_of(log):
+    return float(sum(log[k].sum() for k in ("fl_pivot", "fl_panel", "fl_schur", "fl_rrqr_rank")))
+
+
+def run_oracle(cfg, steps, warmup, threads):
+    """CPU arm: the oracle's factorize() timed exactly where the reference driver times it
+    (tests/spaND.cpp:274-292 -> <<<<tfact)."""
+    import oracle_lib as O
+    import spand_public_b200 as S
+    n, d, L, tol, desc = cfg
+    O.lib().orc_set_threads(threads)
+    A = S.neglapl(n, d)
+    X = S.linspace_nd(n, d)
+    G = S.symmetric_graph(A)
+    times = []
+    info = {}
+    for it in range(warmup + steps):
+        t = O.OracleTree(L, tol=tol)
+        t.set_coords(X)
+        t.partition(G)
+        t.assemble(A)
+        t0 = time.perf_counter()
+        t.factorize()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        if it == warmup + steps - 1:
+            b = S.random(A.shape[0], 2019)
+            ts = time.perf_counter()
+            x = t.solve(b)
+            info["tsolve_s"] = time.perf_counter() - ts
+            info["residual"] = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
+            info["cg_iterations"] = int(t.cg(A, b, 500, 1e-12)[0])
+            info["gflop"] = flops_of(t.log()) / 1e9
+            info["nnz_fact"] = int(t.nnz())
+        del t
+    return A.shape[0], times, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c4")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cg", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = parse_config(args.config)
+    n, d, L, tol, desc = cfg
+    metric, unit = "factorize_throughput", "Mdof/s"
+
+    if args.impl == "reference":
+        # The reference's own CPU path = the oracle port (the reference cannot be compiled here).
+        if rank != 0:
+            return 0
+        sample_name = "s64" if args.steps + args.warmup <= 8 else "s48"
+        if args.config in ("c1", "c2"):
+            sample_name = args.config
+        scfg = CONFIGS[sample_name]
+        cores = os.cpu_count() or 1
+        N, times, info = run_oracle(scfg, args.steps, args.warmup, cores)
+        tmean = float(np.mean(times))
+        val = N / tmean / 1e6
+        out = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmean * 1e3, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": desc, "sample": scfg[4]},
+               "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port",
+                                "sample": f"full factorize() of {scfg[4]} (same family/tolerance as the workload), "
+                                          f"OpenBLAS threads={cores}; throughput in dofs/s is size-normalised"},
+               "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "factorize_time_s": tmean, **info}
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import spand_public_b200 as S
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the spaND B200 path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = measure_fp64_peak(torch, dev) if rank == 0 else None
+    A = S.neglapl(n, d)
+    N = A.shape[0]
+    X = S.linspace_nd(n, d)
+    G = S.symmetric_graph(A)
+    b = S.random(N, 2019)
+    t = S.Tree(L)
+    t.set_device(local_rank)
+    t.set_tol(tol)
+    t.set_use_geo(True)
+    t.set_Xcoo(X)
+    tp0 = time.perf_counter()
+    t.partition(G)
+    tpart = time.perf_counter() - tp0
+    h2d = A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + b.nbytes
+    d2h = b.nbytes
+
+    def step():
+        t0 = time.perf_counter()
+        t.assemble(A)
+        t1 = time.perf_counter()
+        t.factorize()
+        t2 = time.perf_counter()
+        x = t.solve(b)
+        t3 = time.perf_counter()
+        return t.factorize_seconds(), t3 - t0, t1 - t0, t3 - t2, x
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dev_times, e2e_times, tassm, tsolve = [], [], [], []
+    launches = 0
+    for _ in range(args.steps):
+        ft, et, ta, ts, x = step()
+        dev_times.append(ft)
+        e2e_times.append(et)
+        tassm.append(ta)
+        tsolve.append(ts)
+        launches += t.kernel_launches()
+    barrier()
+    clocks = sampler.stop()
+    tdev = float(np.sum(dev_times))
+    te2e = float(np.sum(e2e_times))
+    if dist is not None:
+        tt = torch.tensor([tdev, te2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tdev, te2e = float(tt[0]), float(tt[1])
+    lg = t.log()
+    res = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
+    cg_it, t_cg = None, None
+    if not args.no_cg and rank == 0:
+        cg_it, _ = t.cg(A, b, 500, 1e-12)
+        t_cg = t.t_cg
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    units = N * args.steps * world
+    value = units / tdev / 1e6
+    e2e_val = units / te2e / 1e6
+    flops = flops_of(lg)
+    pk = peaks()
+    hbm_peak = pk.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in pk else "fallback (B200_PROFILING.md)"
+    # dominant phase and its roofline (algorithmic bytes / flops per SURVEY.md 8(d), device time per phase)
+    phases = {"eliminate": lg["t_elim"].sum(), "scale": lg["t_scale"].sum(), "sparsify": lg["t_spars"].sum(),
+              "merge": lg["t_merge"].sum()}
+    dom = max(phases, key=phases.get)
+    nl = {"sparsify": lg["wavefronts"].sum(), "eliminate": 0, "scale": 0, "merge": 0}
+    if dom == "eliminate":
+        fl = float(lg["fl_schur"].sum())
+        roof = {"bound": "tensor", "kernel": "gemm_tiled_kernel/gemm_small_kernel (Schur updates, eliminate phase)",
+                "achieved": fl / phases[dom] / 1e12, "peak": fp64_peak or 40.0, "unit": "TFLOP/s",
+                "peak_source": ("cuBLAS DGEMM 8192^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)"
+                                if fp64_peak else "nominal 40 TFLOP/s (vendor)")}
+    else:
+        by = {"scale": lg["by_scale"].sum(), "sparsify": lg["by_rrqr"].sum(), "merge": lg["by_merge"].sum()}[dom]
+        kern = {"scale": "potrf_step/trsm_step (two-sided scaling)", "sparsify": "rrqr_kernel (gather + QRCP + scatter)",
+                "merge": "copy_kernel + memset"}[dom]
+        roof = {"bound": "hbm", "kernel": kern, "achieved": float(by) / phases[dom] / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "peak_source": hbm_src}
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
+    roof["traffic"] = None
+    roof["phase_seconds"] = {k: float(v) for k, v in phases.items()}
+    roof["note"] = ("achieved = algorithmic bytes of the phase (SURVEY.md 8d) / device time of the whole phase "
+                    "(CUDA events on the factorization stream, includes launch gaps and host planning stalls)")
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        scfg = CONFIGS["s64"] if args.config in ("c4", "c3") else cfg
+        Nc, times, info = run_oracle(scfg, 1, 0, 1)
+        cpu = {"value": Nc / times[0] / 1e6, "unit": unit, "cores": 1, "kind": "port",
+               "sample": f"one full factorize() of {scfg[4]} by the oracle port (OpenBLAS 1 thread, as the reference's "
+                         f"mkl_sequential build); {times[0]:.2f} s",
+               "factorize_time_s": times[0], "cg_iterations": info["cg_iterations"], "residual": info["residual"]}
+
+    out = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tdev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "N": N, "parallelism": "single GPU" if world == 1 else f"{world} replicas",
+                   "l2": "inputs (assembled blocks, ~%.1f GB) are larger than L2" % (t.arena_bytes() / 1e9),
+                   "partition": "geometric modified ND on linspace_nd coordinates (host, untimed: %.2f s)" % tpart},
+        "factorize_time_s": tdev / args.steps, "fp64_tflops": flops / (tdev / args.steps) / 1e12,
+        "gflop_per_factorization": flops / 1e9, "fp64_dgemm_peak_tflops": fp64_peak,
+        "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "seconds_per_step": te2e / args.steps, "assemble_s": float(np.mean(tassm)),
+                "solve_s": float(np.mean(tsolve))},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "residual_one_solve": res, "cg_iterations": cg_it, "cg_seconds": t_cg, "nnz_fact": int(t.nnz()),
+        "arena_gb": t.arena_bytes() / 1e9,
+        "per_level": {k: [float(v) for v in lg[k]] for k in ("t_elim", "t_scale", "t_spars", "t_merge", "t_host",
+                                                               "launches", "wavefronts", "dofs_left_spars")},
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,213 @@
+"""Pins the CPU oracle (and the shared host front end) against every known-answer / property test the
+reference holds for this path (reference tests/tests.cpp; line numbers in each test). CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle_lib as O
+import spand_public_b200 as S
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_choose_rank_golden():
+    # tests/tests.cpp:254-262
+    errs = np.array([1.0, -0.1, 0.01, -0.001, 1e-4])
+    L = O.lib()
+    assert L.orc_choose_rank(errs, 5, 1e-1) == 2
+    assert L.orc_choose_rank(errs, 5, 1e-2) == 3
+    assert L.orc_choose_rank(errs, 5, 1.0) == 0
+    assert L.orc_choose_rank(errs, 5, 0.0) == 5
+    assert L.orc_choose_rank(errs, 5, 1e-16) == 5
+
+
+def test_swap2perm_golden():
+    # tests/tests.cpp:349-357
+    swap = np.array([3, 3, 2, 5, 4, 5], dtype=np.int32)
+    perm = np.zeros(6, dtype=np.int32)
+    O.lib().orc_swap2perm(swap, 6, perm)
+    assert perm.tolist() == [3, 0, 2, 5, 4, 1]
+
+
+def test_block2dense_golden():
+    # tests/tests.cpp:264-305
+    A = sp.csc_matrix((np.array([1.0, -2.0, 3.0]), (np.array([0, 2, 1]), np.array([0, 2, 3]))), shape=(5, 5))
+    A.sort_indices()
+    out = np.zeros(9)
+    O.lib().orc_block2dense(5, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data, 1, 1, 3, 3, out, 0)
+    assert np.array_equal(out.reshape(3, 3, order="F"), np.array([[0, 0, 3], [0, -2, 0], [0, 0, 0]], dtype=float))
+    B = sp.csc_matrix((np.array([1.0, 2.0, 3.0, 4.0, 5.0]), (np.array([0, 1, 1, 2, 0]), np.array([1, 0, 2, 1, 3]))),
+                      shape=(3, 4))
+    B.sort_indices()
+    out = np.zeros(6)
+    O.lib().orc_block2dense(4, B.indptr.astype(np.int32), B.indices.astype(np.int32), B.data, 0, 0, 2, 3, out, 1)
+    assert np.array_equal(out.reshape(3, 2, order="F"), np.array([[0, 2], [1, 0], [0, 3]], dtype=float))
+
+
+def test_linspace_nd_golden():
+    # tests/tests.cpp:307-316
+    X2 = S.linspace_nd(3, 2)
+    assert np.array_equal(X2, np.array([[0, 0, 0, 1, 1, 1, 2, 2, 2], [0, 1, 2, 0, 1, 2, 0, 1, 2]], dtype=float))
+    X3 = S.linspace_nd(2, 3)
+    assert np.array_equal(X3, np.array([[0, 0, 0, 0, 1, 1, 1, 1], [0, 0, 1, 1, 0, 0, 1, 1], [0, 1, 0, 1, 0, 1, 0, 1]],
+                                       dtype=float))
+
+
+def test_partition_square_golden():
+    # tests/tests.cpp:378-412 — geometric MND of the 5x5 Laplacian with 3 levels
+    g = json.load(open(os.path.join(GOLD, "partition_square.json")))
+    A = S.neglapl(5, 2)
+    X = S.linspace_nd(5, 2)
+    for make in ("oracle", "product"):
+        if make == "oracle":
+            t = O.OracleTree(3)
+            t.set_coords(X)
+            t.partition(A)
+            ids = t.partition_ids()
+        else:
+            t = S.Tree(3)
+            t.set_use_geo(True)
+            t.set_Xcoo(X)
+            ids = t.partition(A)
+        got = {"self": list(zip(ids[0].tolist(), ids[1].tolist())), "l": list(zip(ids[2].tolist(), ids[3].tolist())),
+               "r": list(zip(ids[4].tolist(), ids[5].tolist()))}
+        for k in ("self", "l", "r"):
+            assert [list(x) for x in got[k]] == g[k], (make, k)
+
+
+def _should_be_disconnected(lvl1, lvl2, sep1, sep2):
+    # src/util.cpp:28-43
+    while lvl2 > lvl1:
+        lvl1 += 1
+        sep1 //= 2
+    while lvl1 > lvl2:
+        lvl2 += 1
+        sep2 //= 2
+    return sep1 != sep2
+
+
+@pytest.mark.parametrize("n,d", [(5, 2), (20, 2), (5, 3), (15, 3)])
+@pytest.mark.parametrize("geo", [True, False])
+def test_partition_consistency(n, d, geo):
+    # tests/tests.cpp:417-481 (MND rows; RB/LoRaSp are out of scope)
+    A = S.neglapl(n, d)
+    X = S.linspace_nd(n, d)
+    Ac = A.tocoo()
+    for nlevels in range(1, 8):
+        t = S.Tree(nlevels)
+        if geo:
+            t.set_use_geo(True)
+            t.set_Xcoo(X)
+        sl, ss, ll, ls, rl, rs = t.partition(A)
+        assert len(sl) == n**d
+        for i, j in zip(Ac.row, Ac.col):
+            assert not _should_be_disconnected(sl[i], sl[j], ss[i], ss[j])
+        for i in range(n**d):
+            if sl[i] == 0:
+                assert (ll[i], ls[i]) == (sl[i], ss[i]) and (rl[i], rs[i]) == (sl[i], ss[i])
+            else:
+                assert sl[i] > ll[i] and sl[i] > rl[i]
+                a, b = ll[i], ls[i]
+                while a < sl[i] - 1:
+                    a, b = a + 1, b // 2
+                c, e = rl[i], rs[i]
+                while c < sl[i] - 1:
+                    c, e = c + 1, e // 2
+                assert b == 2 * ss[i] and e == 2 * ss[i] + 1
+        p = t.get_assembly_perm()
+        assert sorted(p.tolist()) == list(range(n**d))
+
+
+def _unsym(A, seed):
+    rng = np.random.RandomState(seed)
+    B = A.copy().tocsc()
+    B.data = B.data + rng.uniform(-0.1, 0.1, B.nnz)
+    return B
+
+
+@pytest.mark.parametrize("n,d", [(5, 2), (10, 2), (20, 2), (5, 3), (10, 3)])
+def test_assembly_consistency(n, d):
+    # tests/tests.cpp:488-547 : P^T A P == get_trailing_mat(), SPD and GEN, algebraic MND
+    A = S.neglapl(n, d)
+    for nlevels in range(2, 5):
+        for kind, M in ((O.SPD, A), (O.GEN, _unsym(A, n))):
+            t = O.OracleTree(nlevels, symm_kind=kind, scaling_kind=O.LLT if kind == O.SPD else O.PLU)
+            t.partition(A)
+            t.assemble(M)
+            p = t.perm()
+            ref = M.tocsc()[p, :][:, p]
+            assert abs(ref - t.trailing_mat()).max() == 0.0
+
+
+@pytest.mark.parametrize("n,d", [(5, 2), (10, 2), (20, 2), (5, 3), (15, 3)])
+def test_exact_residual(n, d):
+    # tests/tests.cpp:562-609 : tol in {1e-14, 1e-14, 0} x skip in {0, 4, 1000}: one solve gives <= 1e-10
+    A = S.neglapl(n, d)
+    N = A.shape[0]
+    lmin = 1 if N < 1000 else 8
+    for nlevels in range(lmin, lmin + 5):
+        for kind, sk, M in ((O.SPD, O.LLT, A), (O.GEN, O.PLU, _unsym(A, d))):
+            for tol, skip in ((1e-14, 0), (1e-14, 4), (0.0, 1000)):
+                t = O.OracleTree(nlevels, tol=tol, skip=skip, symm_kind=kind, scaling_kind=sk)
+                t.partition(S.symmetric_graph(M))
+                t.assemble(M)
+                t.factorize()
+                b = S.random(N, nlevels + 2019)
+                x = t.solve(b)
+                assert np.linalg.norm(M @ x - b) / np.linalg.norm(b) <= 1e-10
+
+
+@pytest.mark.parametrize("n,d", [(5, 2), (10, 2), (20, 2), (5, 3), (15, 3)])
+def test_approx_residual(n, d):
+    # tests/tests.cpp:799-856 : err <= 5e-12 (tol = 0) else err <= 200 tol
+    A = S.neglapl(n, d)
+    N = A.shape[0]
+    for nlevels in range(1, 6):
+        for skip in range(0, 3):
+            for tol in (0.0, 1e-10, 1e-6, 1e-2, 10.0):
+                t = O.OracleTree(nlevels, tol=tol, skip=skip)
+                t.partition(A)
+                t.assemble(A)
+                t.factorize()
+                b = S.random(N, 2019)
+                x = t.solve(b)
+                err = np.linalg.norm(A @ x - b) / np.linalg.norm(b)
+                assert err <= (5e-12 if tol == 0.0 else tol * 2e2), (nlevels, skip, tol, err)
+
+
+def test_oracle_repro():
+    # tests/tests.cpp:917-994 : repeated factorizations give bit-identical x
+    A = S.neglapl(16, 2)
+    b = S.random(256, 2019)
+    ref = None
+    for _ in range(4):
+        t = O.OracleTree(4, tol=1e-2)
+        t.partition(A)
+        t.assemble(A)
+        t.factorize()
+        x = t.solve(b)
+        if ref is None:
+            ref = x
+        assert np.array_equal(ref, x)
+
+
+def test_readme_run_shape():
+    # README.md:112-230 (indicative only: algebraic METIS of another version): C1 with the shipped coordinates
+    g = json.load(open(os.path.join(GOLD, "c1_oracle.json")))
+    A = S.neglapl(32, 2)
+    X = np.array(g["coords_first8"])
+    assert X.shape == (2, 8)
+    t = O.OracleTree(5, tol=1e-2)
+    t.set_coords(S.linspace_nd(32, 2)[::-1] + 1.0)  # mats/32x32.mm: 1-based tensor coordinates, x fastest
+    t.partition(S.symmetric_graph(A))
+    t.assemble(A)
+    t.factorize()
+    lg = t.log()
+    assert lg["dofs_left_elim"].astype(int).tolist() == g["dofs_left_elim"]
+    assert lg["dofs_left_spars"].astype(int).tolist() == g["dofs_left_spars"]
+    assert t.nnz() == g["nnz"]
+    it, _ = t.cg(A, S.random(1024, 2019), 100, 1e-12)
+    assert it == g["cg"]
