@@ -236,11 +236,6 @@ __global__ void __launch_bounds__(128) gemm_small_kernel(const GemmTask* __restr
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Rank-revealing QR with column pivoting, one CTA per cluster (truncated at the first sub-tolerance
-// pivot, which is exactly geqp3 + choose_rank). Gathers [A_s,n ... (A_n,s)^T ...], factors, scatters
-// R P^T back into the edge blocks in place, stores V/tau, and publishes the rank in csize[].
-// ------------------------------------------------------------------------------------------------
 template <int NT>
 __device__ __forceinline__ double block_sum(double v, double* red) {
     v = warp_sum(v);
@@ -252,278 +247,6 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 #pragma unroll
     for (int w = 0; w < NT / 32; w++) s += red[w];
     return s;
-}
-
-template <int NT, int SMEM_ELEMS>
-__global__ void __launch_bounds__(NT) rrqr_kernel(const QrTask* __restrict__ tasks, const QrSrc* __restrict__ srcs,
-                                                  int* csize, double tol) {
-    QrTask t = tasks[blockIdx.x];
-    const QrSrc* src = srcs + t.src0;
-    int rows = t.rows;
-    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NT / 32;
-    __shared__ double red[NW];
-    __shared__ int redi[NW];
-    __shared__ double sWs[SMEM_ELEMS > 0 ? SMEM_ELEMS : 1];
-    __shared__ int s_int[4];
-
-    // total columns from the neighbours' current sizes
-    int cols = 0;
-    for (int s = 0; s < t.nsrc; s++) cols += csize[src[s].nbr];
-    if (rows == 0) return;
-    int mn = min(rows, cols);
-    if (tol >= 1.0) {  // choose_rank: tol >= 1 -> 0
-        if (tid == 0) csize[t.cluster] = 0;
-        return;
-    }
-    if (cols == 0) {  // rank 0 < rows: cluster vanishes, no reflectors
-        if (tid == 0) csize[t.cluster] = 0;
-        return;
-    }
-    double* W = (SMEM_ELEMS > 0 && rows * cols <= SMEM_ELEMS) ? sWs : t.W;
-    double* vn1 = t.W + (size_t)rows * t.maxcols;
-    double* vn2 = vn1 + t.maxcols;
-    int* jpvt = t.ipiv;
-    int* ipvt = t.ipiv + t.maxcols;
-    const int ldw = rows;
-
-    // ---- gather ----
-    {
-        int c0 = 0;
-        for (int s = 0; s < t.nsrc; s++) {
-            QrSrc q = src[s];
-            int w = csize[q.nbr];
-            int tot = rows * w;
-            if (!q.transposed) {
-                for (int e = tid; e < tot; e += NT) {
-                    int i = e % rows, j = e / rows;
-                    W[i + (size_t)(c0 + j) * ldw] = q.blk[i + (size_t)j * q.ld];
-                }
-            } else {
-                for (int e = tid; e < tot; e += NT) {
-                    int j = e % w, i = e / w;  // block is w x rows, read along its columns
-                    W[i + (size_t)(c0 + j) * ldw] = q.blk[j + (size_t)i * q.ld];
-                }
-            }
-            c0 += w;
-        }
-    }
-    __syncthreads();
-    // ---- initial column norms ----
-    const bool thread_cols = rows <= 16;
-    if (thread_cols) {
-        for (int j = tid; j < cols; j += NT) {
-            double s = 0.0;
-            for (int i = 0; i < rows; i++) {
-                double v = W[i + (size_t)j * ldw];
-                s += v * v;
-            }
-            s = sqrt(s);
-            vn1[j] = s;
-            vn2[j] = s;
-            jpvt[j] = j;
-        }
-    } else {
-        for (int j = warp; j < cols; j += NW) {
-            double s = 0.0;
-            for (int i = lane; i < rows; i += 32) {
-                double v = W[i + (size_t)j * ldw];
-                s += v * v;
-            }
-            s = sqrt(warp_sum(s));
-            if (lane == 0) {
-                vn1[j] = s;
-                vn2[j] = s;
-                jpvt[j] = j;
-            }
-        }
-    }
-    __syncthreads();
-
-    const double tol3z = sqrt(DBL_EPSILON);
-    int rank = mn;
-    double r00 = 0.0;
-    for (int k = 0; k < mn; k++) {
-        // ---- pivot: first index of the max partial norm in [k, cols) ----
-        double best = -1.0;
-        int bi = k;
-        for (int j = k + tid; j < cols; j += NT) {
-            double v = vn1[j];
-            if (v > best) {
-                best = v;
-                bi = j;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) {
-                best = ob;
-                bi = oi;
-            }
-        }
-        if (lane == 0) {
-            red[warp] = best;
-            redi[warp] = bi;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double bb = red[0];
-            int ii = redi[0];
-            for (int w = 1; w < NW; w++)
-                if (red[w] > bb || (red[w] == bb && redi[w] < ii)) {
-                    bb = red[w];
-                    ii = redi[w];
-                }
-            s_int[0] = ii;
-        }
-        __syncthreads();
-        int pvt = s_int[0];
-        if (pvt != k) {
-            for (int i = tid; i < rows; i += NT) {
-                double a = W[i + (size_t)k * ldw];
-                W[i + (size_t)k * ldw] = W[i + (size_t)pvt * ldw];
-                W[i + (size_t)pvt * ldw] = a;
-            }
-            if (tid == 0) {
-                int jt = jpvt[k];
-                jpvt[k] = jpvt[pvt];
-                jpvt[pvt] = jt;
-                vn1[pvt] = vn1[k];
-                vn2[pvt] = vn2[k];
-            }
-        }
-        __syncthreads();
-        // ---- Householder reflector for W[k:rows, k] (dlarfg) ----
-        double ss = 0.0;
-        for (int i = k + 1 + tid; i < rows; i += NT) {
-            double v = W[i + (size_t)k * ldw];
-            ss += v * v;
-        }
-        ss = block_sum<NT>(ss, red);
-        double alpha = W[k + (size_t)k * ldw];
-        double xnorm = sqrt(ss);
-        double beta, tau, scal;
-        if (xnorm == 0.0) {
-            beta = alpha;
-            tau = 0.0;
-            scal = 0.0;
-        } else {
-            beta = -copysign(hypot(alpha, xnorm), alpha);
-            tau = (beta - alpha) / beta;
-            scal = 1.0 / (alpha - beta);
-        }
-        if (k == 0) {
-            r00 = fabs(beta);
-        } else if (tol != 0.0 && !(fabs(beta) / r00 >= tol)) {
-            rank = k;
-            break;
-        }
-        __syncthreads();
-        for (int i = k + 1 + tid; i < rows; i += NT) W[i + (size_t)k * ldw] *= scal;
-        if (tid == 0) {
-            W[k + (size_t)k * ldw] = beta;
-            t.tau[k] = tau;
-        }
-        __syncthreads();
-        // ---- apply H to the trailing columns and downdate their partial norms (dlaqp2) ----
-        const double* v = W + (size_t)k * ldw;
-        if (thread_cols) {
-            for (int j = k + 1 + tid; j < cols; j += NT) {
-                double* cj = W + (size_t)j * ldw;
-                double w = cj[k];
-                for (int i = k + 1; i < rows; i++) w += v[i] * cj[i];
-                w *= tau;
-                cj[k] -= w;
-                for (int i = k + 1; i < rows; i++) cj[i] -= w * v[i];
-                double n1 = vn1[j];
-                if (n1 != 0.0) {
-                    double tmp = fabs(cj[k]) / n1;
-                    tmp = fmax(0.0, 1.0 - tmp * tmp);
-                    double r = n1 / vn2[j];
-                    double tmp2 = tmp * r * r;
-                    if (tmp2 <= tol3z) {
-                        double s = 0.0;
-                        for (int i = k + 1; i < rows; i++) s += cj[i] * cj[i];
-                        s = sqrt(s);
-                        vn1[j] = s;
-                        vn2[j] = s;
-                    } else {
-                        vn1[j] = n1 * sqrt(tmp);
-                    }
-                }
-            }
-        } else {
-            for (int j = k + 1 + warp; j < cols; j += NW) {
-                double* cj = W + (size_t)j * ldw;
-                double w = 0.0;
-                for (int i = k + 1 + lane; i < rows; i += 32) w += v[i] * cj[i];
-                w = warp_sum(w);
-                double ckj = cj[k];
-                w = (w + ckj) * tau;
-                for (int i = k + 1 + lane; i < rows; i += 32) cj[i] -= w * v[i];
-                double newk = ckj - w;
-                double n1 = vn1[j];
-                bool recompute = false;
-                double newn = 0.0;
-                if (n1 != 0.0) {
-                    double tmp = fabs(newk) / n1;
-                    tmp = fmax(0.0, 1.0 - tmp * tmp);
-                    double r = n1 / vn2[j];
-                    double tmp2 = tmp * r * r;
-                    if (tmp2 <= tol3z) recompute = true;
-                    else newn = n1 * sqrt(tmp);
-                }
-                if (recompute) {
-                    __syncwarp();
-                    double s = 0.0;
-                    for (int i = k + 1 + lane; i < rows; i += 32) s += cj[i] * cj[i];
-                    s = sqrt(warp_sum(s));
-                    if (lane == 0) {
-                        vn1[j] = s;
-                        vn2[j] = s;
-                    }
-                } else if (lane == 0 && n1 != 0.0) {
-                    vn1[j] = newn;
-                }
-                if (lane == 0) cj[k] = newk;
-            }
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    if (rank >= rows) return;  // nothing to do (tree.cpp:1317-1319); csize unchanged
-
-    // ---- V, inverse pivots ----
-    for (int e = tid; e < rows * rank; e += NT) t.V[e] = W[e];
-    for (int j = tid; j < cols; j += NT) ipvt[jpvt[j]] = j;
-    __syncthreads();
-    // ---- scatter R[:rank,:] P^T back into the blocks, in place ----
-    {
-        int c0 = 0;
-        for (int s = 0; s < t.nsrc; s++) {
-            QrSrc q = src[s];
-            int w = csize[q.nbr];
-            int tot = rank * w;
-            if (!q.transposed) {
-                for (int e = tid; e < tot; e += NT) {
-                    int i = e % rank, c = e / rank;
-                    int j = ipvt[c0 + c];
-                    q.blk[i + (size_t)c * q.ld] = (i <= j) ? W[i + (size_t)j * ldw] : 0.0;
-                }
-            } else {
-                for (int e = tid; e < tot; e += NT) {
-                    int c = e % w, i = e / w;
-                    int j = ipvt[c0 + c];
-                    q.blk[c + (size_t)i * q.ld] = (i <= j) ? W[i + (size_t)j * ldw] : 0.0;
-                }
-            }
-            c0 += w;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) csize[t.cluster] = rank;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -770,10 +493,6 @@ void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const in
 
 void launch_gemm_small(const GemmTask* t, int nt, const GemmContrib* c, cudaStream_t st) {
     if (nt > 0) gemm_small_kernel<<<(nt + 3) / 4, 128, 0, st>>>(t, nt, c);
-}
-
-void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, cudaStream_t st) {
-    if (nt > 0) rrqr_kernel<256, 0><<<nt, 256, 0, st>>>(t, s, csize, tol);
 }
 
 void launch_copy(const CopyTask* t, int nt, cudaStream_t st) {

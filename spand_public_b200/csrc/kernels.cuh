@@ -64,11 +64,11 @@ struct QrTask {
     int cluster;
     int rows;     // current size of the cluster (it has not been sparsified before)
     int src0, nsrc;
-    double* W;    // scratch: rows x maxcols (+ norms)
+    double* W;    // scratch: rows x maxcols panel (used when a column slab does not fit in shared memory) + 2 * maxcols norms
     int maxcols;
     double* V;    // out: rows x rank Householder vectors (unit diagonal implicit), ld = rows
     double* tau;  // out: rank
-    int* ipiv;    // scratch: 2 * maxcols
+    int* ipiv;    // scratch: 2 * maxcols (virtual positions, jpvt)
 };
 
 struct CopyTask {
@@ -115,7 +115,11 @@ void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const in
                        cudaStream_t st);
 void launch_gemm_small(const GemmTask* t, int nt, const GemmContrib* c, cudaStream_t st);
 // csize: device array of current cluster sizes (read for neighbours, written with the rank)
-void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, cudaStream_t st);
+// One thread-block cluster of G CTAs (1,2,4,8,16) per task; nthreads 128 (G must be 1) or 512; smem = dynamic shared
+// memory per CTA: >= 8*rows, and >= 8*(rows*ceil(cols/G)+rows) keeps the panel resident in (distributed) shared memory.
+void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int nthreads, int smem,
+                 cudaStream_t st);
+int rrqr_max_smem();
 void launch_copy(const CopyTask* t, int nt, cudaStream_t st);
 void launch_trsv(const TrsvTask* t, int nt, int trans, cudaStream_t st);
 void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, cudaStream_t st);

@@ -687,22 +687,57 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             tasks.push_back(t);
             task_color.push_back(col);
         }
-        // order tasks by colour (stable), launch one batch per colour
+        // Launch classes: cluster size G and shared-memory bucket, chosen so that the panel stays resident in
+        // (distributed) shared memory whenever it fits in 16 CTAs.
+        const int MAXS = rrqr_max_smem();
+        auto need = [](const QrTask& t, int G) {
+            long cpc = (t.maxcols + G - 1) / G;
+            return ((long)t.rows * cpc + t.rows) * (long)sizeof(double);
+        };
+        std::vector<int> klass(tasks.size());   // (G index << 4) | bucket ; tiny class = 0
+        std::vector<int> smem_need(tasks.size());
+        for (size_t i = 0; i < tasks.size(); i++) {
+            const QrTask& t = tasks[i];
+            if (need(t, 1) <= 20 * 1024) {
+                klass[i] = 0;
+                smem_need[i] = (int)need(t, 1);
+                continue;
+            }
+            int gi = 0, G = 1;
+            while (G < 16 && need(t, G) > MAXS) {
+                G *= 2;
+                gi++;
+            }
+            long nd = need(t, G);
+            if (nd > MAXS) nd = (long)t.rows * sizeof(double);  // panel stays in L2-resident scratch
+            int bucket = nd <= 48 * 1024 ? 1 : (nd <= 100 * 1024 ? 2 : 3);
+            klass[i] = ((gi + 1) << 4) | bucket;
+            smem_need[i] = (int)nd;
+        }
+        // order tasks by (colour, class), stable
         std::vector<int> idx(tasks.size());
         for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
-        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return task_color[a] < task_color[b]; });
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+            if (task_color[a] != task_color[b]) return task_color[a] < task_color[b];
+            return klass[a] < klass[b];
+        });
         std::vector<QrTask> sorted(tasks.size());
-        std::vector<int> cbegin(ncolors + 1, 0);
-        for (size_t i = 0; i < idx.size(); i++) {
-            sorted[i] = tasks[idx[i]];
-            cbegin[task_color[idx[i]] + 1]++;
-        }
-        for (int c = 0; c < ncolors; c++) cbegin[c + 1] += cbegin[c];
+        for (size_t i = 0; i < idx.size(); i++) sorted[i] = tasks[idx[i]];
         QrTask* dt = to_device(sorted, scratch_);
         QrSrc* ds = to_device(srcs, scratch_);
-        for (int c = 0; c < ncolors; c++) {
-            launch_rrqr(dt + cbegin[c], cbegin[c + 1] - cbegin[c], ds, d_csize_, tol, st_);
+        for (size_t b = 0; b < idx.size();) {
+            size_t e = b;
+            int smem = 0;
+            while (e < idx.size() && task_color[idx[e]] == task_color[idx[b]] && klass[idx[e]] == klass[idx[b]]) {
+                smem = std::max(smem, smem_need[idx[e]]);
+                e++;
+            }
+            int k = klass[idx[b]];
+            int G = (k == 0) ? 1 : (1 << ((k >> 4) - 1));
+            smem = (smem + 1023) & ~1023;
+            launch_rrqr(dt + b, (int)(e - b), ds, d_csize_, tol, G, k == 0 ? 128 : 512, smem, st_);
             lg.launches++;
+            b = e;
         }
         lg.wavefronts = ncolors;
         // ranks back to the host: the one synchronisation of the level
