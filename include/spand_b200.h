@@ -86,6 +86,14 @@ double spand_factorize_seconds(spand_tree* t);
 long long spand_kernel_launches(spand_tree* t);
 long long spand_arena_bytes(spand_tree* t);
 
+/* Per-kernel-family device time of the last factorize(): CUDA events recorded around every launch of the
+ * family on the factorization stream (the role of the reference's per-routine Profile counters potf/trsm/
+ * gemm/geqp3/merge_copy, include/util.h:262-309). Enable with spand_set_profile(t, 1) before factorize(). */
+int spand_set_profile(spand_tree* t, int on);
+int spand_num_families(void);
+const char* spand_family_name(int f);
+int spand_get_family_stats(spand_tree* t, double* ms, long long* launches);
+
 /* Tree::get_trailing_mat                            include/tree.h:153, src/tree.cpp:1730-1763
  * permuted ordering, CSC; call with null pointers to get nnz first */
 int spand_trailing(spand_tree* t, int* colptr, int* rowind, double* val);

@@ -30,7 +30,7 @@ EXPORTS = [
     "spand_get_nlevels", "spand_num_clusters", "spand_get_stats", "spand_log_fields", "spand_log_field_name",
     "spand_get_log", "spand_factorize_seconds", "spand_kernel_launches", "spand_arena_bytes", "spand_trailing",
     "spand_util_random", "spand_util_linspace_nd", "spand_util_neglapl", "spand_util_aniso", "spand_util_mm_read",
-    "spand_util_mm_read_dense",
+    "spand_util_mm_read_dense", "spand_set_profile", "spand_num_families", "spand_family_name", "spand_get_family_stats",
 ]
 
 
@@ -87,6 +87,11 @@ def lib():
     L.spand_arena_bytes.restype = C.c_longlong
     L.spand_arena_bytes.argtypes = [_p]
     L.spand_trailing.argtypes = [_p, _p, _p, _p]
+    L.spand_set_profile.argtypes = [_p, _i]
+    L.spand_num_families.argtypes = []
+    L.spand_family_name.restype = C.c_char_p
+    L.spand_family_name.argtypes = [_i]
+    L.spand_get_family_stats.argtypes = [_p, _dp, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
     L.spand_util_random.argtypes = [_i, _i, _dp]
     L.spand_util_linspace_nd.argtypes = [_i, _i, _dp]
     L.spand_util_neglapl.argtypes = [_i, _i, _p, _p, _p]
@@ -256,6 +261,16 @@ class Tree:
     def factorize_seconds(self): return self._l.spand_factorize_seconds(self._h)
     def kernel_launches(self): return self._l.spand_kernel_launches(self._h)
     def arena_bytes(self): return self._l.spand_arena_bytes(self._h)
+
+    def set_profile(self, on): self._l.spand_set_profile(self._h, int(on))
+
+    def family_stats(self):
+        """{family: (device ms, launches)} of the last factorize(); ms is 0 unless set_profile(True)."""
+        nf = self._l.spand_num_families()
+        ms = np.zeros(nf)
+        ln = np.zeros(nf, dtype=np.int64)
+        self._l.spand_get_family_stats(self._h, ms, ln)
+        return {self._l.spand_family_name(i).decode(): (float(ms[i]), int(ln[i])) for i in range(nf)}
 
     def stats(self):
         n = self._l.spand_num_clusters(self._h)

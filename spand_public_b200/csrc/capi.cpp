@@ -54,6 +54,16 @@ int spand_set_use_geo(spand_tree* t, int geo) { t->t.use_geo = geo != 0; return 
 int spand_set_verb(spand_tree* t, int verb) { t->t.verb = verb != 0; return 0; }
 int spand_set_use_sparsify(spand_tree* t, int use) { t->t.use_want_sparsify = use != 0; return 0; }
 int spand_set_device(spand_tree* t, int device) { t->t.device = device; return 0; }
+int spand_set_profile(spand_tree* t, int on) { t->t.profile_families = on != 0; return 0; }
+int spand_num_families(void) { return Tree::F_COUNT; }
+const char* spand_family_name(int f) { return Tree::family_name(f); }
+int spand_get_family_stats(spand_tree* t, double* ms, long long* launches) {
+    for (int f = 0; f < Tree::F_COUNT; f++) {
+        ms[f] = t->t.family_ms[f];
+        launches[f] = t->t.family_launches[f];
+    }
+    return 0;
+}
 int spand_set_stop(spand_tree* t, int level, int phase) {
     t->t.stop_level = level;
     t->t.stop_phase = phase;

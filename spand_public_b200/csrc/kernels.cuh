@@ -60,15 +60,21 @@ struct QrSrc {
     int transposed;  // 0: in-edge  A[s,n] (rows x w);  1: out-edge A[n,s] (w x rows)
 };
 
+constexpr int QR_NB = 16;   // block size of the blocked QRCP (dlaqps-like)
+constexpr int QR_FLD = 17;  // row stride of the F block in shared memory (odd: conflict-free)
+
 struct QrTask {
     int cluster;
     int rows;     // current size of the cluster (it has not been sparsified before)
     int src0, nsrc;
-    double* W;    // scratch: rows x maxcols panel (used when a column slab does not fit in shared memory) + 2 * maxcols norms
-    int maxcols;
+    double* W;    // scratch panel ld x maxcols in global memory (L2-resident), only when !in_smem
+    int maxcols;  // upper bound of the gathered column count (sizes used for the launch layout)
     double* V;    // out: rows x rank Householder vectors (unit diagonal implicit), ld = rows
     double* tau;  // out: rank
-    int* ipiv;    // scratch: 2 * maxcols (virtual positions, jpvt)
+    int ld;       // leading dimension of the panel (shared or global)
+    int L;        // lanes per column (power of two <= 32)
+    int nb;       // block size <= QR_NB
+    int in_smem;  // panel resident in (distributed) shared memory
 };
 
 struct CopyTask {
@@ -115,11 +121,13 @@ void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const in
                        cudaStream_t st);
 void launch_gemm_small(const GemmTask* t, int nt, const GemmContrib* c, cudaStream_t st);
 // csize: device array of current cluster sizes (read for neighbours, written with the rank)
-// One thread-block cluster of G CTAs (1,2,4,8,16) per task; nthreads 128 (G must be 1) or 512; smem = dynamic shared
-// memory per CTA: >= 8*rows, and >= 8*(rows*ceil(cols/G)+rows) keeps the panel resident in (distributed) shared memory.
-void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int nthreads, int smem,
-                 cudaStream_t st);
+// One thread-block cluster of G CTAs per task. Launch shapes: (128 threads, G = 1, panel in shared memory),
+// (256 threads, G = 1..16, panel in distributed shared memory), (512 threads, G = 8, panel in global scratch).
+// smem = dynamic shared memory per CTA >= rrqr_smem_bytes(...) of every task of the launch.
+void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int nthreads, bool in_smem,
+                 int smem, cudaStream_t st);
 int rrqr_max_smem();
+size_t rrqr_smem_bytes(int rows, int maxcols, int G, int nb, int ld, bool in_smem);
 void launch_copy(const CopyTask* t, int nt, cudaStream_t st);
 void launch_trsv(const TrsvTask* t, int nt, int trans, cudaStream_t st);
 void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, cudaStream_t st);

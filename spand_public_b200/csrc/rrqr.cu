@@ -5,14 +5,24 @@
 // choose_rank src/util.cpp:434-452 -> triu(R[:rank,:]) P^T src/tree.cpp:1334-1335 -> scatter
 // src/tree.cpp:1004-1046, plus the (V, tau) of the Orthogonal op src/tree.cpp:1322-1331.
 //
-// Mapping to the machine: one *thread-block cluster* of G CTAs (G = 1,2,4,8,16) per matrix. The gathered
-// panel W = [A_s,n ... (A_n,s)^T ...] (rows x cols, cols >> rows) is distributed by column slabs over the
-// CTAs and stays resident in shared memory (up to ~3.4 MB per cluster over distributed shared memory); only
-// when a slab does not fit is it kept in the L2-resident scratch. Per Householder step the CTAs exchange
-// one pivot candidate each and the pivot owner broadcasts the reflector through DSMEM; two cluster barriers
-// per step. Columns are never physically swapped: LAPACK's swap sequence is tracked as virtual positions so
-// that idamax's first-index tie-breaking (dlaqp2) is reproduced exactly. The factorization stops at the
-// first pivot with |R_kk| / |R_00| < tol, which is exactly geqp3 followed by choose_rank.
+// Mapping to the machine: one team per matrix, a team being a thread-block cluster of G CTAs (G = 1..16). The
+// gathered panel W = [A_s,n ... (A_n,s)^T ...] (rows x cols, cols >> rows) is distributed by column slabs over
+// the CTAs and stays resident in (distributed) shared memory; panels that do not fit stay in the L2-resident
+// scratch arena. The factorization is *blocked* like LAPACK's dlaqps: inside a block of nb <= 16 steps the
+// panel is not updated; each step reads the slab once (F(:,j) = tau W^T v), fixes F with the small V^T v
+// correction, updates only row k of the panel (that is what the partial-norm downdate needs) and the trailing
+// rows receive one rank-nb update W -= V F^T per block.
+//
+// One cluster barrier per Householder step: every CTA *speculatively* builds the reflector of its own best
+// pivot candidate and writes it, with the candidate record, into a slot of every CTA of the cluster (DSMEM);
+// after the barrier all CTAs select the same winner and find its reflector already in local shared memory.
+//
+// Columns are never physically swapped: LAPACK's swap sequence is tracked as virtual positions (pos[c]) so that
+// idamax's first-index tie-breaking (dlaqp2/dlaqps) is reproduced exactly. Partial column norms are carried
+// squared: the dlaqps downdate vn1 <- vn1 sqrt(max(0, 1 - (|a|/vn1)^2)) becomes n1 <- max(0, n1 - a^2) and its
+// safeguard tmp2 <= sqrt(eps) becomes n1_new <= sqrt(eps) n2; a flagged column gets its exact norm at once
+// (column minus its pending block update) instead of closing the block. The factorization stops at the first
+// pivot with |R_kk| / |R_00| < tol, which is exactly geqp3 followed by choose_rank.
 #include <cooperative_groups.h>
 
 #include <cfloat>
@@ -26,15 +36,16 @@ namespace spand {
 
 namespace {
 
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double group_sum(double v, int L) {
+    for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
 
 template <int NT>
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
-    v = warp_sum_d(v);
+    v = group_sum(v, 32);
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __syncthreads();
     if (lane == 0) red[warp] = v;
@@ -45,30 +56,50 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return s;
 }
 
-struct Cand {
+struct Cand {  // local pivot candidate
     double val;
     int pos, col;
 };
 
+struct CandRec {  // what a CTA tells the cluster about its candidate for the next step
+    double val;   // squared partial norm, < 0: none
+    double beta, tau;
+    int pos, col;
+    int stop, pad;
+};
+
 __device__ __forceinline__ bool better(double v, int p, double bv, int bp) { return v > bv || (v == bv && p < bp); }
 
-template <int G, int NT>
-__global__ void __launch_bounds__(NT) rrqr_cluster_kernel(const QrTask* __restrict__ tasks,
-                                                          const QrSrc* __restrict__ srcs, int* csize, double tol,
-                                                          int smem_bytes) {
+__device__ __forceinline__ Cand warp_best(Cand b, int width) {
+    for (int o = width >> 1; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(FULL, b.val, o);
+        int op = __shfl_xor_sync(FULL, b.pos, o);
+        int oc = __shfl_xor_sync(FULL, b.col, o);
+        if (better(ov, op, b.val, b.pos)) b = Cand{ov, op, oc};
+    }
+    return b;
+}
+
+__host__ __device__ constexpr int ceil_pow2(int x) { int p = 1; while (p < x) p *= 2; return p; }
+
+template <int G, int NT, bool SMEM_PANEL>
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrqr_blocked_kernel(const QrTask* __restrict__ tasks,
+                                                          const QrSrc* __restrict__ srcs, int* csize, double tol) {
     constexpr int NW = NT / 32;
+    constexpr int NC = SMEM_PANEL ? 2 : 4;  // columns a lane group works on at once (shares the v loads / MLP)
     const int task_id = blockIdx.x / G;
     const int crank = blockIdx.x % G;
-    QrTask t = tasks[task_id];
+    const QrTask t = tasks[task_id];
     const QrSrc* src = srcs + t.src0;
     const int rows = t.rows;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    __shared__ double red[NW];
-    __shared__ Cand redc[NW];
-    __shared__ Cand cand[16];
-    __shared__ double ctrl[4];
-    extern __shared__ double dsm[];
+    __shared__ double red[2][NW];
+    __shared__ double alpha_s[2];
+    __shared__ Cand redc[2][NW];
+    __shared__ CandRec rec[2][G];
+    __shared__ double aux[QR_NB];
+    extern __shared__ __align__(16) double dsm[];
 
     int cols = 0;
     for (int s = 0; s < t.nsrc; s++) cols += csize[src[s].nbr];
@@ -80,21 +111,103 @@ __global__ void __launch_bounds__(NT) rrqr_cluster_kernel(const QrTask* __restri
     }
     const int mn = min(rows, cols);
     const int cpc = (cols + G - 1) / G;
+    const int cpcm = (t.maxcols + G - 1) / G;  // layout bound used by the host when sizing shared memory
+    const int cpce = (cpcm + 3) & ~3;
     const int c_lo = min(cols, crank * cpc), c_hi = min(cols, c_lo + cpc);
-    const bool in_smem = ((size_t)rows * cpc + rows) * sizeof(double) <= (size_t)smem_bytes;
-    double* Wl = in_smem ? dsm + rows : t.W + (size_t)c_lo * rows;  // local slab, column c at Wl[(c - c_lo) * rows]
-    double* vbuf = dsm;                                             // rows doubles, always in shared memory
-    double* vn1 = t.W + (size_t)rows * t.maxcols;
-    double* vn2 = vn1 + t.maxcols;
-    int* pos = t.ipiv;                 // current (virtual) position of original column c
-    int* colAt = t.ipiv + t.maxcols;   // original column at position p  (== LAPACK's jpvt)
+    const int ncl = c_hi - c_lo;
+    const int ld = t.ld, ldv = (rows + 1) & ~1, L = t.L, FLD = t.nb | 1;
+    const int ngroups = NT / L, grp = tid / L, lig = tid & (L - 1);
+    const int npair = ldv >> 1;
+
+    double* Vs = dsm;                                        // ldv x nb   reflectors of the current block
+    double* Fs = Vs + (size_t)ldv * t.nb;                    // cpcm x FLD
+    double* nq1 = Fs + (((size_t)cpcm * FLD + 1) & ~(size_t)1);  // squared partial norms
+    double* nq2 = nq1 + cpce;                                // squared norms at the last exact computation
+    double* slots = nq2 + cpce;                              // 2 x ldv: own candidate reflectors (double buffered)
+    int* pos = (int*)(slots + (size_t)2 * ldv);              // virtual position of every local column
+    double* slab = (double*)(pos + cpce);
+    double* P;                                               // local slab, column cl at P[cl * ld]
+    if constexpr (SMEM_PANEL) P = slab;
+    else P = t.W + (size_t)c_lo * ld;
+
     cg::cluster_group cluster = cg::this_cluster();
     auto csync = [&]() {
-        if (G > 1) cluster.sync();
+        if constexpr (G > 1) cluster.sync();
         else __syncthreads();
     };
+    const double tol3z = sqrt(DBL_EPSILON);
+    double r00 = 0.0;
 
-    // ---- gather the own column range [c_lo, c_hi) ----
+    // Block-wide best of the per-thread candidates (one block barrier); every thread returns the same result.
+    auto block_best = [&](Cand b, int par) {
+        b = warp_best(b, 32);
+        if (lane == 0) redc[par][warp] = b;
+        __syncthreads();
+        Cand bb = (lane < NW) ? redc[par][lane] : Cand{-1.0, INT_MAX, -1};
+        bb = warp_best(bb, ceil_pow2(NW));
+        bb.val = __shfl_sync(FULL, bb.val, 0);
+        bb.pos = __shfl_sync(FULL, bb.pos, 0);
+        bb.col = __shfl_sync(FULL, bb.col, 0);
+        return bb;
+    };
+    // Speculative reflector of the local candidate `lb` for step kn (index jn inside the current block): the vector
+    // stays in the own slot [kn & 1] (siblings pull it through DSMEM if it wins), its record goes to every CTA.
+    auto propose = [&](Cand lb, int kn, int jn) {
+        const int buf = kn & 1;
+        double* mine = slots + (size_t)buf * ldv;
+        CandRec r;
+        r.val = -1.0;
+        r.beta = r.tau = 0.0;
+        r.pos = INT_MAX;
+        r.col = -1;
+        r.stop = 0;
+        r.pad = 0;
+        if (lb.col >= 0) {
+            const int pl = lb.col - c_lo;
+            const double* pc = P + (size_t)pl * ld;
+            const double* fr = Fs + (size_t)pl * FLD;
+            double ss = 0.0;
+            for (int i = kn + tid; i < rows; i += NT) {
+                double u = pc[i];
+                for (int tt = 0; tt < jn; tt++) u -= Vs[i + (size_t)tt * ldv] * fr[tt];
+                mine[i] = u;
+                if (i > kn) ss += u * u;
+                else alpha_s[buf] = u;
+            }
+            ss = group_sum(ss, 32);
+            if (lane == 0) red[buf][warp] = ss;
+            __syncthreads();
+            ss = (lane < NW) ? red[buf][lane] : 0.0;
+            ss = group_sum(ss, ceil_pow2(NW));
+            ss = __shfl_sync(FULL, ss, 0);
+            const double alpha = alpha_s[buf];
+            double beta, tau, scal;
+            if (ss == 0.0) {
+                beta = alpha;
+                tau = 0.0;
+                scal = 0.0;
+            } else {
+                beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+                tau = (beta - alpha) / beta;
+                scal = 1.0 / (alpha - beta);
+            }
+            const double ref = (kn == 0) ? fabs(beta) : r00;
+            r.val = lb.val;
+            r.pos = lb.pos;
+            r.col = lb.col;
+            r.beta = beta;
+            r.tau = tau;
+            r.stop = (tol != 0.0 && !(fabs(beta) / ref >= tol)) ? 1 : 0;
+            for (int i = kn + tid; i < rows; i += NT) mine[i] = (i == kn) ? 1.0 : mine[i] * scal;
+        }
+        if constexpr (G > 1) {
+            if (warp == 0 && lane < G) cluster.map_shared_rank(&rec[0][0], lane)[buf * G + crank] = r;
+        } else {
+            if (tid == 0) rec[buf][0] = r;
+        }
+    };
+
+    // ---- gather the own column range [c_lo, c_hi); padding rows [rows, ld) are zeroed ----
     {
         int c0 = 0;
         for (int s = 0; s < t.nsrc; s++) {
@@ -104,233 +217,235 @@ __global__ void __launch_bounds__(NT) rrqr_cluster_kernel(const QrTask* __restri
             if (a < b) {
                 int nc = b - a, off = a - c0;
                 int tot = rows * nc;
-                double* dst = Wl + (size_t)(a - c_lo) * rows;
+                double* dst = P + (size_t)(a - c_lo) * ld;
                 if (!q.transposed) {
                     const double* sp = q.blk + (size_t)off * q.ld;
                     for (int e = tid; e < tot; e += NT) {
                         int i = e % rows, j = e / rows;
-                        dst[i + (size_t)j * rows] = sp[i + (size_t)j * q.ld];
+                        dst[i + (size_t)j * ld] = sp[i + (size_t)j * q.ld];
                     }
                 } else {
                     const double* sp = q.blk + off;  // block is w x rows
                     for (int e = tid; e < tot; e += NT) {
                         int j = e % nc, i = e / nc;
-                        dst[i + (size_t)j * rows] = sp[j + (size_t)i * q.ld];
+                        dst[i + (size_t)j * ld] = sp[j + (size_t)i * q.ld];
                     }
                 }
             }
             c0 += w;
         }
+        const int padr = ld - rows;
+        for (int e = tid; e < padr * ncl; e += NT) P[rows + e % padr + (size_t)(e / padr) * ld] = 0.0;
     }
     __syncthreads();
-    const bool thread_cols = rows <= 16;
-    // ---- initial column norms, identity positions ----
-    if (thread_cols) {
-        for (int c = c_lo + tid; c < c_hi; c += NT) {
-            const double* cj = Wl + (size_t)(c - c_lo) * rows;
+    // ---- initial squared column norms, identity positions, first candidates ----
+    {
+        Cand best{-1.0, INT_MAX, -1};
+        for (int base = 0; base < ncl; base += ngroups) {
+            int cl = base + grp;
+            bool valid = cl < ncl;
+            const double* cj = P + (size_t)(valid ? cl : 0) * ld;
             double s = 0.0;
-            for (int i = 0; i < rows; i++) s += cj[i] * cj[i];
-            s = sqrt(s);
-            vn1[c] = s;
-            vn2[c] = s;
-            pos[c] = c;
-            colAt[c] = c;
-        }
-    } else {
-        for (int c = c_lo + warp; c < c_hi; c += NW) {
-            const double* cj = Wl + (size_t)(c - c_lo) * rows;
-            double s = 0.0;
-            for (int i = lane; i < rows; i += 32) s += cj[i] * cj[i];
-            s = sqrt(warp_sum_d(s));
-            if (lane == 0) {
-                vn1[c] = s;
-                vn2[c] = s;
-                pos[c] = c;
-                colAt[c] = c;
+            if (valid)
+                for (int i = lig; i < rows; i += L) s += cj[i] * cj[i];
+            s = group_sum(s, L);
+            if (valid && lig == 0) {
+                nq1[cl] = s;
+                nq2[cl] = s;
+                pos[cl] = c_lo + cl;
+                if (better(s, c_lo + cl, best.val, best.pos)) best = Cand{s, c_lo + cl, c_lo + cl};
             }
         }
+        Cand lb = block_best(best, 1);
+        propose(lb, 0, 0);
     }
-    __threadfence();
     csync();
 
-    const double tol3z = sqrt(DBL_EPSILON);
     int rank = mn;
-    double r00 = 0.0;
+    int k0 = 0, nb = min(t.nb, mn);
     for (int k = 0; k < mn; k++) {
-        // ---- 1. local pivot candidate: max partial norm, ties -> smallest current position (idamax) ----
-        Cand best{-1.0, INT_MAX, -1};
-        for (int c = c_lo + tid; c < c_hi; c += NT) {
-            int p = pos[c];
-            if (p >= k) {
-                double v = vn1[c];
-                if (better(v, p, best.val, best.pos)) best = Cand{v, p, c};
-            }
+        const int j = k - k0, par = k & 1;
+        // ---- every CTA selects the same winner among the G proposals ----
+        int wi = 0;
+        if constexpr (G > 2) {
+            Cand c = (lane < G) ? Cand{rec[par][lane].val, rec[par][lane].pos, lane} : Cand{-2.0, INT_MAX, 0};
+            wi = warp_best(c, ceil_pow2(G)).col;
+            wi = __shfl_sync(FULL, wi, 0);
+        } else if constexpr (G == 2) {
+            if (better(rec[par][1].val, rec[par][1].pos, rec[par][0].val, rec[par][0].pos)) wi = 1;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, best.val, o);
-            int op = __shfl_xor_sync(0xffffffffu, best.pos, o);
-            int oc = __shfl_xor_sync(0xffffffffu, best.col, o);
-            if (better(ov, op, best.val, best.pos)) best = Cand{ov, op, oc};
-        }
-        if (lane == 0) redc[warp] = best;
-        __syncthreads();
-        if (tid == 0) {
-            Cand b = redc[0];
-            for (int w = 1; w < NW; w++)
-                if (better(redc[w].val, redc[w].pos, b.val, b.pos)) b = redc[w];
-            if (G > 1) {
-                for (int r = 0; r < G; r++) {
-                    Cand* rc = cluster.map_shared_rank(cand, r);
-                    rc[crank] = b;
-                }
-            } else {
-                cand[0] = b;
-            }
-        }
-        csync();
-        // ---- 2. global pivot (every CTA reduces the same G candidates) ----
-        Cand piv = cand[0];
-#pragma unroll
-        for (int r = 1; r < G; r++)
-            if (better(cand[r].val, cand[r].pos, piv.val, piv.pos)) piv = cand[r];
-        const int pcol = piv.col, ppos = piv.pos;
-        const int owner = pcol / cpc;
-        if (crank == 0 && tid == 0 && ppos != k) {  // virtual swap of positions k and ppos
-            int ck = colAt[k];
-            colAt[ppos] = ck;
-            pos[ck] = ppos;
-            colAt[k] = pcol;
-            pos[pcol] = k;
-            __threadfence();
-        }
-        // ---- 3. owner: Householder reflector (dlarfg), broadcast v / beta / tau / stop ----
-        if (crank == owner) {
-            double* col = Wl + (size_t)(pcol - c_lo) * rows;
-            double ss = 0.0;
-            for (int i = k + 1 + tid; i < rows; i += NT) ss += col[i] * col[i];
-            ss = block_sum_d<NT>(ss, red);
-            double alpha = col[k];
-            double xnorm = sqrt(ss);
-            double beta, tau, scal;
-            if (xnorm == 0.0) {
-                beta = alpha;
-                tau = 0.0;
-                scal = 0.0;
-            } else {
-                beta = -copysign(hypot(alpha, xnorm), alpha);
-                tau = (beta - alpha) / beta;
-                scal = 1.0 / (alpha - beta);
-            }
-            bool stop = (k > 0 && tol != 0.0 && !(fabs(beta) / r00 >= tol));
-            __syncthreads();
-            if (!stop) {
-                for (int i = k + 1 + tid; i < rows; i += NT) col[i] *= scal;
-                if (tid == 0) {
-                    col[k] = beta;
-                    t.tau[k] = tau;
-                }
-            }
-            __syncthreads();
-            for (int r = 0; r < G; r++) {
-                double* rv = (G > 1) ? cluster.map_shared_rank(vbuf, r) : vbuf;
-                if (!stop)
-                    for (int i = k + 1 + tid; i < rows; i += NT) rv[i] = col[i];
-                if (tid == 0) {
-                    double* rc = (G > 1) ? cluster.map_shared_rank(ctrl, r) : ctrl;
-                    rc[0] = beta;
-                    rc[1] = tau;
-                    rc[2] = stop ? 1.0 : 0.0;
-                }
-            }
-        }
-        csync();
-        const double beta = ctrl[0], tau = ctrl[1];
-        const bool stop = ctrl[2] != 0.0;
-        if (k == 0) r00 = fabs(beta);
-        if (stop) {
+        const CandRec win = rec[par][wi];
+        const int pcol = win.col, ppos = win.pos;
+        if (pcol < 0) {  // no admissible column (NaN norms): stop here
             rank = k;
             break;
         }
-        // ---- 4. apply H to the own active columns, downdate their partial norms (dlaqp2) ----
-        const double* v = vbuf;
-        if (thread_cols) {
-            for (int c = c_lo + tid; c < c_hi; c += NT) {
-                if (pos[c] <= k) continue;
-                double* cj = Wl + (size_t)(c - c_lo) * rows;
-                double w = cj[k];
-                for (int i = k + 1; i < rows; i++) w += v[i] * cj[i];
-                w *= tau;
-                cj[k] -= w;
-                for (int i = k + 1; i < rows; i++) cj[i] -= w * v[i];
-                double n1 = vn1[c];
-                if (n1 != 0.0) {
-                    double tmp = fabs(cj[k]) / n1;
-                    tmp = fmax(0.0, 1.0 - tmp * tmp);
-                    double r = n1 / vn2[c];
-                    double tmp2 = tmp * r * r;
-                    if (tmp2 <= tol3z) {
-                        double s = 0.0;
-                        for (int i = k + 1; i < rows; i++) s += cj[i] * cj[i];
-                        s = sqrt(s);
-                        vn1[c] = s;
-                        vn2[c] = s;
-                    } else {
-                        vn1[c] = n1 * sqrt(tmp);
-                    }
-                }
+        const double beta = win.beta, tau = win.tau;
+        if (k == 0) r00 = fabs(beta);
+        if (win.stop) {
+            rank = k;
+            break;
+        }
+        // ---- pull the winner's reflector into column j of the block (zero outside [k, rows)) ----
+        double* vj = Vs + (size_t)j * ldv;
+        {
+            const double* wv = slots + (size_t)par * ldv;
+            if constexpr (G > 1) wv = cluster.map_shared_rank(wv, wi);
+            const bool own = (crank == wi);
+            for (int i = tid; i < ldv; i += NT) {
+                double v = (i >= k && i < rows) ? wv[i] : 0.0;
+                vj[i] = v;
+                if (own && i > k && i < rows) t.V[i + (size_t)k * rows] = v;
             }
-        } else {
-            for (int c = c_lo + warp; c < c_hi; c += NW) {
-                if (pos[c] <= k) continue;
-                double* cj = Wl + (size_t)(c - c_lo) * rows;
-                double w = 0.0;
-                for (int i = k + 1 + lane; i < rows; i += 32) w += v[i] * cj[i];
-                w = warp_sum_d(w);
-                double ckj = cj[k];
-                w = (w + ckj) * tau;
-                for (int i = k + 1 + lane; i < rows; i += 32) cj[i] -= w * v[i];
-                double newk = ckj - w;
-                double n1 = vn1[c];
-                bool recompute = false;
-                double newn = 0.0;
-                if (n1 != 0.0) {
-                    double tmp = fabs(newk) / n1;
-                    tmp = fmax(0.0, 1.0 - tmp * tmp);
-                    double r = n1 / vn2[c];
-                    double tmp2 = tmp * r * r;
-                    if (tmp2 <= tol3z) recompute = true;
-                    else newn = n1 * sqrt(tmp);
-                }
-                if (recompute) {
-                    __syncwarp();
-                    double s = 0.0;
-                    for (int i = k + 1 + lane; i < rows; i += 32) s += cj[i] * cj[i];
-                    s = sqrt(warp_sum_d(s));
-                    if (lane == 0) {
-                        vn1[c] = s;
-                        vn2[c] = s;
-                    }
-                } else if (lane == 0 && n1 != 0.0) {
-                    vn1[c] = newn;
-                }
-                if (lane == 0) cj[k] = newk;
+            if (own && tid == 0) {
+                P[k + (size_t)(pcol - c_lo) * ld] = beta;
+                t.tau[k] = tau;
             }
         }
         __syncthreads();
+        // ---- aux = V(k:, 0:j)^T v ----
+        if (j > 0) {
+            for (int tt = warp; tt < j; tt += NW) {
+                const double* vt = Vs + (size_t)tt * ldv;
+                double s = 0.0;
+                for (int i = k + lane; i < rows; i += 32) s += vt[i] * vj[i];
+                s = group_sum(s, 32);
+                if (lane == 0) aux[tt] = s;
+            }
+            __syncthreads();
+        }
+        // ---- F(:, j), row k of the panel, partial norms, local candidate for step k + 1 ----
+        Cand best{-1.0, INT_MAX, -1};
+        const double2* v2 = reinterpret_cast<const double2*>(vj);
+        for (int base = 0; base < ncl; base += NC * ngroups) {
+            int cl[NC], p[NC];
+            bool act[NC], need[NC];
+            double s[NC], f[NC], a_k[NC], n1[NC], newn[NC];
+            const double2* c2[NC];
+            bool any_act = false;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                cl[c] = base + c * ngroups + grp;
+                const bool valid = cl[c] < ncl;
+                p[c] = -1;
+                if (valid) {
+                    p[c] = pos[cl[c]];
+                    if (c_lo + cl[c] == pcol) {
+                        p[c] = k;
+                        if (lig == 0) pos[cl[c]] = k;
+                    } else if (p[c] == k) {  // virtual swap: the column at position k takes the pivot's place
+                        p[c] = ppos;
+                        if (lig == 0) pos[cl[c]] = ppos;
+                    }
+                }
+                act[c] = valid && p[c] > k;
+                any_act |= act[c];
+                if (!act[c]) cl[c] = 0;
+                c2[c] = reinterpret_cast<const double2*>(P + (size_t)cl[c] * ld);
+                s[c] = 0.0;
+                need[c] = false;
+                f[c] = a_k[c] = n1[c] = newn[c] = 0.0;
+            }
+            if (any_act) {
+                for (int i2 = (k >> 1) + lig; i2 < npair; i2 += L) {
+                    const double2 vv = v2[i2];
+#pragma unroll
+                    for (int c = 0; c < NC; c++)
+                        if (act[c]) {
+                            const double2 a = c2[c][i2];
+                            s[c] = fma(a.x, vv.x, s[c]);
+                            s[c] = fma(a.y, vv.y, s[c]);
+                        }
+                }
+            }
+            bool any_need = false;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                s[c] = group_sum(s[c], L);
+                if (act[c]) {
+                    const double* cj = P + (size_t)cl[c] * ld;
+                    const double* fr = Fs + (size_t)cl[c] * FLD;
+                    double corr = 0.0, rk = cj[k];
+                    for (int tt = 0; tt < j; tt++) {
+                        const double ft = fr[tt];
+                        corr = fma(ft, aux[tt], corr);
+                        rk = fma(-Vs[k + (size_t)tt * ldv], ft, rk);
+                    }
+                    f[c] = tau * (s[c] - corr);
+                    a_k[c] = rk - f[c];
+                    n1[c] = nq1[cl[c]];
+                    if (n1[c] != 0.0) {
+                        newn[c] = fmax(0.0, n1[c] - a_k[c] * a_k[c]);
+                        need[c] = newn[c] <= tol3z * nq2[cl[c]];
+                    }
+                }
+                any_need |= need[c];
+            }
+            if (__any_sync(FULL, any_need)) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    if (!__any_sync(FULL, need[c])) continue;
+                    double q = 0.0;
+                    if (need[c]) {
+                        const double* cj = P + (size_t)cl[c] * ld;
+                        const double* fr = Fs + (size_t)cl[c] * FLD;
+                        for (int i = k + 1 + lig; i < rows; i += L) {
+                            double u = cj[i];
+                            for (int tt = 0; tt < j; tt++) u -= Vs[i + (size_t)tt * ldv] * fr[tt];
+                            u -= vj[i] * f[c];
+                            q += u * u;
+                        }
+                    }
+                    q = group_sum(q, L);
+                    if (need[c]) newn[c] = q;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+                if (act[c] && lig == 0) {
+                    Fs[(size_t)cl[c] * FLD + j] = f[c];
+                    P[k + (size_t)cl[c] * ld] = a_k[c];
+                    if (n1[c] != 0.0) {
+                        nq1[cl[c]] = newn[c];
+                        if (need[c]) nq2[cl[c]] = newn[c];
+                    }
+                    if (better(newn[c], p[c], best.val, best.pos)) best = Cand{newn[c], p[c], c_lo + cl[c]};
+                }
+        }
+        if (k + 1 >= mn) break;  // factorization complete, rank = mn
+        Cand lb = block_best(best, par);  // contains a block barrier: F and row k are visible below
+        // ---- end of block: trailing rows of the own active columns  W -= V F^T ----
+        int jn = j + 1;
+        if (j == nb - 1) {
+            const int kend = k + 1;
+            for (int base = 0; base < ncl; base += ngroups) {
+                const int cl = base + grp;
+                if (cl >= ncl || pos[cl] < kend) continue;
+                double* cj = P + (size_t)cl * ld;
+                double f[QR_NB];
+#pragma unroll
+                for (int tt = 0; tt < QR_NB; tt++) f[tt] = (tt < nb) ? Fs[(size_t)cl * FLD + tt] : 0.0;
+                for (int i = kend + lig; i < rows; i += L) {
+                    double a = cj[i];
+#pragma unroll
+                    for (int tt = 0; tt < QR_NB; tt++)
+                        if (tt < nb) a -= Vs[i + (size_t)tt * ldv] * f[tt];
+                    cj[i] = a;
+                }
+            }
+            k0 = kend;
+            nb = min(t.nb, mn - k0);
+            jn = 0;
+            __syncthreads();
+        }
+        propose(lb, k + 1, jn);
+        csync();
     }
+    // All CTAs leave the loop at the same step. One more barrier so that no CTA exits (or starts scattering over
+    // its panel) while a sibling may still be pulling from its slots.
+    csync();
     if (rank >= rows) return;  // nothing to do (tree.cpp:1317-1319); csize unchanged
 
-    __syncthreads();
-    // ---- V: the own pivot columns, in pivot order ----
-    for (int c = c_lo + warp; c < c_hi; c += NW) {
-        int p = pos[c];
-        if (p < rank) {
-            const double* cj = Wl + (size_t)(c - c_lo) * rows;
-            double* vd = t.V + (size_t)p * rows;
-            for (int i = lane; i < rows; i += 32) vd[i] = cj[i];
-        }
-    }
     // ---- scatter triu(R[:rank,:]) P^T back into the own columns of the edge blocks, in place ----
     {
         int c0 = 0;
@@ -344,16 +459,16 @@ __global__ void __launch_bounds__(NT) rrqr_cluster_kernel(const QrTask* __restri
                 if (!q.transposed) {
                     double* dp = q.blk + (size_t)off * q.ld;
                     for (int e = tid; e < tot; e += NT) {
-                        int i = e % rank, j = e / rank;
-                        int p = pos[a + j];
-                        dp[i + (size_t)j * q.ld] = (p >= rank || i <= p) ? Wl[i + (size_t)(a + j - c_lo) * rows] : 0.0;
+                        int i = e % rank, jj = e / rank;
+                        int p = pos[a + jj - c_lo];
+                        dp[i + (size_t)jj * q.ld] = (p >= rank || i <= p) ? P[i + (size_t)(a + jj - c_lo) * ld] : 0.0;
                     }
                 } else {
                     double* dp = q.blk + off;
                     for (int e = tid; e < tot; e += NT) {
-                        int j = e % nc, i = e / nc;
-                        int p = pos[a + j];
-                        dp[j + (size_t)i * q.ld] = (p >= rank || i <= p) ? Wl[i + (size_t)(a + j - c_lo) * rows] : 0.0;
+                        int jj = e % nc, i = e / nc;
+                        int p = pos[a + jj - c_lo];
+                        dp[jj + (size_t)i * q.ld] = (p >= rank || i <= p) ? P[i + (size_t)(a + jj - c_lo) * ld] : 0.0;
                     }
                 }
             }
@@ -363,9 +478,9 @@ __global__ void __launch_bounds__(NT) rrqr_cluster_kernel(const QrTask* __restri
     if (crank == 0 && tid == 0) csize[t.cluster] = rank;
 }
 
-template <int G, int NT>
+template <int G, int NT, bool SP>
 void launch_one(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int smem, cudaStream_t st) {
-    auto kern = rrqr_cluster_kernel<G, NT>;
+    auto kern = rrqr_blocked_kernel<G, NT, SP>;
     static int configured_smem = -1;
     if (smem > configured_smem) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -384,26 +499,47 @@ void launch_one(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, t, s, csize, tol, smem);
+    cudaLaunchKernelEx(&cfg, kern, t, s, csize, tol);
 }
 
 }  // namespace
 
-int rrqr_max_smem() { return 216 * 1024; }
+int rrqr_max_smem() { return 224 * 1024; }
 
-void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int nthreads, int smem,
-                 cudaStream_t st) {
+size_t rrqr_smem_bytes(int rows, int maxcols, int G, int nb, int ld, bool in_smem) {
+    size_t cpcm = (size_t)(maxcols + G - 1) / G;
+    size_t cpce = (cpcm + 3) & ~(size_t)3;
+    size_t ldv = ((size_t)rows + 1) & ~(size_t)1;
+    size_t fld = (size_t)(nb | 1);
+    size_t doubles = ldv * nb + ((cpcm * fld + 1) & ~(size_t)1) + 2 * cpce + 2 * ldv + (in_smem ? (size_t)ld * cpcm : 0);
+    return doubles * sizeof(double) + cpce * sizeof(int);
+}
+
+void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int nthreads, bool in_smem,
+                 int smem, cudaStream_t st) {
     if (nt <= 0) return;
-    if (nthreads <= 128) {
-        launch_one<1, 128>(t, nt, s, csize, tol, smem, st);
+    if (!in_smem) {
+        launch_one<8, 512, false>(t, nt, s, csize, tol, smem, st);
         return;
     }
-    switch (G) {
-        case 1: launch_one<1, 512>(t, nt, s, csize, tol, smem, st); break;
-        case 2: launch_one<2, 512>(t, nt, s, csize, tol, smem, st); break;
-        case 4: launch_one<4, 512>(t, nt, s, csize, tol, smem, st); break;
-        case 8: launch_one<8, 512>(t, nt, s, csize, tol, smem, st); break;
-        default: launch_one<16, 512>(t, nt, s, csize, tol, smem, st); break;
+    if (nthreads <= 128) {
+        launch_one<1, 128, true>(t, nt, s, csize, tol, smem, st);
+    } else if (nthreads <= 256) {
+        switch (G) {
+            case 1: launch_one<1, 256, true>(t, nt, s, csize, tol, smem, st); break;
+            case 2: launch_one<2, 256, true>(t, nt, s, csize, tol, smem, st); break;
+            case 4: launch_one<4, 256, true>(t, nt, s, csize, tol, smem, st); break;
+            case 8: launch_one<8, 256, true>(t, nt, s, csize, tol, smem, st); break;
+            default: launch_one<16, 256, true>(t, nt, s, csize, tol, smem, st); break;
+        }
+    } else {
+        switch (G) {
+            case 1: launch_one<1, 512, true>(t, nt, s, csize, tol, smem, st); break;
+            case 2: launch_one<2, 512, true>(t, nt, s, csize, tol, smem, st); break;
+            case 4: launch_one<4, 512, true>(t, nt, s, csize, tol, smem, st); break;
+            case 8: launch_one<8, 512, true>(t, nt, s, csize, tol, smem, st); break;
+            default: launch_one<16, 512, true>(t, nt, s, csize, tol, smem, st); break;
+        }
     }
 }
 

@@ -110,6 +110,11 @@ void Tree::ensure_device() {
     scratch_ = new DeviceArena((size_t)256 << 20);
     stager_.reserve((size_t)64 << 20);
     CK(cudaMalloc((void**)&d_err_, sizeof(int)));
+    for (int i = 0; i < kSide; i++) {
+        CK(cudaStreamCreateWithFlags(&side_[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_join_[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
 }
 
 void Tree::free_device() {
@@ -120,8 +125,56 @@ void Tree::free_device() {
     arena_ = scratch_ = nullptr;
     if (d_err_) cudaFree(d_err_);
     d_err_ = nullptr;
+    for (int i = 0; i < kSide; i++) {
+        cudaStreamDestroy(side_[i]);
+        cudaEventDestroy(ev_join_[i]);
+    }
+    cudaEventDestroy(ev_fork_);
+    for (auto e : ev_pool_) cudaEventDestroy(e);
+    ev_pool_.clear();
     cudaStreamDestroy(st_);
     st_ = nullptr;
+}
+
+const char* Tree::family_name(int f) {
+    static const char* names[F_COUNT] = {"potrf", "trsm", "gemm", "rrqr", "copy"};
+    return (f >= 0 && f < F_COUNT) ? names[f] : "";
+}
+
+cudaEvent_t Tree::fam_begin(int fam) {
+    family_launches[fam]++;
+    if (!profile_families) return nullptr;
+    cudaEvent_t a;
+    if (ev_pool_.empty()) CK(cudaEventCreate(&a));
+    else {
+        a = ev_pool_.back();
+        ev_pool_.pop_back();
+    }
+    CK(cudaEventRecord(a, st_));
+    return a;
+}
+
+void Tree::fam_end(int fam, cudaEvent_t a) {
+    if (!profile_families) return;
+    cudaEvent_t b;
+    if (ev_pool_.empty()) CK(cudaEventCreate(&b));
+    else {
+        b = ev_pool_.back();
+        ev_pool_.pop_back();
+    }
+    CK(cudaEventRecord(b, st_));
+    fam_events_.push_back({fam, a, b});
+}
+
+void Tree::fam_resolve() {
+    for (auto& e : fam_events_) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e.a, e.b));
+        family_ms[e.fam] += ms;
+        ev_pool_.push_back(e.a);
+        ev_pool_.push_back(e.b);
+    }
+    fam_events_.clear();
 }
 
 template <class T>
@@ -317,7 +370,9 @@ void Tree::run_gemm(std::vector<GemmTask>& tasks, std::vector<GemmContrib>& cont
     GemmContrib* dc = to_device(contribs, scratch_);
     if (!small.empty()) {
         GemmTask* dt = to_device(small, scratch_);
+        auto ev = fam_begin(F_GEMM);
         launch_gemm_small(dt, (int)small.size(), dc, st_);
+        fam_end(F_GEMM, ev);
         lg.launches++;
     }
     if (!big.empty()) {
@@ -326,7 +381,9 @@ void Tree::run_gemm(std::vector<GemmTask>& tasks, std::vector<GemmContrib>& cont
             prefix[i + 1] = prefix[i] + ((big[i].m + 63) / 64) * ((big[i].n + 63) / 64);
         GemmTask* dt = to_device(big, scratch_);
         int* dp = to_device(prefix, scratch_);
+        auto ev = fam_begin(F_GEMM);
         launch_gemm_tiled(dt, (int)big.size(), dc, dp, prefix.back(), st_);
+        fam_end(F_GEMM, ev);
         lg.launches++;
     }
 }
@@ -337,7 +394,9 @@ void Tree::run_potrf(std::vector<PotrfTask>& tasks, LevelLog& lg) {
     for (auto& t : tasks) maxn = std::max(maxn, t.n);
     PotrfTask* dt = to_device(tasks, scratch_);
     for (int j0 = 0; j0 < maxn; j0 += NB) {
+        auto ev = fam_begin(F_POTRF);
         launch_potrf_step(dt, (int)tasks.size(), j0, d_err_, st_);
+        fam_end(F_POTRF, ev);
         lg.launches++;
         if (j0 + NB >= maxn) break;
         std::vector<TrsmTask> panel;
@@ -366,7 +425,9 @@ void Tree::run_potrf(std::vector<PotrfTask>& tasks, LevelLog& lg) {
             con.push_back({p.B, p.B, t.ld, t.ld, NB});
         }
         TrsmTask* dp = to_device(panel, scratch_);
+        ev = fam_begin(F_TRSM);
         launch_trsm_step(TRSM_RLT, dp, (int)panel.size(), 0, max_m, st_);
+        fam_end(F_TRSM, ev);
         lg.launches++;
         run_gemm(upd, con, lg);
     }
@@ -389,7 +450,9 @@ void Tree::run_trsm(int mode, std::vector<TrsmTask>& all, LevelLog& lg) {
         }
         TrsmTask* dt = to_device(tasks, scratch_);
         for (int j0 = 0; j0 < maxn; j0 += NB) {
+            auto ev = fam_begin(F_TRSM);
             launch_trsm_step(mode, dt, (int)tasks.size(), j0, max_m, st_);
+            fam_end(F_TRSM, ev);
             lg.launches++;
             if (j0 + NB >= maxn) break;
             std::vector<GemmTask> upd;
@@ -678,40 +741,83 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             t.maxcols = maxcols;
             color[s - first] = col;
             ncolors = std::max(ncolors, col + 1);
-            size_t wdoubles = (size_t)t.rows * maxcols + 2 * (size_t)maxcols;
-            t.W = scratch_->alloc_n<double>(wdoubles);
-            t.ipiv = scratch_->alloc_n<int>(2 * (size_t)maxcols + 1);
+            t.W = nullptr;
             int kmax = std::min(t.rows, maxcols);
             t.V = arena_->alloc_n<double>((size_t)t.rows * kmax);
             t.tau = arena_->alloc_n<double>(kmax);
             tasks.push_back(t);
             task_color.push_back(col);
         }
-        // Launch classes: cluster size G and shared-memory bucket, chosen so that the panel stays resident in
-        // (distributed) shared memory whenever it fits in 16 CTAs.
+        // Launch classes: (threads, cluster size G, shared-memory bucket). The panel stays resident in (distributed)
+        // shared memory whenever it fits in 16 CTAs; otherwise it lives in the (L2-resident) scratch arena.
         const int MAXS = rrqr_max_smem();
-        auto need = [](const QrTask& t, int G) {
-            long cpc = (t.maxcols + G - 1) / G;
-            return ((long)t.rows * cpc + t.rows) * (long)sizeof(double);
-        };
-        std::vector<int> klass(tasks.size());   // (G index << 4) | bucket ; tiny class = 0
+        static const int kBuckets[] = {12 << 10, 24 << 10, 40 << 10, 72 << 10, 112 << 10, 224 << 10};
+        auto pow2floor = [](int x) { int p = 1; while (2 * p <= x) p *= 2; return p; };
+        auto pow2ceil = [](int x) { int p = 1; while (p < x) p *= 2; return p; };
+        // class = (mode << 8) | (log2 G << 4) | bucket; mode 0: 128 threads (G = 1), 1: 256 threads, 2: panel in the
+        // global scratch (512 threads, G = 8), 3: 512 threads
+        std::vector<int> klass(tasks.size());
         std::vector<int> smem_need(tasks.size());
+        const int kNB = 6;
+        std::vector<int> per_color(ncolors, 0);
+        for (int c : task_color) per_color[c]++;
         for (size_t i = 0; i < tasks.size(); i++) {
-            const QrTask& t = tasks[i];
-            if (need(t, 1) <= 20 * 1024) {
-                klass[i] = 0;
-                smem_need[i] = (int)need(t, 1);
+            QrTask& t = tasks[i];
+            int mn = std::max(1, std::min(t.rows, t.maxcols));
+            t.nb = std::min(QR_NB, mn);
+            auto config = [&](int NT, int G, bool in_smem) {
+                int cpcm = std::max(1, (t.maxcols + G - 1) / G);
+                int L = in_smem ? std::min(32, std::max(1, pow2floor(NT / cpcm))) : 32;
+                L = std::min(L, pow2ceil(std::max(1, (t.rows + 1) / 2)));  // a lane works on pairs of rows
+                int ld = (t.rows + 1) & ~1;
+                if (in_smem && L < 8)
+                    while (ld % 16 != (2 * L) % 16) ld += 2;  // conflict-free 128-bit shared loads
+                t.L = L;
+                t.ld = ld;
+                t.in_smem = in_smem ? 1 : 0;
+                return (long)rrqr_smem_bytes(t.rows, t.maxcols, G, t.nb, t.ld, in_smem);
+            };
+            auto bucket_of = [&](long nd) {
+                int b = 0;
+                while (b < kNB - 1 && nd > kBuckets[b]) b++;
+                return b;
+            };
+            long nd = config(128, 1, true);
+            if (t.rows <= 64 && nd <= kBuckets[2]) {
+                klass[i] = bucket_of(nd);
+                smem_need[i] = (int)nd;
                 continue;
             }
-            int gi = 0, G = 1;
-            while (G < 16 && need(t, G) > MAXS) {
-                G *= 2;
-                gi++;
+            // Cluster size: wide enough that the wavefront fills the GPU (about two CTAs per SM), at least what the
+            // panel needs to stay in shared memory.
+            int want = 1;
+            while (want < 16 && per_color[task_color[i]] * want < 296) want *= 2;
+            int g = 0;
+            while ((1 << g) < want) g++;
+            int gi = -1, nt = 256;
+            for (; g <= 4 && gi < 0; g++) {
+                nd = config(256, 1 << g, true);
+                if (nd <= kBuckets[4]) gi = g;
+                else if (nd <= MAXS) {
+                    nt = 512;
+                    nd = config(512, 1 << g, true);
+                    gi = g;
+                }
             }
-            long nd = need(t, G);
-            if (nd > MAXS) nd = (long)t.rows * sizeof(double);  // panel stays in L2-resident scratch
-            int bucket = nd <= 48 * 1024 ? 1 : (nd <= 100 * 1024 ? 2 : 3);
-            klass[i] = ((gi + 1) << 4) | bucket;
+            if (gi >= 0) {
+                klass[i] = ((nt == 256 ? 1 : 3) << 8) | (gi << 4) | bucket_of(nd);
+                smem_need[i] = (int)nd;
+                continue;
+            }
+            // panel stays in the scratch arena: 8 CTAs stream their slabs from L2
+            nd = config(512, 8, false);
+            while (nd > MAXS && t.nb > 2) {
+                t.nb /= 2;
+                nd = config(512, 8, false);
+            }
+            if (nd > MAXS) throw std::runtime_error("sparsify: interface cluster too large for the RRQR kernel");
+            t.W = scratch_->alloc_n<double>((size_t)t.ld * t.maxcols);
+            klass[i] = (2 << 8) | (3 << 4) | bucket_of(nd);
             smem_need[i] = (int)nd;
         }
         // order tasks by (colour, class), stable
@@ -725,19 +831,39 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         for (size_t i = 0; i < idx.size(); i++) sorted[i] = tasks[idx[i]];
         QrTask* dt = to_device(sorted, scratch_);
         QrSrc* ds = to_device(srcs, scratch_);
+        // One launch per (colour, class). The classes of a colour are independent: they run concurrently on side
+        // streams forked from / joined into the factorization stream.
         for (size_t b = 0; b < idx.size();) {
-            size_t e = b;
-            int smem = 0;
-            while (e < idx.size() && task_color[idx[e]] == task_color[idx[b]] && klass[idx[e]] == klass[idx[b]]) {
-                smem = std::max(smem, smem_need[idx[e]]);
-                e++;
+            size_t cend = b;
+            while (cend < idx.size() && task_color[idx[cend]] == task_color[idx[b]]) cend++;
+            auto ev = fam_begin(F_RRQR);
+            CK(cudaEventRecord(ev_fork_, st_));
+            int nside = 0;
+            while (b < cend) {
+                size_t e = b;
+                int smem = 0;
+                while (e < cend && klass[idx[e]] == klass[idx[b]]) {
+                    smem = std::max(smem, smem_need[idx[e]]);
+                    e++;
+                }
+                int k = klass[idx[b]];
+                int mode = k >> 8, G = 1 << ((k >> 4) & 15);
+                smem = (smem + 1023) & ~1023;
+                cudaStream_t s = side_[nside % kSide];
+                CK(cudaStreamWaitEvent(s, ev_fork_, 0));
+                launch_rrqr(dt + b, (int)(e - b), ds, d_csize_, tol, G, mode == 0 ? 128 : (mode == 1 ? 256 : 512),
+                            mode != 2, smem, s);
+                nside++;
+                lg.launches++;
+                family_launches[F_RRQR]++;
+                b = e;
             }
-            int k = klass[idx[b]];
-            int G = (k == 0) ? 1 : (1 << ((k >> 4) - 1));
-            smem = (smem + 1023) & ~1023;
-            launch_rrqr(dt + b, (int)(e - b), ds, d_csize_, tol, G, k == 0 ? 128 : 512, smem, st_);
-            lg.launches++;
-            b = e;
+            for (int i = 0; i < std::min(nside, kSide); i++) {
+                CK(cudaEventRecord(ev_join_[i], side_[i]));
+                CK(cudaStreamWaitEvent(st_, ev_join_[i], 0));
+            }
+            family_launches[F_RRQR]--;  // fam_begin counted the colour once
+            fam_end(F_RRQR, ev);
         }
         lg.wavefronts = ncolors;
         // ranks back to the host: the one synchronisation of the level
@@ -745,10 +871,13 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         CK(cudaMemcpyAsync(h_csize_.data() + first, d_csize_ + first, sizeof(int) * span, cudaMemcpyDeviceToHost, st_));
         check_error();
         std::vector<HouseTask> house;
+        FILE* dump = nullptr;
+        if (const char* fn = getenv("SPAND_DUMP_QR")) dump = fopen(fn, "a");
         for (size_t i = 0; i < tasks.size(); i++) {
             const QrTask& t = tasks[i];
             Cluster& cs = cl_[t.cluster];
             int rank = h_csize_[t.cluster];
+            if (dump) fprintf(dump, "%d %d %d %d %d %d\n", ilvl_, t.cluster, t.rows, t.maxcols, rank, task_color[i]);
             // columns actually seen by this cluster (earlier sparsified neighbours had already shrunk)
             long cols = 0;
             for (int k = 0; k < t.nsrc; k++) {
@@ -773,6 +902,7 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             }
             lg.rank_after += cs.size;
         }
+        if (dump) fclose(dump);
         sl.house = to_device(house, arena_);
         sl.n_house = (int)house.size();
     } else {
@@ -868,7 +998,9 @@ void Tree::phase_merge(LevelLog& lg, SolveLevel& sl) {
         slot[p] = -1;
     }
     double* nb = arena_->alloc_n<double>(total + 1);
+    auto evz = fam_begin(F_COPY);
     CK(cudaMemsetAsync(nb, 0, total * sizeof(double), st_));
+    fam_end(F_COPY, evz);
     lg.by_merge += 8.0 * total;
     std::vector<int> new_ids(ne.size());
     for (size_t i = 0; i < ne.size(); i++) {
@@ -906,7 +1038,9 @@ void Tree::phase_merge(LevelLog& lg, SolveLevel& sl) {
             cl_[c].in.clear();
         }
     CopyTask* dc = to_device(copies, scratch_);
+    auto evc = fam_begin(F_COPY);
     launch_copy(dc, (int)copies.size(), st_);
+    fam_end(F_COPY, evc);
     lg.launches += 2;
 }
 
@@ -920,6 +1054,10 @@ void Tree::factorize() {
     if (ed_.empty() || factorized_) throw std::runtime_error("factorize: call assemble first");
     ensure_device();
     CK(cudaMemsetAsync(d_err_, 0, sizeof(int), st_));
+    for (int f = 0; f < F_COUNT; f++) {
+        family_ms[f] = 0;
+        family_launches[f] = 0;
+    }
     std::vector<cudaEvent_t> ev(nlevels * 5);
     for (auto& e : ev) CK(cudaEventCreate(&e));
     cudaEvent_t ev_begin, ev_end;
@@ -967,6 +1105,7 @@ void Tree::factorize() {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
     t_factorize_device = ms * 1e-3;
+    fam_resolve();
     for (int l = 0; l <= last_level; l++) {
         float a, b, c, d;
         CK(cudaEventElapsedTime(&a, ev[l * 5 + 0], ev[l * 5 + 1]));

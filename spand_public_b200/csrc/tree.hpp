@@ -89,6 +89,13 @@ class Tree {
     bool monitor_flops = false;
     int stop_level = -1, stop_phase = -1;  // parity-test hook (see oracle)
     int device = 0;
+    // per-kernel-family device timing (CUDA events around every launch of the family on the factorization
+    // stream); off by default because the extra events serialise nothing but cost host time
+    bool profile_families = false;
+    enum Family { F_POTRF = 0, F_TRSM, F_GEMM, F_RRQR, F_COPY, F_COUNT };
+    double family_ms[F_COUNT] = {0, 0, 0, 0, 0};
+    long long family_launches[F_COUNT] = {0, 0, 0, 0, 0};
+    static const char* family_name(int f);
 
     void set_coords(int dim, int N, const double* X);
     void partition(const SpMat& A);
@@ -147,6 +154,9 @@ class Tree {
     bool factorized_ = false;
 
     cudaStream_t st_ = nullptr;
+    static constexpr int kSide = 4;  // side streams for independent launches of one wavefront
+    cudaStream_t side_[kSide] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork_ = nullptr, ev_join_[kSide] = {nullptr, nullptr, nullptr, nullptr};
     DeviceArena* arena_ = nullptr;    // blocks, factors, solve descriptors, x
     DeviceArena* scratch_ = nullptr;  // per-level descriptors + RRQR workspaces
     Stager stager_;
@@ -174,6 +184,12 @@ class Tree {
     void run_gemm(std::vector<GemmTask>& tasks, std::vector<GemmContrib>& contribs, LevelLog& lg);
     void check_error();
     int ndofs_left() const;
+    struct FamEvent { int fam; cudaEvent_t a, b; };
+    std::vector<FamEvent> fam_events_;
+    std::vector<cudaEvent_t> ev_pool_;
+    cudaEvent_t fam_begin(int fam);
+    void fam_end(int fam, cudaEvent_t a);
+    void fam_resolve();
 };
 
 }  // namespace spand
