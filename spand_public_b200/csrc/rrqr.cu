@@ -86,7 +86,7 @@ template <int G, int NT, bool SMEM_PANEL>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrqr_blocked_kernel(const QrTask* __restrict__ tasks,
                                                           const QrSrc* __restrict__ srcs, int* csize, double tol) {
     constexpr int NW = NT / 32;
-    constexpr int NC = SMEM_PANEL ? 2 : 4;  // columns a lane group works on at once (shares the v loads / MLP)
+    constexpr int NC = 2;  // columns a lane group works on at once (shares the v loads)
     const int task_id = blockIdx.x / G;
     const int crank = blockIdx.x % G;
     const QrTask t = tasks[task_id];
@@ -317,100 +317,203 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrq
         // ---- F(:, j), row k of the panel, partial norms, local candidate for step k + 1 ----
         Cand best{-1.0, INT_MAX, -1};
         const double2* v2 = reinterpret_cast<const double2*>(vj);
-        for (int base = 0; base < ncl; base += NC * ngroups) {
-            int cl[NC], p[NC];
-            bool act[NC], need[NC];
-            double s[NC], f[NC], a_k[NC], n1[NC], newn[NC];
-            const double2* c2[NC];
-            bool any_act = false;
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                cl[c] = base + c * ngroups + grp;
-                const bool valid = cl[c] < ncl;
-                p[c] = -1;
-                if (valid) {
-                    p[c] = pos[cl[c]];
-                    if (c_lo + cl[c] == pcol) {
-                        p[c] = k;
-                        if (lig == 0) pos[cl[c]] = k;
-                    } else if (p[c] == k) {  // virtual swap: the column at position k takes the pivot's place
-                        p[c] = ppos;
-                        if (lig == 0) pos[cl[c]] = ppos;
+        if constexpr (!SMEM_PANEL) {
+            // Panel in global memory (L == 32): a warp takes WB columns at once. All loads of the batch are in flight
+            // together, the WB x 32 partial sums are transpose-reduced with WB + 1 shuffles, and the scalar epilogue of
+            // the WB columns runs lane-parallel (column c on lanes 4c..4c+3).
+            constexpr int WB = 8;
+            for (int base = 0; base < ncl; base += WB * NW) {
+                const int myc = lane >> 2;
+                int my_cl = base + myc * NW + warp, my_p = -1;
+                const bool my_valid = my_cl < ncl;
+                if (my_valid) {
+                    my_p = pos[my_cl];
+                    if (c_lo + my_cl == pcol) {
+                        my_p = k;
+                        if ((lane & 3) == 0) pos[my_cl] = k;
+                    } else if (my_p == k) {
+                        my_p = ppos;
+                        if ((lane & 3) == 0) pos[my_cl] = ppos;
                     }
                 }
-                act[c] = valid && p[c] > k;
-                any_act |= act[c];
-                if (!act[c]) cl[c] = 0;
-                c2[c] = reinterpret_cast<const double2*>(P + (size_t)cl[c] * ld);
-                s[c] = 0.0;
-                need[c] = false;
-                f[c] = a_k[c] = n1[c] = newn[c] = 0.0;
-            }
-            if (any_act) {
-                for (int i2 = (k >> 1) + lig; i2 < npair; i2 += L) {
+                const bool my_act = my_valid && my_p > k;
+                if (!my_act) my_cl = 0;
+                const unsigned actmask = __ballot_sync(FULL, my_act);
+                if (actmask == 0) continue;
+                double s[WB];
+                const double2* c2[WB];
+#pragma unroll
+                for (int c = 0; c < WB; c++) {
+                    s[c] = 0.0;
+                    const int clc = (actmask >> (4 * c)) & 1 ? base + c * NW + warp : 0;
+                    c2[c] = reinterpret_cast<const double2*>(P + (size_t)clc * ld);
+                }
+                for (int i2 = (k >> 1) + lane; i2 < npair; i2 += 32) {
                     const double2 vv = v2[i2];
 #pragma unroll
-                    for (int c = 0; c < NC; c++)
-                        if (act[c]) {
+                    for (int c = 0; c < WB; c++)
+                        if ((actmask >> (4 * c)) & 1) {
                             const double2 a = c2[c][i2];
                             s[c] = fma(a.x, vv.x, s[c]);
                             s[c] = fma(a.y, vv.y, s[c]);
                         }
                 }
-            }
-            bool any_need = false;
 #pragma unroll
-            for (int c = 0; c < NC; c++) {
-                s[c] = group_sum(s[c], L);
-                if (act[c]) {
-                    const double* cj = P + (size_t)cl[c] * ld;
-                    const double* fr = Fs + (size_t)cl[c] * FLD;
+                for (int h = WB / 2, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+                    const bool up = (lane & bit) != 0;
+#pragma unroll
+                    for (int i = 0; i < h; i++) {
+                        const double keep = up ? s[i + h] : s[i];
+                        const double send = up ? s[i] : s[i + h];
+                        s[i] = keep + __shfl_xor_sync(FULL, send, bit);
+                    }
+                }
+                double tot = s[0];
+                tot += __shfl_xor_sync(FULL, tot, 2);
+                tot += __shfl_xor_sync(FULL, tot, 1);
+                double my_f = 0.0, my_ak = 0.0, my_n1 = 0.0, my_newn = 0.0;
+                bool my_need = false;
+                if (my_act) {
+                    const double* cj = P + (size_t)my_cl * ld;
+                    const double* fr = Fs + (size_t)my_cl * FLD;
                     double corr = 0.0, rk = cj[k];
                     for (int tt = 0; tt < j; tt++) {
                         const double ft = fr[tt];
                         corr = fma(ft, aux[tt], corr);
                         rk = fma(-Vs[k + (size_t)tt * ldv], ft, rk);
                     }
-                    f[c] = tau * (s[c] - corr);
-                    a_k[c] = rk - f[c];
-                    n1[c] = nq1[cl[c]];
-                    if (n1[c] != 0.0) {
-                        newn[c] = fmax(0.0, n1[c] - a_k[c] * a_k[c]);
-                        need[c] = newn[c] <= tol3z * nq2[cl[c]];
+                    my_f = tau * (tot - corr);
+                    my_ak = rk - my_f;
+                    my_n1 = nq1[my_cl];
+                    if (my_n1 != 0.0) {
+                        my_newn = fmax(0.0, my_n1 - my_ak * my_ak);
+                        my_need = my_newn <= tol3z * nq2[my_cl];
                     }
                 }
-                any_need |= need[c];
-            }
-            if (__any_sync(FULL, any_need)) {
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    if (!__any_sync(FULL, need[c])) continue;
+                unsigned nm = __ballot_sync(FULL, my_need && (lane & 3) == 0);
+                while (nm) {
+                    const int srcl = __ffs(nm) - 1;
+                    nm &= nm - 1;
+                    const int ccl = __shfl_sync(FULL, my_cl, srcl);
+                    const double ff = __shfl_sync(FULL, my_f, srcl);
+                    const double* cj = P + (size_t)ccl * ld;
+                    const double* fr = Fs + (size_t)ccl * FLD;
                     double q = 0.0;
-                    if (need[c]) {
-                        const double* cj = P + (size_t)cl[c] * ld;
-                        const double* fr = Fs + (size_t)cl[c] * FLD;
-                        for (int i = k + 1 + lig; i < rows; i += L) {
-                            double u = cj[i];
-                            for (int tt = 0; tt < j; tt++) u -= Vs[i + (size_t)tt * ldv] * fr[tt];
-                            u -= vj[i] * f[c];
-                            q += u * u;
+                    for (int i = k + 1 + lane; i < rows; i += 32) {
+                        double u = cj[i];
+                        for (int tt = 0; tt < j; tt++) u -= Vs[i + (size_t)tt * ldv] * fr[tt];
+                        u -= vj[i] * ff;
+                        q += u * u;
+                    }
+                    q = group_sum(q, 32);
+                    if ((lane >> 2) == (srcl >> 2)) my_newn = q;
+                }
+                if (my_act && (lane & 3) == 0) {
+                    Fs[(size_t)my_cl * FLD + j] = my_f;
+                    P[k + (size_t)my_cl * ld] = my_ak;
+                    if (my_n1 != 0.0) {
+                        nq1[my_cl] = my_newn;
+                        if (my_need) nq2[my_cl] = my_newn;
+                    }
+                    if (better(my_newn, my_p, best.val, best.pos)) best = Cand{my_newn, my_p, c_lo + my_cl};
+                }
+            }
+        } else {
+            for (int base = 0; base < ncl; base += NC * ngroups) {
+                int cl[NC], p[NC];
+                bool act[NC], need[NC];
+                double s[NC], f[NC], a_k[NC], n1[NC], newn[NC];
+                const double2* c2[NC];
+                bool any_act = false;
+    #pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    cl[c] = base + c * ngroups + grp;
+                    const bool valid = cl[c] < ncl;
+                    p[c] = -1;
+                    if (valid) {
+                        p[c] = pos[cl[c]];
+                        if (c_lo + cl[c] == pcol) {
+                            p[c] = k;
+                            if (lig == 0) pos[cl[c]] = k;
+                        } else if (p[c] == k) {  // virtual swap: the column at position k takes the pivot's place
+                            p[c] = ppos;
+                            if (lig == 0) pos[cl[c]] = ppos;
                         }
                     }
-                    q = group_sum(q, L);
-                    if (need[c]) newn[c] = q;
+                    act[c] = valid && p[c] > k;
+                    any_act |= act[c];
+                    if (!act[c]) cl[c] = 0;
+                    c2[c] = reinterpret_cast<const double2*>(P + (size_t)cl[c] * ld);
+                    s[c] = 0.0;
+                    need[c] = false;
+                    f[c] = a_k[c] = n1[c] = newn[c] = 0.0;
                 }
-            }
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-                if (act[c] && lig == 0) {
-                    Fs[(size_t)cl[c] * FLD + j] = f[c];
-                    P[k + (size_t)cl[c] * ld] = a_k[c];
-                    if (n1[c] != 0.0) {
-                        nq1[cl[c]] = newn[c];
-                        if (need[c]) nq2[cl[c]] = newn[c];
+                if (any_act) {
+                    for (int i2 = (k >> 1) + lig; i2 < npair; i2 += L) {
+                        const double2 vv = v2[i2];
+    #pragma unroll
+                        for (int c = 0; c < NC; c++)
+                            if (act[c]) {
+                                const double2 a = c2[c][i2];
+                                s[c] = fma(a.x, vv.x, s[c]);
+                                s[c] = fma(a.y, vv.y, s[c]);
+                            }
                     }
-                    if (better(newn[c], p[c], best.val, best.pos)) best = Cand{newn[c], p[c], c_lo + cl[c]};
                 }
+                bool any_need = false;
+    #pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    s[c] = group_sum(s[c], L);
+                    if (act[c]) {
+                        const double* cj = P + (size_t)cl[c] * ld;
+                        const double* fr = Fs + (size_t)cl[c] * FLD;
+                        double corr = 0.0, rk = cj[k];
+                        for (int tt = 0; tt < j; tt++) {
+                            const double ft = fr[tt];
+                            corr = fma(ft, aux[tt], corr);
+                            rk = fma(-Vs[k + (size_t)tt * ldv], ft, rk);
+                        }
+                        f[c] = tau * (s[c] - corr);
+                        a_k[c] = rk - f[c];
+                        n1[c] = nq1[cl[c]];
+                        if (n1[c] != 0.0) {
+                            newn[c] = fmax(0.0, n1[c] - a_k[c] * a_k[c]);
+                            need[c] = newn[c] <= tol3z * nq2[cl[c]];
+                        }
+                    }
+                    any_need |= need[c];
+                }
+                if (__any_sync(FULL, any_need)) {
+    #pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        if (!__any_sync(FULL, need[c])) continue;
+                        double q = 0.0;
+                        if (need[c]) {
+                            const double* cj = P + (size_t)cl[c] * ld;
+                            const double* fr = Fs + (size_t)cl[c] * FLD;
+                            for (int i = k + 1 + lig; i < rows; i += L) {
+                                double u = cj[i];
+                                for (int tt = 0; tt < j; tt++) u -= Vs[i + (size_t)tt * ldv] * fr[tt];
+                                u -= vj[i] * f[c];
+                                q += u * u;
+                            }
+                        }
+                        q = group_sum(q, L);
+                        if (need[c]) newn[c] = q;
+                    }
+                }
+    #pragma unroll
+                for (int c = 0; c < NC; c++)
+                    if (act[c] && lig == 0) {
+                        Fs[(size_t)cl[c] * FLD + j] = f[c];
+                        P[k + (size_t)cl[c] * ld] = a_k[c];
+                        if (n1[c] != 0.0) {
+                            nq1[cl[c]] = newn[c];
+                            if (need[c]) nq2[cl[c]] = newn[c];
+                        }
+                        if (better(newn[c], p[c], best.val, best.pos)) best = Cand{newn[c], p[c], c_lo + cl[c]};
+                    }
+            }
         }
         if (k + 1 >= mn) break;  // factorization complete, rank = mn
         Cand lb = block_best(best, par);  // contains a block barrier: F and row k are visible below
@@ -519,7 +622,8 @@ void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol
                  int smem, cudaStream_t st) {
     if (nt <= 0) return;
     if (!in_smem) {
-        launch_one<8, 512, false>(t, nt, s, csize, tol, smem, st);
+        if (G <= 8) launch_one<8, 512, false>(t, nt, s, csize, tol, smem, st);
+        else launch_one<16, 512, false>(t, nt, s, csize, tol, smem, st);
         return;
     }
     if (nthreads <= 128) {

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -759,6 +760,9 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         std::vector<int> klass(tasks.size());
         std::vector<int> smem_need(tasks.size());
         const int kNB = 6;
+        // test hooks: force every task through one kernel shape (tests/test_gpu_parity.py)
+        const bool force_global = getenv("SPAND_RRQR_FORCE_GLOBAL") != nullptr;
+        const int force_g = getenv("SPAND_RRQR_FORCE_G") ? atoi(getenv("SPAND_RRQR_FORCE_G")) : 0;
         std::vector<int> per_color(ncolors, 0);
         for (int c : task_color) per_color[c]++;
         for (size_t i = 0; i < tasks.size(); i++) {
@@ -783,7 +787,7 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 return b;
             };
             long nd = config(128, 1, true);
-            if (t.rows <= 64 && nd <= kBuckets[2]) {
+            if (!force_global && force_g == 0 && t.rows <= 64 && nd <= kBuckets[2]) {
                 klass[i] = bucket_of(nd);
                 smem_need[i] = (int)nd;
                 continue;
@@ -792,10 +796,11 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             // panel needs to stay in shared memory.
             int want = 1;
             while (want < 16 && per_color[task_color[i]] * want < 296) want *= 2;
+            if (force_g > 0) want = force_g;
             int g = 0;
             while ((1 << g) < want) g++;
             int gi = -1, nt = 256;
-            for (; g <= 4 && gi < 0; g++) {
+            for (; g <= 4 && gi < 0 && !force_global; g++) {
                 nd = config(256, 1 << g, true);
                 if (nd <= kBuckets[4]) gi = g;
                 else if (nd <= MAXS) {
@@ -809,15 +814,15 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 smem_need[i] = (int)nd;
                 continue;
             }
-            // panel stays in the scratch arena: 8 CTAs stream their slabs from L2
-            nd = config(512, 8, false);
+            // panel stays in the scratch arena: 16 CTAs stream their slabs from L2
+            nd = config(512, 16, false);
             while (nd > MAXS && t.nb > 2) {
                 t.nb /= 2;
-                nd = config(512, 8, false);
+                nd = config(512, 16, false);
             }
             if (nd > MAXS) throw std::runtime_error("sparsify: interface cluster too large for the RRQR kernel");
             t.W = scratch_->alloc_n<double>((size_t)t.ld * t.maxcols);
-            klass[i] = (2 << 8) | (3 << 4) | bucket_of(nd);
+            klass[i] = (2 << 8) | (4 << 4) | bucket_of(nd);
             smem_need[i] = (int)nd;
         }
         // order tasks by (colour, class), stable

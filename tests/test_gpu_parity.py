@@ -165,6 +165,36 @@ def test_full_factorization_vs_oracle(n, d, L, tol, coords):
     assert np.linalg.norm(A @ xg - b) / np.linalg.norm(b) < 1e-11
 
 
+@pytest.mark.parametrize("env", [{"SPAND_RRQR_FORCE_GLOBAL": "1"}, {"SPAND_RRQR_FORCE_G": "1"}, {"SPAND_RRQR_FORCE_G": "2"},
+                                 {"SPAND_RRQR_FORCE_G": "4"}, {"SPAND_RRQR_FORCE_G": "8"}, {"SPAND_RRQR_FORCE_G": "16"}])
+def test_every_rrqr_kernel_shape_matches_oracle(env, monkeypatch):
+    """The RRQR launch shape (warp team, CTA, 2..16-CTA cluster with the panel in distributed shared memory, 16-CTA
+    cluster streaming the panel from global scratch) is picked from the task size; force each shape on one problem and
+    compare ranks / trailing matrix / residual with the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n, d, L, tol = 20, 3, 6, 1e-2
+    A, g, o = _pair(n, d, L, tol)
+    g.assemble(A)
+    o.assemble(A)
+    g.factorize()
+    o.factorize()
+    diff, ndiff = _rank_report(g, o)
+    assert ndiff <= max(2, 0.03 * len(diff)), (env, ndiff, abs(diff).max())
+    assert abs(g.nnz() - o.nnz()) <= 0.005 * o.nnz()
+    b = S.random(A.shape[0], 2019)
+    xg, xo = g.solve(b), o.solve(b)
+    rg = np.linalg.norm(A @ xg - b) / np.linalg.norm(b)
+    ro = np.linalg.norm(A @ xo - b) / np.linalg.norm(b)
+    assert rg <= 200 * tol and abs(rg - ro) <= 0.25 * ro
+    # exact configuration: the factorization must stay exact whatever the shape
+    A, g, o = _pair(12, 3, 4, 1e-14)
+    g.assemble(A)
+    g.factorize()
+    x = g.solve(b[:A.shape[0]])
+    assert np.linalg.norm(A @ x - b[:A.shape[0]]) / np.linalg.norm(b[:A.shape[0]]) <= 1e-10
+
+
 def test_solve_matches_oracle_when_factors_match():
     """Same factor (exact config) => GPU replay of the recorded operations equals the oracle's to rounding."""
     A, g, o = _pair(15, 3, 5, 0.0)
