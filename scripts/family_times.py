@@ -22,6 +22,8 @@ t.assemble(A); t.factorize()
 lg = t.log()
 out = {"config": desc, "factorize_s": t.factorize_seconds(), "families": t.family_stats(),
        "phases": {k: float(lg[k].sum()) for k in ("t_elim", "t_scale", "t_spars", "t_merge", "t_host")},
+       "plan": {k: [round(float(v), 4) for v in lg[k]] for k in ("t_plan_elim", "t_plan_scale", "t_plan_spars", "t_plan_merge")},
+       "dev": {k: [round(float(v), 4) for v in lg[k]] for k in ("t_elim", "t_scale", "t_spars", "t_merge")},
        "flops": {k: float(lg[k].sum()) for k in ("fl_pivot", "fl_panel", "fl_schur", "fl_rrqr_rank", "fl_rrqr_full")},
        "bytes": {k: float(lg[k].sum()) for k in ("by_scale", "by_rrqr", "by_merge")}}
 print(json.dumps(out))

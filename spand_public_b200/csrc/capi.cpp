@@ -30,7 +30,8 @@ int guarded(spand_tree* h, F&& f) {
 const char* kLogNames[] = {"dofs_nd", "dofs_left_nd", "dofs_left_elim", "dofs_left_spars", "fact_nnz", "rank_before",
                            "rank_after", "nspars", "ignored", "nbrs", "t_elim", "t_scale", "t_spars", "t_merge",
                            "fl_pivot", "fl_panel", "fl_schur", "fl_rrqr_rank", "fl_rrqr_full", "by_scale", "by_rrqr",
-                           "by_merge", "t_host", "launches", "wavefronts"};
+                           "by_merge", "t_host", "launches", "wavefronts", "t_plan_elim", "t_plan_scale", "t_plan_spars",
+                           "t_plan_merge"};
 constexpr int kLogFields = sizeof(kLogNames) / sizeof(kLogNames[0]);
 }  // namespace
 
@@ -136,7 +137,7 @@ int spand_get_log(spand_tree* t, double* out) {
                                 (double)g.rank_after, (double)g.nspars, (double)g.ignored, (double)g.nbrs, g.t_elim,
                                 g.t_scale, g.t_spars, g.t_merge, g.fl_pivot, g.fl_panel, g.fl_schur, g.fl_rrqr_rank,
                                 g.fl_rrqr_full, g.by_scale, g.by_rrqr, g.by_merge, g.t_host, (double)g.launches,
-                                (double)g.wavefronts};
+                                (double)g.wavefronts, g.t_plan_elim, g.t_plan_scale, g.t_plan_spars, g.t_plan_merge};
         std::memcpy(out + (size_t)kLogFields * l, v, sizeof(v));
     }
     return 0;

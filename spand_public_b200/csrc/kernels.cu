@@ -1,6 +1,7 @@
 // sm_100a kernels for the spaND factorization hot path. See kernels.cuh for the mapping to the
 // reference's BLAS/LAPACK call sites. All matrices are FP64, column-major.
 #include <cfloat>
+#include <climits>
 #include <cstdio>
 
 #include "kernels.cuh"
@@ -73,7 +74,12 @@ __global__ void __launch_bounds__(NB) trsm_step_kernel(const TrsmTask* __restric
         for (int p = 0; p < nb; p++)
             if (tid >= p && tid < nb) Ts[p * LDS + tid] = T[tid + (size_t)p * t.ldt];
     }
-    if (MODE == TRSM_LLN) {
+    if (MODE == TRSM_LLU) {
+        if (tid < nb) Ts[tid * LDS + tid] = 1.0;
+    } else if (t.diag != nullptr) {
+        if (tid < nb) Ts[tid * LDS + tid] = t.diag[j0 + tid];
+    }
+    if (MODE == TRSM_LLN || MODE == TRSM_LLU) {
         // X = B[j0:j0+nb, f0:f0+fw]; Xs[c*LDS + i]
         double* B = t.B + j0 + (size_t)f0 * t.ldb;
         for (int c = 0; c < fw; c++)
@@ -104,6 +110,243 @@ __global__ void __launch_bounds__(NB) trsm_step_kernel(const TrsmTask* __restric
             }
             for (int j = 0; j < nb; j++) B[tid + (size_t)j * t.ldb] = Xs[j * LDS + tid];
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// GETRF with partial pivoting (dgetrf semantics: first maximal |a| wins) + split_LU (src/util.cpp:213-227).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_entry(double* A, int ld, int i, int j, const double* d) {
+    // d = diag of the LAPACK factor. L(i,j) = l_ij |d_j|^1/2 ; U(i,j) = s_i (u_ij / d_i), s_i = sign(d_i) |d_i|^1/2
+    double a = A[i + (size_t)j * ld];
+    if (i > j) A[i + (size_t)j * ld] = a * sqrt(fabs(d[j]));
+    else if (i < j) {
+        double di = d[i];
+        double si = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sqrt(fabs(di));
+        A[i + (size_t)j * ld] = si * ((1.0 / di) * a);
+    } else A[i + (size_t)j * ld] = sqrt(fabs(a));
+}
+
+__global__ void __launch_bounds__(NB) getrf_small_kernel(const GetrfTask* __restrict__ tasks, int* err) {
+    GetrfTask t = tasks[blockIdx.x];
+    const int n = t.n;
+    if (n <= 0) return;
+    __shared__ double S[NB * LDS];  // S[j * LDS + i] = A(i, j)
+    __shared__ double dd[NB];
+    __shared__ int piv_s, prm[NB];
+    const int i = threadIdx.x;
+    for (int j = 0; j < n; j++)
+        if (i < n) S[j * LDS + i] = t.A[i + (size_t)j * t.ld];
+    if (i < n) prm[i] = i;
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        // pivot search: first row with the largest |a_ik|, i >= k (two warps)
+        double v = (i >= k && i < n) ? fabs(S[k * LDS + i]) : -1.0;
+        int idx = i;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) {
+                v = ov;
+                idx = oi;
+            }
+        }
+        __shared__ double wv[2];
+        __shared__ int wi[2];
+        if ((i & 31) == 0) {
+            wv[i >> 5] = v;
+            wi[i >> 5] = idx;
+        }
+        __syncthreads();
+        if (i == 0) {
+            int p = (wv[1] > wv[0]) ? wi[1] : wi[0];  // ties: warp 0 holds the smaller indices
+            piv_s = p;
+            t.ipiv[k] = p;
+            int tmp = prm[p];
+            prm[p] = prm[k];
+            prm[k] = tmp;
+        }
+        __syncthreads();
+        const int p = piv_s;
+        if (p != k && i < n) {  // swap rows k and p (thread i = column i)
+            double a = S[i * LDS + k];
+            S[i * LDS + k] = S[i * LDS + p];
+            S[i * LDS + p] = a;
+        }
+        __syncthreads();
+        const double akk = S[k * LDS + k];
+        if (akk == 0.0) {
+            if (i == 0) atomicOr(err, 2);  // dgetrf info > 0: exactly singular
+        } else if (i > k && i < n) {
+            double l = S[k * LDS + i] / akk;
+            S[k * LDS + i] = l;
+            for (int j = k + 1; j < n; j++) S[j * LDS + i] -= l * S[j * LDS + k];
+        }
+        __syncthreads();
+    }
+    if (i < n) {
+        dd[i] = S[i * LDS + i];
+        t.perm[i] = prm[i];
+    }
+    __syncthreads();
+    if (i < n) {
+        double di = dd[i];
+        t.ud[i] = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sqrt(fabs(di));
+    }
+    for (int j = 0; j < n; j++)
+        if (i < n) {
+            double a = S[j * LDS + i], o;
+            if (i > j) o = a * sqrt(fabs(dd[j]));
+            else if (i < j) {
+                double di = dd[i];
+                double si = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sqrt(fabs(di));
+                o = si * ((1.0 / di) * a);
+            } else o = sqrt(fabs(a));
+            t.A[i + (size_t)j * t.ld] = o;
+        }
+}
+
+// Panel [j0, j0 + nbp) x rows [j0, n) of every matrix with n > j0, factored in place (global memory / L2).
+constexpr int GP_T = 256;
+__global__ void __launch_bounds__(GP_T) getrf_panel_kernel(const GetrfTask* __restrict__ tasks, int j0, int* err) {
+    GetrfTask t = tasks[blockIdx.x];
+    const int n = t.n;
+    if (n <= j0) return;
+    const int nbp = min(NB, n - j0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double wv[GP_T / 32];
+    __shared__ int wi[GP_T / 32];
+    __shared__ int piv_s;
+    __shared__ double rowk[NB];
+    double* A = t.A;
+    const size_t ld = t.ld;
+    for (int c = 0; c < nbp; c++) {
+        const int col = j0 + c;
+        double v = -1.0;
+        int idx = INT_MAX;
+        for (int r = col + tid; r < n; r += GP_T) {
+            double a = fabs(A[r + col * ld]);
+            if (a > v) {  // rows visited in increasing order: keeps the first maximum
+                v = a;
+                idx = r;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) {
+                v = ov;
+                idx = oi;
+            }
+        }
+        if (lane == 0) {
+            wv[warp] = v;
+            wi[warp] = idx;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double bv = wv[0];
+            int bi = wi[0];
+            for (int w = 1; w < GP_T / 32; w++)
+                if (wv[w] > bv || (wv[w] == bv && wi[w] < bi)) {
+                    bv = wv[w];
+                    bi = wi[w];
+                }
+            piv_s = bi;
+            t.ipiv[col] = bi;
+        }
+        __syncthreads();
+        const int p = piv_s;
+        if (tid < nbp) {  // swap inside the panel, keep the (new) pivot row in shared memory
+            double a = A[col + (j0 + tid) * ld], b = A[p + (j0 + tid) * ld];
+            if (p != col) {
+                A[col + (j0 + tid) * ld] = b;
+                A[p + (j0 + tid) * ld] = a;
+            } else b = a;
+            rowk[tid] = b;
+        }
+        __syncthreads();
+        const double akk = rowk[c];
+        if (akk == 0.0) {
+            if (tid == 0) atomicOr(err, 2);
+            continue;
+        }
+        const int nr = n - col - 1, ncc = nbp - c - 1;
+        for (int r = tid; r < nr; r += GP_T) A[col + 1 + r + col * ld] /= akk;
+        __syncthreads();
+        for (int e = tid; e < nr * ncc; e += GP_T) {
+            int r = e % nr, cc = e / nr;
+            A[col + 1 + r + (col + 1 + cc) * ld] -= A[col + 1 + r + col * ld] * rowk[c + 1 + cc];
+        }
+        __syncthreads();
+    }
+}
+
+// Row swaps of panel j0 applied to the columns outside the panel; thread per column.
+__global__ void __launch_bounds__(128) getrf_laswp_kernel(const GetrfTask* __restrict__ tasks, int j0) {
+    GetrfTask t = tasks[blockIdx.x];
+    const int n = t.n;
+    if (n <= j0) return;
+    const int nbp = min(NB, n - j0);
+    int c = blockIdx.y * 128 + threadIdx.x;  // index among the n - nbp outside columns
+    if (c >= n - nbp) return;
+    if (c >= j0) c += nbp;
+    double* col = t.A + (size_t)c * t.ld;
+    for (int k = j0; k < j0 + nbp; k++) {
+        int p = t.ipiv[k];
+        if (p != k) {
+            double a = col[k];
+            col[k] = col[p];
+            col[p] = a;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) getrf_finish_kernel(const GetrfTask* __restrict__ tasks) {
+    GetrfTask t = tasks[blockIdx.x];
+    const int n = t.n;
+    if (n <= NB) return;  // small pivots were finished by getrf_small_kernel
+    extern __shared__ double dfin[];  // n: the LAPACK diagonal
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += 256) dfin[i] = t.A[i + (size_t)i * t.ld];
+    if (tid == 0) {  // swap2perm (src/util.cpp:76-88)
+        for (int i = 0; i < n; i++) t.perm[i] = i;
+        for (int i = 0; i < n; i++) {
+            int p = t.ipiv[i];
+            int tmp = t.perm[p];
+            t.perm[p] = t.perm[i];
+            t.perm[i] = tmp;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        double di = dfin[i];
+        t.ud[i] = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sqrt(fabs(di));
+    }
+    for (size_t e = tid; e < (size_t)n * n; e += 256) split_entry(t.A, t.ld, (int)(e % n), (int)(e / n), dfin);
+}
+
+__global__ void __launch_bounds__(128) rowperm_kernel(const RowPermTask* __restrict__ tasks) {
+    RowPermTask t = tasks[blockIdx.x];
+    extern __shared__ double pbuf[];  // n x w strip
+    const int n = t.n;
+    if (n == 0 || t.m == 0) return;
+    const int w = max(1, min(t.m, 6144 / n));
+    for (int c0 = 0; c0 < t.m; c0 += w) {
+        const int cw = min(w, t.m - c0);
+        for (int e = threadIdx.x; e < n * cw; e += 128) {
+            int i = e % n, c = e / n;
+            pbuf[e] = t.B[t.perm[i] + (size_t)(c0 + c) * t.ldb];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < n * cw; e += 128) {
+            int i = e % n, c = e / n;
+            t.B[i + (size_t)(c0 + c) * t.ldb] = pbuf[e];
+        }
+        __syncthreads();
     }
 }
 
@@ -296,6 +539,19 @@ __global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__
     const double* T = t.T;
     double* x = t.x;
     int nblk = (n + SV_B - 1) / SV_B;
+    if (trans == 0 && t.perm != nullptr) {  // x <- x[perm]  (P^T of ScalingPLUQ::fwd, operations.cpp)
+        double tmp[32];
+        for (int r = 0; r < 32; r++) {
+            int i = tid + r * SV_T;
+            tmp[r] = (i < n) ? x[t.perm[i]] : 0.0;
+        }
+        __syncthreads();
+        for (int r = 0; r < 32; r++) {
+            int i = tid + r * SV_T;
+            if (i < n) x[i] = tmp[r];
+        }
+        __syncthreads();
+    }
     if (trans == 0) {
         for (int b = 0; b < nblk; b++) {
             int j0 = b * SV_B, nb = min(SV_B, n - j0);
@@ -347,7 +603,8 @@ __global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__
             if (warp == 0) {
                 double xi = (lane < nb) ? x[j0 + lane] : 0.0;
                 for (int j = nb - 1; j >= 0; j--) {
-                    double xj = __shfl_sync(0xffffffffu, xi, j) / T[(j0 + j) + (size_t)(j0 + j) * t.ld];
+                    double dj = t.diag ? t.diag[j0 + j] : T[(j0 + j) + (size_t)(j0 + j) * t.ld];
+                    double xj = __shfl_sync(0xffffffffu, xi, j) / dj;
                     if (lane == j) xi = xj;
                     if (lane < j) xi -= T[(j0 + lane) + (size_t)(j0 + j) * t.ld] * xj;
                 }
@@ -479,11 +736,37 @@ void launch_trsm_step(int mode, const TrsmTask* t, int nt, int j0, int max_m, cu
         cudaFuncSetAttribute(trsm_step_kernel<TRSM_RLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(trsm_step_kernel<TRSM_LLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(trsm_step_kernel<TRSM_RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(trsm_step_kernel<TRSM_LLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
     if (mode == TRSM_RLT) trsm_step_kernel<TRSM_RLT><<<grid, NB, smem, st>>>(t, j0);
     else if (mode == TRSM_LLN) trsm_step_kernel<TRSM_LLN><<<grid, NB, smem, st>>>(t, j0);
+    else if (mode == TRSM_LLU) trsm_step_kernel<TRSM_LLU><<<grid, NB, smem, st>>>(t, j0);
     else trsm_step_kernel<TRSM_RUN><<<grid, NB, smem, st>>>(t, j0);
+}
+
+void launch_getrf_small(const GetrfTask* t, int nt, int* err, cudaStream_t st) {
+    if (nt > 0) getrf_small_kernel<<<nt, NB, 0, st>>>(t, err);
+}
+void launch_getrf_panel(const GetrfTask* t, int nt, int j0, int* err, cudaStream_t st) {
+    if (nt > 0) getrf_panel_kernel<<<nt, GP_T, 0, st>>>(t, j0, err);
+}
+void launch_getrf_laswp(const GetrfTask* t, int nt, int j0, int max_n, cudaStream_t st) {
+    if (nt <= 0 || max_n <= NB) return;
+    dim3 grid(nt, (max_n + 127) / 128);
+    getrf_laswp_kernel<<<grid, 128, 0, st>>>(t, j0);
+}
+void launch_getrf_finish(const GetrfTask* t, int nt, cudaStream_t st) {
+    if (nt <= 0) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(getrf_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        configured = true;
+    }
+    getrf_finish_kernel<<<nt, 256, 128 * 1024, st>>>(t);
+}
+void launch_rowperm(const RowPermTask* t, int nt, cudaStream_t st) {
+    if (nt > 0) rowperm_kernel<<<nt, 128, 6144 * sizeof(double) + 64, st>>>(t);
 }
 
 void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const int* tile_prefix, int total_tiles,

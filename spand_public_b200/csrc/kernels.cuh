@@ -28,6 +28,7 @@ enum TrsmMode {
     TRSM_RLT = 0,  // B (m x n) <- B T^-T, T lower n x n      (out-edge of an LLT pivot)
     TRSM_LLN = 1,  // B (n x m) <- T^-1 B, T lower n x n      (in-edge of an LLT / PLU pivot)
     TRSM_RUN = 2,  // B (m x n) <- B T^-1, T upper n x n      (out-edge of a PLU pivot)
+    TRSM_LLU = 3,  // B (n x m) <- T^-1 B, T unit lower       (U12 inside the blocked GETRF)
 };
 
 struct TrsmTask {
@@ -36,6 +37,23 @@ struct TrsmTask {
     int ldb, ldt;
     int m;  // free dimension of B
     int n;  // triangle dimension
+    const double* diag;  // nullptr: diagonal of T; else the n diagonal entries (PLU keeps diag(U) beside the block)
+};
+
+// PLU pivot (src/util.cpp:183-227): on exit A holds L (lower, with its non-unit diagonal |d|^1/2) and the strictly
+// upper part of U; ud = diag(U) = sign(d) |d|^1/2; ipiv = LAPACK swap sequence (0-based); perm = swap2perm(ipiv).
+struct GetrfTask {
+    double* A;
+    int ld, n;
+    double* ud;
+    int* ipiv;
+    int* perm;
+};
+
+struct RowPermTask {  // B (n x m) <- B[perm, :]
+    double* B;
+    int ldb, n, m;
+    const int* perm;
 };
 
 struct GemmContrib {
@@ -87,6 +105,8 @@ struct TrsvTask {
     const double* T;
     double* x;
     int ld, n;
+    const double* diag;  // upper solve only: diag(U) kept beside the block (nullptr: diagonal of T)
+    const int* perm;     // forward solve only: x <- x[perm] first (P^T of PLU), nullptr: none
 };
 
 struct GemvContrib {
@@ -116,6 +136,15 @@ struct XCopyTask {
 // All launchers are asynchronous on `st`. `err` is a device int: bit 0 = non-SPD pivot.
 void launch_potrf_step(const PotrfTask* t, int nt, int j0, int* err, cudaStream_t st);
 void launch_trsm_step(int mode, const TrsmTask* t, int nt, int j0, int max_m, cudaStream_t st);
+// GETRF with partial pivoting. n <= 64: one launch does everything (factor, split_LU, perm). Larger: right-looking
+// over 64-wide panels: launch_getrf_panel (pivoting inside the panel) -> launch_getrf_laswp (row swaps outside the
+// panel) -> TRSM_LLU + GEMM from the host driver -> launch_getrf_finish (split_LU + swap2perm) at the end.
+// err bit 1 = exactly singular pivot.
+void launch_getrf_small(const GetrfTask* t, int nt, int* err, cudaStream_t st);
+void launch_getrf_panel(const GetrfTask* t, int nt, int j0, int* err, cudaStream_t st);
+void launch_getrf_laswp(const GetrfTask* t, int nt, int j0, int max_n, cudaStream_t st);
+void launch_getrf_finish(const GetrfTask* t, int nt, cudaStream_t st);
+void launch_rowperm(const RowPermTask* t, int nt, cudaStream_t st);
 // tile_prefix: nt + 1 exclusive prefix of ceil(m/64)*ceil(n/64); total_tiles = tile_prefix[nt]
 void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const int* tile_prefix, int total_tiles,
                        cudaStream_t st);

@@ -407,7 +407,7 @@ void Tree::run_potrf(std::vector<PotrfTask>& tasks, LevelLog& lg) {
         for (auto& t : tasks) {
             int rem = t.n - j0 - NB;
             if (rem <= 0) continue;
-            TrsmTask p;
+            TrsmTask p{};
             p.B = t.A + (j0 + NB) + (size_t)j0 * t.ld;
             p.T = t.A + j0 + (size_t)j0 * t.ld;
             p.ldb = p.ldt = t.ld;
@@ -495,7 +495,10 @@ void Tree::run_trsm(int mode, std::vector<TrsmTask>& all, LevelLog& lg) {
 // ELIMINATE — src/tree.cpp:895-967 for every cluster of level ilvl (mutually non-adjacent)
 // ------------------------------------------------------------------------------------------------
 void Tree::phase_eliminate(LevelLog& lg, SolveLevel& sl) {
-    if (scale_kind != LLT) throw std::runtime_error("PLU elimination is not implemented yet on the device path");
+    if (scale_kind == PLU) {
+        phase_eliminate_plu(lg, sl);
+        return;
+    }
     std::vector<int> E;
     for (int c : bottoms_[current_bottom_])
         if (cl_[c].level == ilvl_ && !cl_[c].eliminated) E.push_back(c);
@@ -511,7 +514,7 @@ void Tree::phase_eliminate(LevelLog& lg, SolveLevel& sl) {
         if (!cs.in.empty()) throw std::runtime_error("eliminate: unexpected in-edges on an SPD interior");
         for (size_t k = 1; k < cs.out.size(); k++) {
             const Edge& e = ed_[cs.out[k]];
-            TrsmTask t;
+            TrsmTask t{};
             t.B = e.A;
             t.ldb = e.ld;
             t.T = piv.A;
@@ -657,11 +660,352 @@ void Tree::phase_eliminate(LevelLog& lg, SolveLevel& sl) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// GEN / PLU variants (src/tree.cpp:614-689, :735-742, :929-956, :838-853; src/util.cpp:183-227)
+// ------------------------------------------------------------------------------------------------
+void Tree::run_getrf(std::vector<GetrfTask>& tasks, LevelLog& lg) {
+    if (tasks.empty()) return;
+    std::vector<GetrfTask> small, big;
+    int maxn = 0;
+    for (auto& t : tasks) {
+        if (t.n <= 0) continue;
+        if (t.n > 4096) throw std::runtime_error("PLU pivot larger than 4096 is not supported by the solve kernels");
+        if (t.n <= NB) small.push_back(t);
+        else {
+            big.push_back(t);
+            maxn = std::max(maxn, t.n);
+        }
+    }
+    if (!small.empty()) {
+        GetrfTask* dt = to_device(small, scratch_);
+        auto ev = fam_begin(F_POTRF);
+        launch_getrf_small(dt, (int)small.size(), d_err_, st_);
+        fam_end(F_POTRF, ev);
+        lg.launches++;
+    }
+    if (big.empty()) return;
+    GetrfTask* dt = to_device(big, scratch_);
+    for (int j0 = 0; j0 < maxn; j0 += NB) {
+        auto ev = fam_begin(F_POTRF);
+        launch_getrf_panel(dt, (int)big.size(), j0, d_err_, st_);
+        launch_getrf_laswp(dt, (int)big.size(), j0, maxn, st_);
+        fam_end(F_POTRF, ev);
+        lg.launches += 2;
+        std::vector<TrsmTask> u12;
+        std::vector<GemmTask> upd;
+        std::vector<GemmContrib> con;
+        int max_m = 0;
+        for (auto& t : big) {
+            int rem = t.n - j0 - NB;
+            if (rem <= 0) continue;
+            TrsmTask p{};
+            p.B = t.A + j0 + (size_t)(j0 + NB) * t.ld;  // U12: NB x rem
+            p.T = t.A + j0 + (size_t)j0 * t.ld;
+            p.ldb = p.ldt = t.ld;
+            p.m = rem;
+            p.n = NB;
+            u12.push_back(p);
+            max_m = std::max(max_m, rem);
+            GemmTask g;
+            g.C = t.A + (j0 + NB) + (size_t)(j0 + NB) * t.ld;
+            g.ldc = t.ld;
+            g.m = g.n = rem;
+            g.c0 = (int)con.size();
+            g.nc = 1;
+            g.flags = GEMM_NN;
+            upd.push_back(g);
+            con.push_back({t.A + (j0 + NB) + (size_t)j0 * t.ld, p.B, t.ld, t.ld, NB});
+        }
+        if (u12.empty()) break;
+        TrsmTask* dp = to_device(u12, scratch_);
+        ev = fam_begin(F_TRSM);
+        launch_trsm_step(TRSM_LLU, dp, (int)u12.size(), 0, max_m, st_);
+        fam_end(F_TRSM, ev);
+        lg.launches++;
+        run_gemm(upd, con, lg);
+    }
+    auto ev = fam_begin(F_POTRF);
+    launch_getrf_finish(dt, (int)big.size(), st_);
+    fam_end(F_POTRF, ev);
+    lg.launches++;
+}
+
+void Tree::run_rowperm(std::vector<RowPermTask>& tasks, LevelLog& lg) {
+    if (tasks.empty()) return;
+    for (auto& t : tasks)
+        if (t.n > 6144) throw std::runtime_error("PLU pivot larger than 6144 is not supported by the row permutation kernel");
+    RowPermTask* dt = to_device(tasks, scratch_);
+    auto ev = fam_begin(F_TRSM);
+    launch_rowperm(dt, (int)tasks.size(), st_);
+    fam_end(F_TRSM, ev);
+    lg.launches++;
+}
+
+void Tree::alloc_plu(Cluster& cs) {
+    size_t n = std::max(1, cs.size);
+    cs.ud = arena_->alloc_n<double>(n);
+    cs.ipiv = arena_->alloc_n<int>(n);
+    cs.perm = arena_->alloc_n<int>(n);
+}
+
+void Tree::phase_eliminate_plu(LevelLog& lg, SolveLevel& sl) {
+    std::vector<int> E;
+    for (int c : bottoms_[current_bottom_])
+        if (cl_[c].level == ilvl_ && !cl_[c].eliminated) E.push_back(c);
+    if (E.empty()) return;
+    std::vector<GetrfTask> getrf;
+    std::vector<RowPermTask> rperm;
+    std::vector<TrsmTask> left, right;
+    for (int s : E) {
+        Cluster& cs = cl_[s];
+        const Edge& piv = ed_[cs.out[0]];
+        double n = cs.size;
+        alloc_plu(cs);
+        getrf.push_back({piv.A, piv.ld, cs.size, cs.ud, cs.ipiv, cs.perm});
+        lg.fl_pivot += 2.0 * n * n * n / 3.0;
+        for (int eid : cs.in) {  // A[s,n] <- L^-1 P^T A[s,n]   (tree.cpp:668-676)
+            const Edge& e = ed_[eid];
+            int w = cl_[e.n1].size;
+            rperm.push_back({e.A, e.ld, cs.size, w, cs.perm});
+            TrsmTask t{};
+            t.B = e.A;
+            t.ldb = e.ld;
+            t.T = piv.A;
+            t.ldt = piv.ld;
+            t.m = w;
+            t.n = cs.size;
+            left.push_back(t);
+            lg.fl_panel += (double)w * n * n;
+        }
+        for (size_t k = 1; k < cs.out.size(); k++) {  // A[n,s] <- A[n,s] U^-1   (tree.cpp:681-689, Q = I)
+            const Edge& e = ed_[cs.out[k]];
+            TrsmTask t{};
+            t.B = e.A;
+            t.ldb = e.ld;
+            t.T = piv.A;
+            t.ldt = piv.ld;
+            t.m = cl_[e.n2].size;
+            t.n = cs.size;
+            t.diag = cs.ud;
+            right.push_back(t);
+            lg.fl_panel += (double)t.m * n * n;
+        }
+    }
+    run_getrf(getrf, lg);
+    run_rowperm(rperm, lg);
+    run_trsm(TRSM_LLN, left, lg);
+    run_trsm(TRSM_RUN, right, lg);
+
+    // Schur complement A[n1,n2] -= A[n1,s] A[s,n2] for every (out, in) pair in the reference's loop order
+    // (tree.cpp:943-947); fill-in edges are created where gemm_edges would create them (:761-772).
+    struct Triple { int target, e1, e2; };
+    std::vector<Triple> triples;
+    std::vector<int> task_of_edge, targets;
+    std::vector<char> fresh;
+    for (int s : E) {
+        const std::vector<int>& out = cl_[s].out;
+        const std::vector<int>& in = cl_[s].in;
+        for (size_t a = 1; a < out.size(); a++) {
+            int e1 = out[a];
+            int n1 = ed_[e1].n2;
+            for (size_t b = 0; b < in.size(); b++) {
+                int e2 = in[b];
+                int n2 = ed_[e2].n1;
+                int tg = find_out(n2, n1);
+                bool is_new = false;
+                if (tg < 0) {
+                    double* A = arena_->alloc_n<double>((size_t)cl_[n1].size * cl_[n2].size);
+                    tg = new_edge(n2, n1, A, std::max(1, cl_[n1].size), false);
+                    cl_[n2].out.push_back(tg);
+                    cl_[n1].in.push_back(tg);
+                    is_new = true;
+                }
+                if ((int)task_of_edge.size() <= tg) task_of_edge.resize(ed_.size() + 1024, -1);
+                if (task_of_edge[tg] < 0) {
+                    task_of_edge[tg] = (int)targets.size();
+                    targets.push_back(tg);
+                    fresh.push_back(is_new);
+                }
+                triples.push_back({tg, e1, e2});
+            }
+        }
+    }
+    {
+        std::vector<GemmTask> tasks(targets.size());
+        std::vector<int> count(targets.size(), 0);
+        for (auto& t : triples) count[task_of_edge[t.target]]++;
+        int off = 0;
+        for (size_t i = 0; i < targets.size(); i++) {
+            const Edge& e = ed_[targets[i]];
+            GemmTask& g = tasks[i];
+            g.C = e.A;
+            g.ldc = e.ld;
+            g.m = cl_[e.n2].size;
+            g.n = cl_[e.n1].size;
+            g.c0 = off;
+            g.nc = 0;
+            g.flags = GEMM_NN | (fresh[i] ? GEMM_ZERO_INIT : 0);
+            off += count[i];
+        }
+        std::vector<GemmContrib> con(triples.size());
+        for (auto& t : triples) {
+            GemmTask& g = tasks[task_of_edge[t.target]];
+            const Edge& a = ed_[t.e1];  // A[n1,s]
+            const Edge& b = ed_[t.e2];  // A[s,n2]
+            int k = cl_[a.n1].size;
+            con[g.c0 + g.nc++] = {a.A, b.A, a.ld, b.ld, k};
+            lg.fl_schur += 2.0 * g.m * g.n * k;
+        }
+        run_gemm(tasks, con, lg);
+    }
+
+    // recorded operations: ScalingPLUQ, GemmOut (forward only), GemmIn (backward only)
+    std::vector<TrsvTask> trsv;
+    std::map<int, std::vector<GemvContrib>> fwd_by_target;
+    std::vector<GemvTask> bwd_tasks;
+    std::vector<GemvContrib> bwd_con;
+    for (int s : E) {
+        Cluster& cs = cl_[s];
+        const Edge& piv = ed_[cs.out[0]];
+        trsv.push_back({piv.A, cs.x, piv.ld, cs.size, cs.ud, cs.perm});
+        nnz_ += (long long)cs.size * cs.size + 2LL * cs.size;
+        for (size_t k = 1; k < cs.out.size(); k++) {
+            const Edge& e = ed_[cs.out[k]];
+            int nsz = cl_[e.n2].size;
+            nnz_ += (long long)cs.size * nsz;
+            if (nsz == 0 || cs.size == 0) continue;
+            fwd_by_target[e.n2].push_back({e.A, cs.x, e.ld, cs.size});
+        }
+        GemvTask bt;
+        bt.y = cs.x;
+        bt.m = cs.size;
+        bt.c0 = (int)bwd_con.size();
+        bt.nc = 0;
+        for (int eid : cs.in) {
+            const Edge& e = ed_[eid];
+            int nsz = cl_[e.n1].size;
+            nnz_ += (long long)cs.size * nsz;
+            if (nsz == 0 || cs.size == 0) continue;
+            bwd_con.push_back({e.A, cl_[e.n1].x, e.ld, nsz});  // x_s -= A[s,n] x_n  (no transpose)
+            bt.nc++;
+        }
+        if (bt.nc > 0) bwd_tasks.push_back(bt);
+    }
+    std::vector<GemvTask> fwd_tasks;
+    std::vector<GemvContrib> fwd_con;
+    for (auto& kv : fwd_by_target) {
+        GemvTask t;
+        t.y = cl_[kv.first].x;
+        t.m = cl_[kv.first].size;
+        t.c0 = (int)fwd_con.size();
+        t.nc = (int)kv.second.size();
+        fwd_con.insert(fwd_con.end(), kv.second.begin(), kv.second.end());
+        fwd_tasks.push_back(t);
+    }
+    sl.e_trsv = to_device(trsv, arena_);
+    sl.n_e_trsv = (int)trsv.size();
+    sl.e_gemv_f = to_device(fwd_tasks, arena_);
+    sl.e_gemv_fc = to_device(fwd_con, arena_);
+    sl.n_e_gemv_f = (int)fwd_tasks.size();
+    sl.e_gemv_b = to_device(bwd_tasks, arena_);
+    sl.e_gemv_bc = to_device(bwd_con, arena_);
+    sl.n_e_gemv_b = (int)bwd_tasks.size();
+
+    // set_eliminated (cluster.cpp:32-45): drop the cluster's out-edges and in-edges from their other endpoints
+    std::vector<int> touched;
+    for (int s : E) {
+        Cluster& cs = cl_[s];
+        for (int e : cs.out) {
+            ed_[e].alive = false;
+            if (ed_[e].n2 != s) touched.push_back(ed_[e].n2);
+        }
+        for (int e : cs.in) {
+            ed_[e].alive = false;
+            touched.push_back(ed_[e].n1);
+        }
+        cs.out.clear();
+        cs.in.clear();
+        cs.eliminated = true;
+    }
+    std::sort(touched.begin(), touched.end());
+    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+    for (int n : touched) {
+        auto& in = cl_[n].in;
+        in.erase(std::remove_if(in.begin(), in.end(), [&](int e) { return !ed_[e].alive; }), in.end());
+        auto& out = cl_[n].out;
+        out.erase(std::remove_if(out.begin(), out.end(), [&](int e) { return !ed_[e].alive; }), out.end());
+    }
+}
+
+void Tree::phase_scale_plu(LevelLog& lg, SolveLevel& sl) {
+    std::vector<GetrfTask> getrf;
+    std::vector<RowPermTask> rperm;
+    std::vector<TrsmTask> right, left;
+    std::vector<TrsvTask> trsv;
+    const std::vector<int>& bottom = bottoms_[current_bottom_];
+    for (int c : bottom) {
+        Cluster& cs = cl_[c];
+        if (cs.eliminated || cs.level <= ilvl_) continue;
+        alloc_plu(cs);
+    }
+    for (int c : bottom) {
+        Cluster& cs = cl_[c];
+        if (cs.eliminated || cs.level <= ilvl_) continue;
+        Edge& piv = ed_[cs.out[0]];
+        double n = cs.size;
+        getrf.push_back({piv.A, piv.ld, cs.size, cs.ud, cs.ipiv, cs.perm});
+        trsv.push_back({piv.A, cs.x, piv.ld, cs.size, cs.ud, cs.perm});
+        nnz_ += (long long)cs.size * cs.size + 2LL * cs.size;
+        lg.fl_pivot += 2.0 * n * n * n / 3.0;
+        lg.by_scale += 16.0 * n * n;
+        for (size_t k = 1; k < cs.out.size(); k++) {
+            const Edge& e = ed_[cs.out[k]];
+            const Cluster& c2 = cl_[e.n2];
+            const Edge& piv2 = ed_[c2.out[0]];
+            // block A[n2,n1] (|n2| x |n1|): out-edge of n1 -> B U_n1^-1 ; in-edge of n2 -> L_n2^-1 P_n2^T B
+            TrsmTask r{};
+            r.B = e.A;
+            r.ldb = e.ld;
+            r.T = piv.A;
+            r.ldt = piv.ld;
+            r.m = c2.size;
+            r.n = cs.size;
+            r.diag = cs.ud;
+            right.push_back(r);
+            rperm.push_back({e.A, e.ld, c2.size, cs.size, c2.perm});
+            TrsmTask l{};
+            l.B = e.A;
+            l.ldb = e.ld;
+            l.T = piv2.A;
+            l.ldt = piv2.ld;
+            l.m = cs.size;
+            l.n = c2.size;
+            left.push_back(l);
+            lg.fl_panel += (double)c2.size * n * n + (double)cs.size * c2.size * c2.size;
+            lg.by_scale += 16.0 * c2.size * n;
+        }
+    }
+    run_getrf(getrf, lg);
+    run_trsm(TRSM_RUN, right, lg);
+    run_rowperm(rperm, lg);
+    run_trsm(TRSM_LLN, left, lg);
+    for (int c : bottom) {
+        Cluster& cs = cl_[c];
+        if (cs.eliminated || cs.level <= ilvl_) continue;
+        ed_[cs.out[0]].identity = true;  // tree.cpp:848 — never materialised
+    }
+    sl.s_trsv = to_device(trsv, arena_);
+    sl.n_s_trsv = (int)trsv.size();
+}
+
+// ------------------------------------------------------------------------------------------------
 // SCALE — src/tree.cpp:796-856 for every remaining cluster: pivot = L L^T, every incident block
 // A[n2,n1] <- L_n2^-1 A[n2,n1] L_n1^-T, pivot := I (kept implicit)
 // ------------------------------------------------------------------------------------------------
 void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
-    if (scale_kind != LLT) throw std::runtime_error("PLU scaling is not implemented yet on the device path");
+    if (scale_kind == PLU) {
+        phase_scale_plu(lg, sl);
+        return;
+    }
     std::vector<PotrfTask> potrf;
     std::vector<TrsmTask> right, left;
     std::vector<TrsvTask> trsv;
@@ -704,6 +1048,7 @@ void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
 // obtained by wavefronts of the dependency DAG; clusters of one wavefront are mutually non-adjacent.
 // ------------------------------------------------------------------------------------------------
 void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
+    const double plan0 = wtime();
     const std::vector<int>& bottom = bottoms_[current_bottom_];
     std::vector<int> S;
     for (int c : bottom) {
@@ -871,6 +1216,7 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             fam_end(F_RRQR, ev);
         }
         lg.wavefronts = ncolors;
+        lg.t_plan_spars = wtime() - plan0;
         // ranks back to the host: the one synchronisation of the level
         for (int c : bottom) old_size[c - first] = cl_[c].size;
         CK(cudaMemcpyAsync(h_csize_.data() + first, d_csize_ + first, sizeof(int) * span, cudaMemcpyDeviceToHost, st_));
@@ -902,7 +1248,8 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 house.push_back({t.V, t.tau, cs.x, t.rows, rank});
                 nnz_ += (long long)t.rows * t.rows;  // Orthogonal (operations.cpp:159-161)
                 long long m = t.rows - rank;
-                nnz_ += m * (m + 1) / 2;  // ScalingLLT(I) of the dropped sibling (tree.cpp:1342)
+                // Scaling op of the dropped sibling (tree.cpp:1342): ScalingLLT(I) or ScalingPLUQ(I, I, id, id)
+                nnz_ += scale_kind == PLU ? m * m + 2 * m : m * (m + 1) / 2;
                 cs.size = rank;
             }
             lg.rank_after += cs.size;
@@ -1078,12 +1425,16 @@ void Tree::factorize() {
         double h0 = wtime();
         if (verb) printf("Level %d, %d dofs left\n", ilvl_, ndofs_left());
         CK(cudaEventRecord(ev[ilvl_ * 5 + 0], st_));
+        double p0 = wtime();
         phase_eliminate(lg, sl);
+        lg.t_plan_elim = wtime() - p0;
         CK(cudaEventRecord(ev[ilvl_ * 5 + 1], st_));
         lg.dofs_left_elim = ndofs_left();
         if (ilvl_ == stop_level && stop_phase == 0) stopped = true;
         if (!stopped && ilvl_ >= skip) {
+            p0 = wtime();
             phase_scale(lg, sl);
+            lg.t_plan_scale = wtime() - p0;
             CK(cudaEventRecord(ev[ilvl_ * 5 + 2], st_));
             if (ilvl_ == stop_level && stop_phase == 1) stopped = true;
             if (!stopped) {
@@ -1097,7 +1448,9 @@ void Tree::factorize() {
             scratch_->reset();
         }
         CK(cudaEventRecord(ev[ilvl_ * 5 + 3], st_));
+        p0 = wtime();
         if (!stopped && ilvl_ < nlevels - 1) phase_merge(lg, sl);
+        lg.t_plan_merge = wtime() - p0;
         CK(cudaEventRecord(ev[ilvl_ * 5 + 4], st_));
         lg.dofs_left_spars = ndofs_left();
         lg.fact_nnz = nnz_;
@@ -1163,9 +1516,11 @@ void Tree::solve_device(double* x_dev) {
         SolveLevel& s = solve_[l];
         launch_xcopy(s.m_bwd, s.n_merge, st_);
         launch_house(s.house, s.n_house, 0, st_);
-        launch_trsv(s.s_trsv, s.n_s_trsv, 1, st_);
-        launch_gemv(s.e_gemv_b, s.n_e_gemv_b, s.e_gemv_bc, 1, st_);
-        launch_trsv(s.e_trsv, s.n_e_trsv, 1, st_);
+        // LLT: x <- L^-T x, x_s -= A[n,s]^T x_n ; PLU: x <- U^-1 x, x_s -= A[s,n] x_n   (operations.cpp bwd)
+        const bool plu = scale_kind == PLU;
+        launch_trsv(s.s_trsv, s.n_s_trsv, plu ? 2 : 1, st_);
+        launch_gemv(s.e_gemv_b, s.n_e_gemv_b, s.e_gemv_bc, plu ? 0 : 1, st_);
+        launch_trsv(s.e_trsv, s.n_e_trsv, plu ? 2 : 1, st_);
     }
     launch_scatter(N, d_perm_, xleaf, x_dev, st_);  // x = P b
 }

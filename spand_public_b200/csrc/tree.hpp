@@ -36,6 +36,7 @@ struct LevelLog {
     double by_scale = 0, by_rrqr = 0, by_merge = 0;
     // host planning time and launch counts
     double t_host = 0;
+    double t_plan_elim = 0, t_plan_scale = 0, t_plan_spars = 0, t_plan_merge = 0;  // host planning only (no waits)
     int launches = 0;
     int wavefronts = 0;
 };
@@ -127,6 +128,9 @@ class Tree {
         std::vector<int> out;        // edge ids, pivot first
         std::vector<int> in;         // edge ids
         double* x = nullptr;         // device solution segment (orig_size)
+        double* ud = nullptr;        // PLU: diag(U), swap sequence and permutation of the current pivot
+        int* ipiv = nullptr;
+        int* perm = nullptr;
     };
     struct Edge {
         int n1, n2;       // block A[rows of n2, cols of n1]
@@ -179,6 +183,11 @@ class Tree {
     void phase_scale(LevelLog& lg, SolveLevel& sl);
     void phase_sparsify(LevelLog& lg, SolveLevel& sl);
     void phase_merge(LevelLog& lg, SolveLevel& sl);
+    void phase_eliminate_plu(LevelLog& lg, SolveLevel& sl);
+    void phase_scale_plu(LevelLog& lg, SolveLevel& sl);
+    void run_getrf(std::vector<GetrfTask>& tasks, LevelLog& lg);
+    void run_rowperm(std::vector<RowPermTask>& tasks, LevelLog& lg);
+    void alloc_plu(Cluster& cs);
     void run_potrf(std::vector<PotrfTask>& tasks, LevelLog& lg);
     void run_trsm(int mode, std::vector<TrsmTask>& tasks, LevelLog& lg);
     void run_gemm(std::vector<GemmTask>& tasks, std::vector<GemmContrib>& contribs, LevelLog& lg);

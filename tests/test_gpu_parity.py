@@ -285,3 +285,124 @@ def test_large_blocks_exercise_tiled_kernels():
     xg, xo = g.solve(b), o.solve(b)
     assert np.linalg.norm(A @ xg - b) / np.linalg.norm(b) < 1e-12
     assert np.linalg.norm(xg - xo) <= 1e-11 * np.linalg.norm(xo)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GEN / PLU path (reference src/tree.cpp:614-689, :929-956; tests/tests.cpp:98-109 builds the unsymmetric matrices as
+# Laplacian + U(-0.1, 0.1) noise on every stored non-zero)
+# ---------------------------------------------------------------------------------------------------------------------
+def _unsym(A, seed):
+    rng = np.random.RandomState(seed)
+    B = A.copy().tocsc()
+    B.data = B.data + rng.uniform(-0.1, 0.1, B.nnz)
+    return B
+
+
+def _pair_gen(n, d, L, tol, skip=0, seed=7):
+    A = _unsym(S.neglapl(n, d), seed)
+    X = S.linspace_nd(n, d)
+    g = S.Tree(L)
+    g.set_tol(tol)
+    g.set_skip(skip)
+    g.set_symm_kind(S.GEN)
+    g.set_scaling_kind(S.PLU)
+    g.set_use_geo(True)
+    g.set_Xcoo(X)
+    o = O.OracleTree(L, tol=tol, skip=skip, symm_kind=O.GEN, scaling_kind=O.PLU)
+    o.set_coords(X)
+    G = S.symmetric_graph(A)
+    g.partition(G)
+    o.partition(G)
+    return A, g, o
+
+
+@pytest.mark.parametrize("n,d,L,tol", [(16, 2, 4, 1e-2), (8, 3, 3, 1e-2), (12, 3, 4, 0.0)])
+def test_plu_stop_points(n, d, L, tol):
+    """Trailing matrix after eliminate / scale / sparsify / merge of the first levels, GPU vs oracle (GEN, PLU)."""
+    A, g, o = _pair_gen(n, d, L, tol)
+    assert (g.get_assembly_perm() == o.perm()).all()
+    for lvl in range(min(L, 2)):
+        for ph in range(4):
+            g.set_stop(lvl, ph)
+            o.set_stop(lvl, ph)
+            g.assemble(A)
+            o.partition(S.symmetric_graph(A))
+            o.assemble(A)
+            g.factorize()
+            o.factorize()
+            Tg, To = g.get_trailing_mat(), o.trailing_mat()
+            assert Tg.shape == To.shape
+            ranks_equal = (g.stats()[2] == o.stats()[2]).all()
+            if ranks_equal:
+                err = abs(Tg - To).max() if Tg.nnz + To.nnz else 0.0
+                ref = abs(To).max() if To.nnz else 1.0
+                # after an RRQR the signs/rounding of R may differ slightly; before it the match is to rounding
+                lim = 1e-10 if (lvl == 0 and ph < 2) or tol == 0.0 else 1e-6
+                assert err <= lim * max(ref, 1.0), (lvl, ph, err, ref)
+            assert g.nnz() == o.nnz() or not ranks_equal
+
+
+@pytest.mark.parametrize("n,d,L,tol,skip", [(5, 2, 3, 1e-14, 0), (10, 2, 4, 1e-14, 4), (20, 2, 5, 0.0, 1000),
+                                            (5, 3, 3, 0.0, 0), (12, 3, 5, 1e-14, 0)])
+def test_plu_exact_residual(n, d, L, tol, skip):
+    """ApproxTest.Exact (tests/tests.cpp:562-609) for (GEN, PLU): one solve gives |Ax-b|/|b| <= 1e-10."""
+    A, g, o = _pair_gen(n, d, L, tol, skip)
+    g.assemble(A)
+    g.factorize()
+    b = S.random(A.shape[0], 2019)
+    x = g.solve(b)
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 1e-10
+
+
+@pytest.mark.parametrize("n,d,L,tol", [(32, 2, 5, 1e-2), (16, 3, 5, 1e-2), (20, 3, 6, 1e-3)])
+def test_plu_full_factorization_vs_oracle(n, d, L, tol):
+    A, g, o = _pair_gen(n, d, L, tol)
+    g.assemble(A)
+    o.assemble(A)
+    g.factorize()
+    o.factorize()
+    diff, ndiff = _rank_report(g, o)
+    assert ndiff <= max(2, 0.03 * len(diff)), (ndiff, abs(diff).max())
+    assert abs(g.nnz() - o.nnz()) <= 0.005 * o.nnz()
+    lg, lo = g.log(), o.log()
+    assert np.allclose(lg["dofs_left_spars"], lo["dofs_left_spars"], rtol=0.02, atol=4)
+    b = S.random(A.shape[0], 2019)
+    xg, xo = g.solve(b), o.solve(b)
+    rg = np.linalg.norm(A @ xg - b) / np.linalg.norm(b)
+    ro = np.linalg.norm(A @ xo - b) / np.linalg.norm(b)
+    assert rg <= 200 * tol and abs(rg - ro) <= 0.25 * ro
+
+
+def test_plu_large_pivots_blocked_getrf():
+    """Uncompressed top separators (576 and 24-wide strips) go through the blocked GETRF / laswp / TRSM_LLU path."""
+    A, g, o = _pair_gen(24, 3, 3, 0.0)
+    g.assemble(A)
+    o.assemble(A)
+    g.factorize()
+    o.factorize()
+    b = S.random(A.shape[0], 2019)
+    xg, xo = g.solve(b), o.solve(b)
+    assert np.linalg.norm(A @ xg - b) / np.linalg.norm(b) <= 1e-10
+    assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) <= 1e-9
+    assert g.nnz() == o.nnz()
+
+
+def test_plu_singular_pivot_raises():
+    """getf_cluster throws 'Error: Singular Pivot' (src/tree.cpp:625-628)."""
+    import scipy.sparse as sp
+    n = 8
+    A = S.neglapl(n, 2).tolil()
+    A[0, :] = 0.0
+    A[:, 0] = 0.0
+    A = sp.csc_matrix(A)
+    X = S.linspace_nd(n, 2)
+    g = S.Tree(2)
+    g.set_tol(0.0)
+    g.set_symm_kind(S.GEN)
+    g.set_scaling_kind(S.PLU)
+    g.set_use_geo(True)
+    g.set_Xcoo(X)
+    g.partition(S.symmetric_graph(S.neglapl(n, 2)))
+    g.assemble(A)
+    with pytest.raises(RuntimeError, match="Singular Pivot"):
+        g.factorize()
