@@ -131,7 +131,7 @@ int spand_log_fields(void) { return kLogFields; }
 const char* spand_log_field_name(int i) { return (i >= 0 && i < kLogFields) ? kLogNames[i] : ""; }
 int spand_get_log(spand_tree* t, double* out) {
     for (int l = 0; l < t->t.nlevels; l++) {
-        const LevelLog& g = t->t.log[l];
+        const LevelLog& g = t->t.logs()[l];
         double v[kLogFields] = {(double)g.dofs_nd, (double)g.dofs_left_nd, (double)g.dofs_left_elim,
                                 (double)g.dofs_left_spars, (double)g.fact_nnz, (double)g.rank_before,
                                 (double)g.rank_after, (double)g.nspars, (double)g.ignored, (double)g.nbrs, g.t_elim,

@@ -1,5 +1,6 @@
 // sm_100a kernels for the spaND factorization hot path. See kernels.cuh for the mapping to the
 // reference's BLAS/LAPACK call sites. All matrices are FP64, column-major.
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cstdio>
@@ -21,15 +22,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ------------------------------------------------------------------------------------------------
 // POTRF, one 64x64 diagonal block per CTA (left-looking, one thread per row).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NB) potrf_step_kernel(const PotrfTask* __restrict__ tasks, int j0, int* err) {
-    PotrfTask t = tasks[blockIdx.x];
-    int nb = min(NB, t.n - j0);
-    if (nb <= 0) return;
-    double* A = t.A + j0 + (size_t)j0 * t.ld;
+__device__ __forceinline__ void potrf_tile64(double* A, int ld, int nb, int* err) {
     __shared__ double S[NB * LDS];
     int i = threadIdx.x;
     for (int j = 0; j < nb; j++)
-        if (i < nb && i >= j) S[j * LDS + i] = A[i + (size_t)j * t.ld];
+        if (i < nb && i >= j) S[j * LDS + i] = A[i + (size_t)j * ld];
     __syncthreads();
     for (int k = 0; k < nb; k++) {
         double v = 0.0;
@@ -46,44 +43,47 @@ __global__ void __launch_bounds__(NB) potrf_step_kernel(const PotrfTask* __restr
         __syncthreads();
     }
     for (int j = 0; j < nb; j++)
-        if (i < nb && i >= j) A[i + (size_t)j * t.ld] = S[j * LDS + i];
+        if (i < nb && i >= j) A[i + (size_t)j * ld] = S[j * LDS + i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NB) potrf_step_kernel(const PotrfTask* __restrict__ tasks, int j0, int* err) {
+    PotrfTask t = tasks[blockIdx.x];
+    int nb = min(NB, t.n - j0);
+    if (nb <= 0) return;
+    potrf_tile64(t.A + j0 + (size_t)j0 * t.ld, t.ld, nb, err);
 }
 
 // ------------------------------------------------------------------------------------------------
 // TRSM against one 64x64 diagonal block of the triangle; CTA = (task, 64-wide strip of the free dim).
 // ------------------------------------------------------------------------------------------------
+// One (64-wide step of the triangle) x (64-wide strip of the free dimension). T points at the diagonal block, B at
+// the strip (LLN/LLU: nb x fw, rows = unknowns; RLT/RUN: fw x nb, columns = unknowns). 64 threads.
 template <int MODE>
-__global__ void __launch_bounds__(NB) trsm_step_kernel(const TrsmTask* __restrict__ tasks, int j0) {
-    TrsmTask t = tasks[blockIdx.x];
-    int nb = min(NB, t.n - j0);
-    int f0 = blockIdx.y * NB;  // offset in the free dimension
-    if (nb <= 0 || f0 >= t.m) return;
-    int fw = min(NB, t.m - f0);
-    extern __shared__ double trsm_smem[];
+__device__ __forceinline__ void trsm_tile64(const double* T, int ldt, const double* diag, double* B, int ldb, int fw,
+                                            int nb, double* trsm_smem) {
     double* Ts = trsm_smem;
     double* Xs = trsm_smem + NB * LDS;
     int tid = threadIdx.x;
-    const double* T = t.T + j0 + (size_t)j0 * t.ldt;
     // Ts[p*LDS + j] = coefficient multiplying unknown p in equation j (p <= j)
     if (MODE == TRSM_RUN) {
         // U[p][j], p <= j : column j contiguous in p
         for (int j = 0; j < nb; j++)
-            if (tid <= j) Ts[tid * LDS + j] = T[tid + (size_t)j * t.ldt];
+            if (tid <= j) Ts[tid * LDS + j] = T[tid + (size_t)j * ldt];
     } else {
         // L[j][p], p <= j : column p contiguous in j
         for (int p = 0; p < nb; p++)
-            if (tid >= p && tid < nb) Ts[p * LDS + tid] = T[tid + (size_t)p * t.ldt];
+            if (tid >= p && tid < nb) Ts[p * LDS + tid] = T[tid + (size_t)p * ldt];
     }
     if (MODE == TRSM_LLU) {
         if (tid < nb) Ts[tid * LDS + tid] = 1.0;
-    } else if (t.diag != nullptr) {
-        if (tid < nb) Ts[tid * LDS + tid] = t.diag[j0 + tid];
+    } else if (diag != nullptr) {
+        if (tid < nb) Ts[tid * LDS + tid] = diag[tid];
     }
     if (MODE == TRSM_LLN || MODE == TRSM_LLU) {
-        // X = B[j0:j0+nb, f0:f0+fw]; Xs[c*LDS + i]
-        double* B = t.B + j0 + (size_t)f0 * t.ldb;
+        // X = B[0:nb, 0:fw]; Xs[c*LDS + i]
         for (int c = 0; c < fw; c++)
-            if (tid < nb) Xs[c * LDS + tid] = B[tid + (size_t)c * t.ldb];
+            if (tid < nb) Xs[c * LDS + tid] = B[tid + (size_t)c * ldb];
         __syncthreads();
         if (tid < fw) {
             double* x = Xs + tid * LDS;
@@ -95,12 +95,11 @@ __global__ void __launch_bounds__(NB) trsm_step_kernel(const TrsmTask* __restric
         }
         __syncthreads();
         for (int c = 0; c < fw; c++)
-            if (tid < nb) B[tid + (size_t)c * t.ldb] = Xs[c * LDS + tid];
+            if (tid < nb) B[tid + (size_t)c * ldb] = Xs[c * LDS + tid];
     } else {
-        // X = B[f0:f0+fw, j0:j0+nb]; Xs[j*LDS + r]
-        double* B = t.B + f0 + (size_t)j0 * t.ldb;
+        // X = B[0:fw, 0:nb]; Xs[j*LDS + r]
         for (int j = 0; j < nb; j++)
-            if (tid < fw) Xs[j * LDS + tid] = B[tid + (size_t)j * t.ldb];
+            if (tid < fw) Xs[j * LDS + tid] = B[tid + (size_t)j * ldb];
         __syncthreads();
         if (tid < fw) {
             for (int j = 0; j < nb; j++) {
@@ -108,9 +107,23 @@ __global__ void __launch_bounds__(NB) trsm_step_kernel(const TrsmTask* __restric
                 for (int p = 0; p < j; p++) v -= Xs[p * LDS + tid] * Ts[p * LDS + j];
                 Xs[j * LDS + tid] = v / Ts[j * LDS + j];
             }
-            for (int j = 0; j < nb; j++) B[tid + (size_t)j * t.ldb] = Xs[j * LDS + tid];
+            for (int j = 0; j < nb; j++) B[tid + (size_t)j * ldb] = Xs[j * LDS + tid];
         }
     }
+    __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NB) trsm_step_kernel(const TrsmTask* __restrict__ tasks, int j0) {
+    TrsmTask t = tasks[blockIdx.x];
+    int nb = min(NB, t.n - j0);
+    int f0 = blockIdx.y * NB;  // offset in the free dimension
+    if (nb <= 0 || f0 >= t.m) return;
+    int fw = min(NB, t.m - f0);
+    extern __shared__ double trsm_smem[];
+    const double* T = t.T + j0 + (size_t)j0 * t.ldt;
+    double* B = (MODE == TRSM_LLN || MODE == TRSM_LLU) ? t.B + j0 + (size_t)f0 * t.ldb : t.B + f0 + (size_t)j0 * t.ldb;
+    trsm_tile64<MODE>(T, t.ldt, t.diag ? t.diag + j0 : nullptr, B, t.ldb, fw, nb, trsm_smem);
 }
 
 
@@ -363,24 +376,11 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256) gemm_tiled_kernel(const GemmTask* __restrict__ tasks, int nt,
-                                                         const GemmContrib* __restrict__ contribs,
-                                                         const int* __restrict__ tile_prefix) {
-    int b = blockIdx.x;
-    int lo = 0, hi = nt - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (tile_prefix[mid] <= b) lo = mid;
-        else hi = mid - 1;
-    }
-    GemmTask t = tasks[lo];
-    int local = b - tile_prefix[lo];
-    int tm = (t.m + GT - 1) / GT;
-    int tile_r = local % tm, tile_c = local / tm;
-    if ((t.flags & GEMM_LOWER) && tile_c > tile_r) return;
-    int row0 = tile_r * GT, col0 = tile_c * GT;
-    bool nn = (t.flags & GEMM_NN) != 0;
-
+// One 64x64 tile of one target; contributions come through fetch(ci) in a fixed order (deterministic sums).
+template <class Fetch>
+__device__ __forceinline__ void gemm_tile64(double* C, int ldc, int m, int n, int flags, int row0, int col0, int nc,
+                                            Fetch fetch) {
+    bool nn = (flags & GEMM_NN) != 0;
     __shared__ double As[GK * GLD];
     __shared__ double Bs[GK * GLD];
     int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -394,21 +394,21 @@ __global__ void __launch_bounds__(256) gemm_tiled_kernel(const GemmTask* __restr
     int arow = tid & 63, ak = tid >> 6;  // A loader: rows contiguous
     int bk_nn = tid & 15, bj_nn = tid >> 4;
 
-    for (int ci = 0; ci < t.nc; ci++) {
-        GemmContrib c = contribs[t.c0 + ci];
+    for (int ci = 0; ci < nc; ci++) {
+        GemmContrib c = fetch(ci);
         for (int k0 = 0; k0 < c.k; k0 += GK) {
             double ra[4], rb[4];
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 int kk = k0 + ak + 4 * s;
                 int gi = row0 + arow;
-                ra[s] = (gi < t.m && kk < c.k) ? c.A[gi + (size_t)kk * c.lda] : 0.0;
+                ra[s] = (gi < m && kk < c.k) ? c.A[gi + (size_t)kk * c.lda] : 0.0;
                 if (!nn) {
                     int gj = col0 + arow;
-                    rb[s] = (gj < t.n && kk < c.k) ? c.B[gj + (size_t)kk * c.ldb] : 0.0;
+                    rb[s] = (gj < n && kk < c.k) ? c.B[gj + (size_t)kk * c.ldb] : 0.0;
                 } else {
                     int kk2 = k0 + bk_nn, gj = col0 + bj_nn + 16 * s;
-                    rb[s] = (gj < t.n && kk2 < c.k) ? c.B[kk2 + (size_t)gj * c.ldb] : 0.0;
+                    rb[s] = (gj < n && kk2 < c.k) ? c.B[kk2 + (size_t)gj * c.ldb] : 0.0;
                 }
             }
             __syncthreads();
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(256) gemm_tiled_kernel(const GemmTask* __restr
             }
         }
     }
-    bool zero = (t.flags & GEMM_ZERO_INIT) != 0, lower = (t.flags & GEMM_LOWER) != 0;
+    bool zero = (flags & GEMM_ZERO_INIT) != 0, lower = (flags & GEMM_LOWER) != 0;
 #pragma unroll
     for (int mi = 0; mi < 2; mi++)
 #pragma unroll
@@ -443,11 +443,31 @@ __global__ void __launch_bounds__(256) gemm_tiled_kernel(const GemmTask* __restr
             for (int e = 0; e < 2; e++) {
                 int gi = row0 + wm * 16 + mi * 8 + (lane >> 2);
                 int gj = col0 + wn * 32 + ni * 8 + 2 * (lane & 3) + e;
-                if (gi < t.m && gj < t.n && (!lower || gi >= gj)) {
-                    double* p = t.C + gi + (size_t)gj * t.ldc;
+                if (gi < m && gj < n && (!lower || gi >= gj)) {
+                    double* p = C + gi + (size_t)gj * ldc;
                     *p = (zero ? 0.0 : *p) - acc[mi][ni][e];
                 }
             }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) gemm_tiled_kernel(const GemmTask* __restrict__ tasks, int nt,
+                                                         const GemmContrib* __restrict__ contribs,
+                                                         const int* __restrict__ tile_prefix) {
+    int b = blockIdx.x;
+    int lo = 0, hi = nt - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (tile_prefix[mid] <= b) lo = mid;
+        else hi = mid - 1;
+    }
+    GemmTask t = tasks[lo];
+    int local = b - tile_prefix[lo];
+    int tm = (t.m + GT - 1) / GT;
+    int tile_r = local % tm, tile_c = local / tm;
+    if ((t.flags & GEMM_LOWER) && tile_c > tile_r) return;
+    const GemmContrib* cc = contribs + t.c0;
+    gemm_tile64(t.C, t.ldc, t.m, t.n, t.flags, tile_r * GT, tile_c * GT, t.nc, [cc](int ci) { return cc[ci]; });
 }
 
 // Tiny targets: one warp per target, plain FMAs out of L1/L2.
@@ -654,6 +674,7 @@ __global__ void __launch_bounds__(SV_T) gemv_kernel(const GemvTask* __restrict__
 // trans == 1: x <- Q^T x = H_{r-1} .. H_0 x ; trans == 0: x <- Q x = H_0 .. H_{r-1} x   (dormqr, one vector)
 __global__ void __launch_bounds__(SV_T) house_kernel(const HouseTask* __restrict__ tasks, int trans) {
     HouseTask t = tasks[blockIdx.x];
+    if (t.rank >= t.rows) return;  // not sparsified: no Orthogonal op was recorded (src/tree.cpp:1317-1319)
     int tid = threadIdx.x;
     __shared__ double red[SV_T / 32];
     for (int s = 0; s < t.rank; s++) {
@@ -712,6 +733,366 @@ __global__ void gather_kernel(int n, const int* __restrict__ idx, const double* 
 }
 __global__ void scatter_kernel(int n, const int* __restrict__ idx, const double* __restrict__ src, double* dst) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[idx[i]] = src[i];
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Plan-driven batches (see kernels.cuh): ids resolved through DevTables, all dimensions <= SMALL_DIM.
+// ------------------------------------------------------------------------------------------------
+constexpr int WLD = 33;  // row stride of the per-warp 32 x 32 tiles
+constexpr unsigned FULLM = 0xffffffffu;
+
+__device__ __forceinline__ void push_mid(int* mid, int* cnt, int ti) { mid[atomicAdd(cnt, 1)] = ti; }
+
+__global__ void __launch_bounds__(128) potrf_sym_kernel(DevTables T, const int* __restrict__ clusters,
+                                                        const int* __restrict__ piv, int nt, int* mid, int* cnt, int* err) {
+    __shared__ double Sw[4][32 * WLD];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * 4 + w;
+    if (ti >= nt) return;
+    const int n = T.csize[clusters[ti]];
+    if (n <= 0 || n > SMALL_DIM) return;
+    if (n > 32) {
+        if (lane == 0) push_mid(mid, cnt, ti);
+        return;
+    }
+    const int e = piv[ti];
+    double* A = T.eptr[e];
+    const int ld = T.eld[e];
+    double* S = Sw[w];
+    for (int x = lane; x < n * n; x += 32) {
+        int i = x % n, j = x / n;
+        if (i >= j) S[j * WLD + i] = A[i + (size_t)j * ld];
+    }
+    __syncwarp();
+    for (int k = 0; k < n; k++) {
+        double v = 0.0;
+        if (lane >= k && lane < n) {
+            v = S[k * WLD + lane];
+            for (int p = 0; p < k; p++) v -= S[p * WLD + lane] * S[p * WLD + k];
+        }
+        const double d = __shfl_sync(FULLM, v, k);
+        const double r = sqrt(d);
+        if (lane == k) {
+            if (!(d > 0.0)) atomicOr(err, 1);
+            S[k * WLD + k] = r;
+        } else if (lane > k && lane < n) S[k * WLD + lane] = v / r;
+        __syncwarp();
+    }
+    for (int x = lane; x < n * n; x += 32) {
+        int i = x % n, j = x / n;
+        if (i >= j) A[i + (size_t)j * ld] = S[j * WLD + i];
+    }
+}
+
+__global__ void __launch_bounds__(NB) potrf_mid_kernel(DevTables T, const int* __restrict__ clusters,
+                                                       const int* __restrict__ piv, const int* __restrict__ mid,
+                                                       const int* __restrict__ cnt, int* err) {
+    const int nmid = *cnt;
+    for (int q = blockIdx.x; q < nmid; q += gridDim.x) {
+        const int ti = mid[q];
+        const int e = piv[ti];
+        potrf_tile64(T.eptr[e], T.eld[e], T.csize[clusters[ti]], err);
+    }
+}
+
+// In-warp triangular solves on a tile Bs[col * WLD + row] (rows x cols); the triangle is read from global memory
+// (uniform addresses: one broadcast transaction per load, L1-resident).
+__device__ __forceinline__ void warp_solve_right_lt(double* Bs, int rows, int cols, const double* L, int ldl, int lane) {
+    // B <- B L^-T : lane = row of B
+    if (lane < rows)
+        for (int j = 0; j < cols; j++) {
+            double v = Bs[j * WLD + lane];
+            for (int p = 0; p < j; p++) v -= Bs[p * WLD + lane] * L[j + (size_t)p * ldl];
+            Bs[j * WLD + lane] = v / L[j + (size_t)j * ldl];
+        }
+}
+__device__ __forceinline__ void warp_solve_left_ln(double* Bs, int rows, int cols, const double* L, int ldl, int lane) {
+    // B <- L^-1 B : lane = column of B
+    if (lane < cols) {
+        double* x = Bs + lane * WLD;
+        for (int i = 0; i < rows; i++) {
+            double v = x[i];
+            for (int p = 0; p < i; p++) v -= L[i + (size_t)p * ldl] * x[p];
+            x[i] = v / L[i + (size_t)i * ldl];
+        }
+    }
+}
+__device__ __forceinline__ void warp_tile_load(double* Bs, const double* B, int ldb, int rows, int cols, int lane) {
+    for (int x = lane; x < rows * cols; x += 32) {
+        int i = x % rows, j = x / rows;
+        Bs[j * WLD + i] = B[i + (size_t)j * ldb];
+    }
+}
+__device__ __forceinline__ void warp_tile_store(const double* Bs, double* B, int ldb, int rows, int cols, int lane) {
+    for (int x = lane; x < rows * cols; x += 32) {
+        int i = x % rows, j = x / rows;
+        B[i + (size_t)j * ldb] = Bs[j * WLD + i];
+    }
+}
+
+// MODE: TRSM_RLT (B is cm x cn) or TRSM_LLN (B is cn x cm)
+template <int MODE>
+__global__ void __launch_bounds__(128) trsm_sym_kernel(DevTables T, const SymTrsm* __restrict__ tasks, int nt, int* mid,
+                                                       int* cnt) {
+    __shared__ double Sw[4][32 * WLD];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * 4 + w;
+    if (ti >= nt) return;
+    const SymTrsm t = tasks[ti];
+    const int m = T.csize[t.cm], n = T.csize[t.cn];
+    if (m <= 0 || n <= 0 || m > SMALL_DIM || n > SMALL_DIM) return;
+    if (m > 32 || n > 32) {
+        if (lane == 0) push_mid(mid, cnt, ti);
+        return;
+    }
+    double* B = T.eptr[t.eB];
+    const int ldb = T.eld[t.eB];
+    const double* L = T.eptr[t.eT];
+    const int ldl = T.eld[t.eT];
+    double* S = Sw[w];
+    if (MODE == TRSM_RLT) {
+        warp_tile_load(S, B, ldb, m, n, lane);
+        __syncwarp();
+        warp_solve_right_lt(S, m, n, L, ldl, lane);
+        __syncwarp();
+        warp_tile_store(S, B, ldb, m, n, lane);
+    } else {
+        warp_tile_load(S, B, ldb, n, m, lane);
+        __syncwarp();
+        warp_solve_left_ln(S, n, m, L, ldl, lane);
+        __syncwarp();
+        warp_tile_store(S, B, ldb, n, m, lane);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NB) trsm_mid_kernel(DevTables T, const SymTrsm* __restrict__ tasks,
+                                                      const int* __restrict__ mid, const int* __restrict__ cnt) {
+    extern __shared__ double trsm_smem[];
+    const int nmid = *cnt;
+    for (int q = blockIdx.x; q < nmid; q += gridDim.x) {
+        const SymTrsm t = tasks[mid[q]];
+        trsm_tile64<MODE>(T.eptr[t.eT], T.eld[t.eT], nullptr, T.eptr[t.eB], T.eld[t.eB], T.csize[t.cm], T.csize[t.cn],
+                          trsm_smem);
+    }
+}
+
+// Two-sided scaling of one off-diagonal block: B (|c2| x |c1|) <- L_c2^-1 (B L_c1^-T)   (src/tree.cpp:796-856)
+__global__ void __launch_bounds__(128) scale_sym_kernel(DevTables T, const SymTrsm* __restrict__ right,
+                                                        const SymTrsm* __restrict__ left, int nt, int* mid, int* cnt) {
+    __shared__ double Sw[4][32 * WLD];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * 4 + w;
+    if (ti >= nt) return;
+    const SymTrsm r = right[ti];
+    const int rows = T.csize[r.cm], cols = T.csize[r.cn];
+    if (rows <= 0 || cols <= 0 || rows > SMALL_DIM || cols > SMALL_DIM) return;
+    if (rows > 32 || cols > 32) {
+        if (lane == 0) push_mid(mid, cnt, ti);
+        return;
+    }
+    const int eL = left[ti].eT;
+    double* B = T.eptr[r.eB];
+    const int ldb = T.eld[r.eB];
+    double* S = Sw[w];
+    warp_tile_load(S, B, ldb, rows, cols, lane);
+    __syncwarp();
+    warp_solve_right_lt(S, rows, cols, T.eptr[r.eT], T.eld[r.eT], lane);
+    __syncwarp();
+    warp_solve_left_ln(S, rows, cols, T.eptr[eL], T.eld[eL], lane);
+    __syncwarp();
+    warp_tile_store(S, B, ldb, rows, cols, lane);
+}
+
+__global__ void __launch_bounds__(NB) scale_mid_kernel(DevTables T, const SymTrsm* __restrict__ right,
+                                                       const SymTrsm* __restrict__ left, const int* __restrict__ mid,
+                                                       const int* __restrict__ cnt) {
+    extern __shared__ double trsm_smem[];
+    const int nmid = *cnt;
+    for (int q = blockIdx.x; q < nmid; q += gridDim.x) {
+        const SymTrsm r = right[mid[q]];
+        const int eL = left[mid[q]].eT;
+        const int rows = T.csize[r.cm], cols = T.csize[r.cn];
+        double* B = T.eptr[r.eB];
+        const int ldb = T.eld[r.eB];
+        trsm_tile64<TRSM_RLT>(T.eptr[r.eT], T.eld[r.eT], nullptr, B, ldb, rows, cols, trsm_smem);
+        trsm_tile64<TRSM_LLN>(T.eptr[eL], T.eld[eL], nullptr, B, ldb, cols, rows, trsm_smem);
+    }
+}
+
+__device__ __forceinline__ GemmContrib resolve_contrib(const DevTables& T, const SymCon c) {
+    GemmContrib g;
+    g.A = T.eptr[c.e1];
+    g.lda = T.eld[c.e1];
+    g.B = T.eptr[c.e2];
+    g.ldb = T.eld[c.e2];
+    g.k = T.csize[T.en1[c.e1]];
+    return g;
+}
+
+__global__ void __launch_bounds__(128) gemm_sym_small_kernel(DevTables T, const SymGemm* __restrict__ tasks, int nt,
+                                                             const SymCon* __restrict__ con, int* mid, int* cnt) {
+    const int ti = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ti >= nt) return;
+    const int lane = threadIdx.x & 31;
+    const SymGemm t = tasks[ti];
+    const int m = T.csize[T.en2[t.target]], n = T.csize[T.en1[t.target]];
+    if (m <= 0 || n <= 0 || m > SMALL_DIM || n > SMALL_DIM) return;
+    if (m * n > 1024) {
+        if (lane == 0) push_mid(mid, cnt, ti);
+        return;
+    }
+    const bool nn = (t.flags & GEMM_NN) != 0, zero = (t.flags & GEMM_ZERO_INIT) != 0, lower = (t.flags & GEMM_LOWER) != 0;
+    double* C = T.eptr[t.target];
+    const int ldc = T.eld[t.target];
+    const int total = m * n;
+    for (int e = lane; e < total; e += 32) {
+        const int i = e % m, j = e / m;
+        if (lower && j > i) continue;
+        double acc = 0.0;
+        for (int ci = 0; ci < t.nc; ci++) {
+            const GemmContrib c = resolve_contrib(T, con[t.c0 + ci]);
+            const double* a = c.A + i;
+            if (!nn) {
+                const double* bb = c.B + j;
+                for (int p = 0; p < c.k; p++) acc += a[(size_t)p * c.lda] * bb[(size_t)p * c.ldb];
+            } else {
+                const double* bb = c.B + (size_t)j * c.ldb;
+                for (int p = 0; p < c.k; p++) acc += a[(size_t)p * c.lda] * bb[p];
+            }
+        }
+        double* p = C + i + (size_t)j * ldc;
+        *p = (zero ? 0.0 : *p) - acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) gemm_sym_mid_kernel(DevTables T, const SymGemm* __restrict__ tasks,
+                                                           const SymCon* __restrict__ con, const int* __restrict__ mid,
+                                                           const int* __restrict__ cnt) {
+    const int nmid = *cnt;
+    for (int q = blockIdx.x; q < nmid; q += gridDim.x) {
+        const SymGemm t = tasks[mid[q]];
+        const int m = T.csize[T.en2[t.target]], n = T.csize[T.en1[t.target]];
+        const SymCon* cc = con + t.c0;
+        gemm_tile64(T.eptr[t.target], T.eld[t.target], m, n, t.flags, 0, 0, t.nc,
+                    [&T, cc](int ci) { return resolve_contrib(T, cc[ci]); });
+    }
+}
+
+// Merge: child block -> parent block (pre-zeroed). One warp per block of at most COPY_SMALL elements; larger blocks
+// are chunked by the host. Identity pivots (after scaling, src/tree.cpp:811) are written as a diagonal of ones.
+__global__ void __launch_bounds__(128) copy_sym_kernel(DevTables T, const SymCopy* __restrict__ tasks, int nt,
+                                                       int pivots_identity) {
+    const int ti = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ti >= nt) return;
+    const int lane = threadIdx.x & 31;
+    const SymCopy t = tasks[ti];
+    const int rows = T.csize[t.c2], cols = T.csize[t.c1];
+    if (rows <= 0 || cols <= 0) return;
+    const int ldd = T.eld[t.enew];
+    double* dst = T.eptr[t.enew] + T.pos[t.c2] + (size_t)T.pos[t.c1] * ldd;
+    if (pivots_identity && t.c1 == t.c2) {
+        for (int i = lane; i < rows; i += 32) dst[i + (size_t)i * ldd] = 1.0;
+        return;
+    }
+    const int tot = rows * cols;
+    if (tot > COPY_SMALL) return;
+    const double* src = T.eptr[t.eold];
+    const int lds = T.eld[t.eold];
+    if (rows >= 32) {
+        for (int j = 0; j < cols; j++)
+            for (int i = lane; i < rows; i += 32) dst[i + (size_t)j * ldd] = src[i + (size_t)j * lds];
+    } else {
+        for (int e = lane; e < tot; e += 32) {
+            int i = e % rows, j = e / rows;
+            dst[i + (size_t)j * ldd] = src[i + (size_t)j * lds];
+        }
+    }
+}
+
+__global__ void expand_qsrc_kernel(DevTables T, const SymQrSrc* __restrict__ s, int n, QrSrc* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SymQrSrc q = s[i];
+    QrSrc o;
+    o.blk = T.eptr[q.edge];
+    o.ld = T.eld[q.edge];
+    o.nbr = q.nbr;
+    o.transposed = q.transposed;
+    out[i] = o;
+}
+
+__global__ void expand_trsv_kernel(DevTables T, const int* __restrict__ clusters, const int* __restrict__ piv, int nt,
+                                   TrsvTask* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    const int c = clusters[i], e = piv[i];
+    TrsvTask o;
+    o.T = T.eptr[e];
+    o.x = T.xptr[c];
+    o.ld = T.eld[e];
+    o.n = T.csize[c];
+    o.diag = nullptr;
+    o.perm = nullptr;
+    out[i] = o;
+}
+
+__global__ void expand_gemv_kernel(DevTables T, const SymGemv* __restrict__ t, int nt, const SymGemvCon* __restrict__ c,
+                                   int ncon, GemvTask* out, GemvContrib* outc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nt) {
+        SymGemv g = t[i];
+        GemvTask o;
+        o.y = T.xptr[g.cluster];
+        o.m = T.csize[g.cluster];
+        o.c0 = g.c0;
+        o.nc = g.nc;
+        out[i] = o;
+    }
+    if (i < ncon) {
+        SymGemvCon g = c[i];
+        GemvContrib o;
+        o.A = T.eptr[g.edge];
+        o.x = T.xptr[g.xcluster];
+        o.lda = T.eld[g.edge];
+        o.k = T.csize[g.xcluster];
+        outc[i] = o;
+    }
+}
+
+__global__ void expand_xcopy_kernel(DevTables T, const int* __restrict__ children, int n, XCopyTask* fwd, XCopyTask* bwd) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = children[i];
+    double* xc = T.xptr[c];
+    double* xp = T.xptr[T.parent[c]] + T.pos[c];
+    const int sz = T.csize[c];
+    fwd[i] = XCopyTask{xc, xp, sz};
+    bwd[i] = XCopyTask{xp, xc, sz};
+}
+
+__global__ void expand_house_kernel(DevTables T, const QrTask* __restrict__ q, int n, HouseTask* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    QrTask t = q[i];
+    HouseTask o;
+    o.V = t.V;
+    o.tau = t.tau;
+    o.x = T.xptr[t.cluster];
+    o.rows = t.rows;
+    o.rank = min(t.rows, T.csize[t.cluster]);
+    out[i] = o;
+}
+
+__global__ void scatter_values_kernel(const double* __restrict__ val, const unsigned* __restrict__ map, size_t n,
+                                      double* dst) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        unsigned m = map[i];
+        if (m != 0xffffffffu) dst[m] = val[i];
+    }
 }
 
 inline int grid_for(size_t n, int bs, int maxb = 148 * 16) {
@@ -816,6 +1197,74 @@ void launch_gather(int n, const int* idx, const double* src, double* dst, cudaSt
 }
 void launch_scatter(int n, const int* idx, const double* src, double* dst, cudaStream_t st) {
     if (n > 0) scatter_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, idx, src, dst);
+}
+
+// ---- plan-driven launchers ----
+namespace {
+constexpr int kMidGrid = 148 * 8;
+constexpr int kTrsmSmem = 2 * NB * LDS * sizeof(double);
+void configure_mid_smem() {
+    static bool configured = false;
+    if (configured) return;
+    cudaFuncSetAttribute(trsm_mid_kernel<TRSM_RLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(trsm_mid_kernel<TRSM_LLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(scale_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    configured = true;
+}
+}  // namespace
+
+void launch_potrf_sym(const DevTables& T, const int* clusters, const int* piv, int nt, int* mid, int* cnt, int* err,
+                      cudaStream_t st) {
+    if (nt <= 0) return;
+    potrf_sym_kernel<<<(nt + 3) / 4, 128, 0, st>>>(T, clusters, piv, nt, mid, cnt, err);
+    potrf_mid_kernel<<<std::min(nt, kMidGrid), NB, 0, st>>>(T, clusters, piv, mid, cnt, err);
+}
+void launch_trsm_sym(int mode, const DevTables& T, const SymTrsm* tasks, int nt, int* mid, int* cnt, cudaStream_t st) {
+    if (nt <= 0) return;
+    configure_mid_smem();
+    if (mode == TRSM_RLT) {
+        trsm_sym_kernel<TRSM_RLT><<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, mid, cnt);
+        trsm_mid_kernel<TRSM_RLT><<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+    } else {
+        trsm_sym_kernel<TRSM_LLN><<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, mid, cnt);
+        trsm_mid_kernel<TRSM_LLN><<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+    }
+}
+void launch_scale_sym(const DevTables& T, const SymTrsm* right, const SymTrsm* left, int nt, int* mid, int* cnt,
+                      cudaStream_t st) {
+    if (nt <= 0) return;
+    configure_mid_smem();
+    scale_sym_kernel<<<(nt + 3) / 4, 128, 0, st>>>(T, right, left, nt, mid, cnt);
+    scale_mid_kernel<<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, right, left, mid, cnt);
+}
+void launch_gemm_sym(const DevTables& T, const SymGemm* tasks, int nt, const SymCon* con, int* mid, int* cnt,
+                     cudaStream_t st) {
+    if (nt <= 0) return;
+    gemm_sym_small_kernel<<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, con, mid, cnt);
+    gemm_sym_mid_kernel<<<std::min(nt, kMidGrid), 256, 0, st>>>(T, tasks, con, mid, cnt);
+}
+void launch_copy_sym(const DevTables& T, const SymCopy* tasks, int nt, int pivots_identity, cudaStream_t st) {
+    if (nt > 0) copy_sym_kernel<<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, pivots_identity);
+}
+void launch_expand_qsrc(const DevTables& T, const SymQrSrc* s, int n, QrSrc* out, cudaStream_t st) {
+    if (n > 0) expand_qsrc_kernel<<<(n + 255) / 256, 256, 0, st>>>(T, s, n, out);
+}
+void launch_expand_trsv(const DevTables& T, const int* clusters, const int* piv, int nt, TrsvTask* out, cudaStream_t st) {
+    if (nt > 0) expand_trsv_kernel<<<(nt + 255) / 256, 256, 0, st>>>(T, clusters, piv, nt, out);
+}
+void launch_expand_gemv(const DevTables& T, const SymGemv* t, int nt, const SymGemvCon* c, int ncon, GemvTask* out,
+                        GemvContrib* outc, cudaStream_t st) {
+    int n = std::max(nt, ncon);
+    if (n > 0) expand_gemv_kernel<<<(n + 255) / 256, 256, 0, st>>>(T, t, nt, c, ncon, out, outc);
+}
+void launch_expand_xcopy(const DevTables& T, const int* children, int n, XCopyTask* fwd, XCopyTask* bwd, cudaStream_t st) {
+    if (n > 0) expand_xcopy_kernel<<<(n + 255) / 256, 256, 0, st>>>(T, children, n, fwd, bwd);
+}
+void launch_expand_house(const DevTables& T, const QrTask* q, int n, HouseTask* out, cudaStream_t st) {
+    if (n > 0) expand_house_kernel<<<(n + 255) / 256, 256, 0, st>>>(T, q, n, out);
+}
+void launch_scatter_values(const double* val, const unsigned* map, size_t n, double* dst, cudaStream_t st) {
+    if (n > 0) scatter_values_kernel<<<grid_for(n, 256), 256, 0, st>>>(val, map, n, dst);
 }
 
 }  // namespace spand

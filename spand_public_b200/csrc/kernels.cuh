@@ -15,6 +15,8 @@
 
 #include <cstdint>
 
+#include "symbolic.hpp"
+
 namespace spand {
 
 constexpr int NB = 64;  // block size of the right-looking blocked POTRF / TRSM
@@ -163,6 +165,45 @@ void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, cud
 void launch_house(const HouseTask* t, int nt, int trans, cudaStream_t st);
 void launch_xcopy(const XCopyTask* t, int nt, cudaStream_t st);
 void launch_fill(double* p, size_t n, double v, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// Plan-driven ("sym") batches: the task arrays of the symbolic plan (symbolic.hpp) are resident on the device and
+// hold ids only; the kernels resolve them through these tables at run time. They serve every task whose
+// dimensions are all <= 64 (one warp for <= 32, one 64-thread CTA through a device-side "mid" list otherwise) and
+// skip the rest, which the host drives through the pointer-based blocked launchers above.
+// ------------------------------------------------------------------------------------------------
+struct DevTables {
+    const int* csize;       // current size of every cluster
+    double* const* eptr;    // block of every edge
+    const int* eld;         // its leading dimension
+    const int* en1;         // column cluster of every edge
+    const int* en2;         // row cluster of every edge
+    double* const* xptr;    // solution segment of every cluster
+    const int* pos;         // offset of a cluster inside its parent (valid after the merge planning of its level)
+    const int* parent;
+};
+constexpr int SMALL_DIM = 64;      // largest dimension served by the plan-driven kernels
+constexpr int COPY_SMALL = 4096;   // largest block (elements) copied by one warp in the merge
+
+// mid / cnt: device work list (capacity nt) and its counter (zeroed by the caller) used inside the launcher
+void launch_potrf_sym(const DevTables& T, const int* clusters, const int* piv, int nt, int* mid, int* cnt, int* err,
+                      cudaStream_t st);
+void launch_trsm_sym(int mode, const DevTables& T, const SymTrsm* tasks, int nt, int* mid, int* cnt, cudaStream_t st);
+// two-sided scaling of a block: B <- L_row^-1 (B L_col^-T); right[i] / left[i] describe the same block
+void launch_scale_sym(const DevTables& T, const SymTrsm* right, const SymTrsm* left, int nt, int* mid, int* cnt,
+                      cudaStream_t st);
+void launch_gemm_sym(const DevTables& T, const SymGemm* tasks, int nt, const SymCon* con, int* mid, int* cnt,
+                     cudaStream_t st);
+void launch_copy_sym(const DevTables& T, const SymCopy* tasks, int nt, int pivots_identity, cudaStream_t st);
+void launch_expand_qsrc(const DevTables& T, const SymQrSrc* s, int n, QrSrc* out, cudaStream_t st);
+// recorded operations -> solve batches (sizes are captured now)
+void launch_expand_trsv(const DevTables& T, const int* clusters, const int* piv, int nt, TrsvTask* out, cudaStream_t st);
+void launch_expand_gemv(const DevTables& T, const SymGemv* t, int nt, const SymGemvCon* c, int ncon, GemvTask* out,
+                        GemvContrib* outc, cudaStream_t st);
+void launch_expand_xcopy(const DevTables& T, const int* children, int n, XCopyTask* fwd, XCopyTask* bwd, cudaStream_t st);
+void launch_expand_house(const DevTables& T, const QrTask* q, int n, HouseTask* out, cudaStream_t st);
+// assembly: dst[map[k]] = val[k] for map[k] != 0xffffffff
+void launch_scatter_values(const double* val, const unsigned* map, size_t n, double* dst, cudaStream_t st);
 
 // PCG building blocks (src/is.cpp:39-121)
 void launch_spmv(int n, const int* rowptr, const int* colind, const double* val, const double* x, double* y,

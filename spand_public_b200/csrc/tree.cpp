@@ -90,7 +90,7 @@ void Stager::upload(void* dst, const void* src, size_t bytes, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// construction / partition / assemble
+// construction / partition / analyze / assemble
 // ------------------------------------------------------------------------------------------------
 Tree::Tree(int nlevels_) : nlevels(nlevels_) {
     if (nlevels <= 0) throw std::runtime_error("nlevels must be > 0");
@@ -109,8 +109,10 @@ void Tree::ensure_device() {
     CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     arena_ = new DeviceArena((size_t)1 << 30);
     scratch_ = new DeviceArena((size_t)256 << 20);
+    sym_arena_ = new DeviceArena((size_t)256 << 20);
     stager_.reserve((size_t)64 << 20);
     CK(cudaMalloc((void**)&d_err_, sizeof(int)));
+    CK(cudaMalloc((void**)&d_cnt_, sizeof(int) * 64));
     for (int i = 0; i < kSide; i++) {
         CK(cudaStreamCreateWithFlags(&side_[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ev_join_[i], cudaEventDisableTiming));
@@ -123,9 +125,12 @@ void Tree::free_device() {
     cudaStreamSynchronize(st_);
     delete arena_;
     delete scratch_;
-    arena_ = scratch_ = nullptr;
+    delete sym_arena_;
+    arena_ = scratch_ = sym_arena_ = nullptr;
+    plan_valid_ = false;
     if (d_err_) cudaFree(d_err_);
-    d_err_ = nullptr;
+    if (d_cnt_) cudaFree(d_cnt_);
+    d_err_ = d_cnt_ = nullptr;
     for (int i = 0; i < kSide; i++) {
         cudaStreamDestroy(side_[i]);
         cudaEventDestroy(ev_join_[i]);
@@ -186,6 +191,11 @@ T* Tree::to_device(const std::vector<T>& v, DeviceArena* where) {
     return d;
 }
 
+int* Tree::next_counter() {
+    if (cnt_next_ >= 64) throw std::runtime_error("internal: out of work-list counters");
+    return d_cnt_ + cnt_next_++;
+}
+
 void Tree::set_coords(int dim, int N_, const double* X) {
     Xcoo_ = DenseMat(dim, N_);
     std::copy(X, X + (size_t)dim * N_, Xcoo_.a.begin());
@@ -196,32 +206,145 @@ void Tree::set_coords(int dim, int N_, const double* X) {
 void Tree::partition(const SpMat& A) {
     if (use_geo && !have_coords_) throw std::runtime_error("use_geo set without coordinates");
     ord = build_ordering(A, nlevels, use_geo ? &Xcoo_ : nullptr, verb);
+    ord_serial_++;
     N = A.rows;
     log.assign(nlevels, LevelLog());
     for (auto& p : ord.part) log[p.self.lvl].dofs_nd += 1;
     for (int l = nlevels - 2; l >= 0; l--) log[l].dofs_left_nd = log[l + 1].dofs_nd + log[l + 1].dofs_left_nd;
 }
 
-int Tree::new_edge(int n1, int n2, double* A, int ld, bool original) {
-    Edge e;
-    e.n1 = n1;
-    e.n2 = n2;
-    e.A = A;
-    e.ld = ld;
-    e.original = original;
-    e.alive = true;
-    e.identity = false;
-    ed_.push_back(e);
-    return (int)ed_.size() - 1;
+// Symbolic analysis (once per partition + pattern): leaf block structure (src/tree.cpp:505-575), the map from the
+// non-zeros of A to their position inside the dense leaf blocks (util.cpp:454-486 block2dense), and the plan of
+// every level (symbolic.hpp). Everything is uploaded into sym_arena_ and reused by later assemble() calls.
+void Tree::analyze(const SpMat& A) {
+    const double t0 = wtime();
+    const bool symm = symmetry();
+    const int ncl = ord.norders;
+    std::vector<int> pinv(N), cmap(N);
+    for (int i = 0; i < N; i++) pinv[ord.perm[i]] = i;
+    for (int c : bottoms_[0])
+        for (int k = cl_[c].start; k < cl_[c].start + cl_[c].size; k++) cmap[k] = c;
+    // pass 1: neighbours of every leaf column cluster, pivot first then increasing order (cluster.cpp:113-176)
+    std::vector<int> leaf_n1, leaf_n2;
+    std::vector<int> blk_begin(ncl + 1, 0);
+    leaf_off_.clear();
+    size_t total = 0;
+    {
+        std::vector<int> mark(ncl, -1), nb;
+        for (int s : bottoms_[0]) {
+            nb.clear();
+            const Cluster& cs = cl_[s];
+            for (int pj = cs.start; pj < cs.start + cs.size; pj++) {
+                const int j = ord.perm[pj];
+                for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) {
+                    const int pi = pinv[A.rowind[k]];
+                    if (symm && pi < pj) continue;
+                    const int n = cmap[pi];
+                    if (mark[n] != s) {
+                        mark[n] = s;
+                        nb.push_back(n);
+                    }
+                }
+            }
+            if (mark[s] != s) {
+                mark[s] = s;
+                nb.push_back(s);
+            }
+            std::sort(nb.begin(), nb.end());
+            blk_begin[s] = (int)leaf_n1.size();
+            leaf_n1.push_back(s);
+            leaf_n2.push_back(s);
+            leaf_off_.push_back(total);
+            total += (((size_t)cs.size * cs.size) + 31) & ~(size_t)31;
+            for (int n : nb)
+                if (n != s) {
+                    leaf_n1.push_back(s);
+                    leaf_n2.push_back(n);
+                    leaf_off_.push_back(total);
+                    total += (((size_t)cl_[n].size * cs.size) + 31) & ~(size_t)31;
+                }
+            blk_begin[s + 1] = (int)leaf_n1.size();
+        }
+    }
+    if (total >= 0xffffffffull) throw std::runtime_error("assemble: leaf blocks exceed the 32-bit value map");
+    leaf_total_ = total;
+    // pass 2: value map
+    std::vector<unsigned> valmap(A.nnz(), 0xffffffffu);
+    for (int s : bottoms_[0]) {
+        const Cluster& cs = cl_[s];
+        const int b0 = blk_begin[s], b1 = blk_begin[s + 1];
+        for (int pj = cs.start; pj < cs.start + cs.size; pj++) {
+            const int j = ord.perm[pj];
+            for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) {
+                const int pi = pinv[A.rowind[k]];
+                if (symm && pi < pj) continue;
+                const int n = cmap[pi];
+                int b = b0;
+                if (n != s) b = (int)(std::lower_bound(leaf_n2.begin() + b0 + 1, leaf_n2.begin() + b1, n) - leaf_n2.begin());
+                valmap[k] = (unsigned)(leaf_off_[b] + (size_t)(pi - cl_[n].start) + (size_t)(pj - cs.start) * cl_[n].size);
+            }
+        }
+    }
+    // plan
+    std::vector<SymCluster> sc(ncl);
+    for (int c = 0; c < ncl; c++)
+        sc[c] = SymCluster{cl_[c].level, cl_[c].hlevel, cl_[c].parent, cl_[c].child_begin, cl_[c].child_end, cl_[c].sparsify};
+    build_symbolic(sc, bottoms_, leaf_n1, leaf_n2, symm, use_want_sparsify, plan_);
+    // upload
+    CK(cudaStreamSynchronize(st_));
+    sym_arena_->reset();
+    d_valmap_ = to_device(valmap, sym_arena_);
+    d_en1_ = to_device(plan_.en1, sym_arena_);
+    d_en2_ = to_device(plan_.en2, sym_arena_);
+    {
+        std::vector<int> par(ncl);
+        for (int c = 0; c < ncl; c++) par[c] = cl_[c].parent;
+        d_parent_ = to_device(par, sym_arena_);
+    }
+    dplan_.assign(nlevels, DevLevel());
+    size_t maxlist = 1;
+    for (int l = 0; l < nlevels; l++) {
+        const SymLevel& L = plan_.lv[l];
+        DevLevel& D = dplan_[l];
+        D.E = to_device(L.E, sym_arena_);
+        D.e_piv = to_device(L.e_piv, sym_arena_);
+        D.S = to_device(L.S, sym_arena_);
+        D.s_piv = to_device(L.s_piv, sym_arena_);
+        D.e_out = to_device(L.e_out, sym_arena_);
+        D.e_in = to_device(L.e_in, sym_arena_);
+        D.s_right = to_device(L.s_right, sym_arena_);
+        D.s_left = to_device(L.s_left, sym_arena_);
+        D.e_gemm = to_device(L.e_gemm, sym_arena_);
+        D.e_con = to_device(L.e_con, sym_arena_);
+        D.e_gf = to_device(L.e_gf, sym_arena_);
+        D.e_gb = to_device(L.e_gb, sym_arena_);
+        D.e_gfc = to_device(L.e_gfc, sym_arena_);
+        D.e_gbc = to_device(L.e_gbc, sym_arena_);
+        D.qs = to_device(L.qs, sym_arena_);
+        D.m_copy = to_device(L.m_copy, sym_arena_);
+        if (l + 1 < nlevels) {
+            std::vector<int> ch;
+            for (int p : bottoms_[l + 1])
+                for (int c = cl_[p].child_begin; c < cl_[p].child_end; c++) ch.push_back(c);
+            D.children = to_device(ch, sym_arena_);
+            D.n_children = (int)ch.size();
+        }
+        maxlist = std::max({maxlist, L.E.size(), L.S.size(), L.e_out.size(), L.s_right.size(), L.e_gemm.size()});
+    }
+    d_mid_ = sym_arena_->alloc_n<int>(maxlist);
+    CK(cudaStreamSynchronize(st_));
+    stager_.reset();
+    pat_colptr_ = A.colptr;
+    pat_rowind_ = A.rowind;
+    plan_ord_serial_ = ord_serial_;
+    plan_valid_ = true;
+    t_analyze_ = wtime() - t0;
+    if (verb)
+        printf("symbolic analysis: %zu edges, plan %.1f MB, %.3f s\n", plan_.en1.size(), plan_.bytes() / 1e6, t_analyze_);
 }
 
-int Tree::find_out(int c, int n2) const {
-    for (int e : cl_[c].out)
-        if (ed_[e].n2 == n2) return e;
-    return -1;
-}
-
-// src/tree.cpp:505-575 — dense blocks are built on the host once and uploaded in one copy
+// src/tree.cpp:505-575 — the values go to the device as they are (CSC order) and are scattered into the dense
+// leaf blocks by one kernel
 void Tree::assemble(const SpMat& A) {
     if (N == 0 || A.rows != N) throw std::runtime_error("assemble: call partition first with a matrix of the same size");
     ensure_device();
@@ -235,6 +358,8 @@ void Tree::assemble(const SpMat& A) {
     factorized_ = false;
     current_bottom_ = 0;
     ilvl_ = 0;
+    state_level_ = state_phase_ = -1;
+    logs_final_ = true;
     for (auto& l : log) {
         LevelLog fresh;
         fresh.dofs_nd = l.dofs_nd;
@@ -265,81 +390,55 @@ void Tree::assemble(const SpMat& A) {
             bottoms_[h].push_back(cn.order);
         }
     }
-    ed_.clear();
-    d_csize_ = arena_->alloc_n<int>(ord.norders);
+    const bool reuse = plan_valid_ && plan_ord_serial_ == ord_serial_ && plan_.symmetric == symmetry() &&
+                       plan_.want_flag == use_want_sparsify && pat_colptr_ == A.colptr && pat_rowind_ == A.rowind;
+    if (!reuse) analyze(A);
+
+    const int ncl = ord.norders;
+    const size_t nedges = plan_.en1.size();
+    d_csize_ = arena_->alloc_n<int>(ncl);
+    d_pos_ = arena_->alloc_n<int>(ncl);
+    d_xptr_ = arena_->alloc_n<double*>(ncl);
+    d_eptr_ = arena_->alloc_n<double*>(nedges);
+    d_eld_ = arena_->alloc_n<int>(nedges);
     d_perm_ = arena_->alloc_n<int>(N);
     d_xnat_ = arena_->alloc_n<double>(N);
-    double* d_xleaf = arena_->alloc_n<double>(N);
-    stager_.upload(d_perm_, ord.perm.data(), sizeof(int) * N, st_);
-    h_csize_.assign(ord.norders, 0);
+    d_xleaf_ = arena_->alloc_n<double>(N);
+    tab_ = DevTables{d_csize_, d_eptr_, d_eld_, d_en1_, d_en2_, d_xptr_, d_pos_, d_parent_};
+    h_csize_.assign(ncl, 0);
+    h_pos_.assign(ncl, 0);
+    h_xptr_.assign(ncl, nullptr);
+    h_eptr_.assign(nedges, nullptr);
+    h_eld_.assign(nedges, 1);
+    h_ud_.assign(ncl, nullptr);
+    h_ipiv_.assign(ncl, nullptr);
+    h_pperm_.assign(ncl, nullptr);
+    size_pre_.assign(nlevels, {});
+    size_post_.assign(nlevels, {});
+    phases_done_.assign(nlevels, 0);
     for (int c : bottoms_[0]) {
-        cl_[c].x = d_xleaf + cl_[c].start;
+        h_xptr_[c] = d_xleaf_ + cl_[c].start;
         h_csize_[c] = cl_[c].size;
     }
-    stager_.upload(d_csize_, h_csize_.data(), sizeof(int) * ord.norders, st_);
-
-    SpMat App = symm_perm(A, ord.perm);
-    std::vector<int> cmap(N);
-    for (int c : bottoms_[0])
-        for (int k = cl_[c].start; k < cl_[c].start + cl_[c].size; k++) cmap[k] = c;
-    // pass 1: structure
-    struct Blk { int n1, n2; size_t off; };
-    std::vector<Blk> blks;
-    size_t total = 0;
-    std::vector<int> mark(ord.norders, -1);
-    std::vector<int> nb;
-    for (int s : bottoms_[0]) {
-        nb.clear();
-        const Cluster& cs = cl_[s];
-        for (int j = cs.start; j < cs.start + cs.size; j++)
-            for (int k = App.colptr[j]; k < App.colptr[j + 1]; k++) {
-                int row = App.rowind[k];
-                if (symmetry() && row < j) continue;
-                int n = cmap[row];
-                if (mark[n] != s) {
-                    mark[n] = s;
-                    nb.push_back(n);
-                }
-            }
-        if (mark[s] != s) {
-            mark[s] = s;
-            nb.push_back(s);
-        }
-        std::sort(nb.begin(), nb.end());
-        // pivot first, the rest by increasing order (cluster.cpp:113-123,162-176)
-        blks.push_back({s, s, total});
-        total += (size_t)cs.size * cs.size;
-        for (int n : nb)
-            if (n != s) {
-                blks.push_back({s, n, total});
-                total += (size_t)cl_[n].size * cs.size;
-            }
+    double* dblocks = arena_->alloc_n<double>(leaf_total_);
+    for (int e = 0; e < plan_.nleaf_edges; e++) {
+        h_eptr_[e] = dblocks + leaf_off_[e];
+        h_eld_[e] = std::max(1, cl_[plan_.en2[e]].size);
     }
-    // pass 2: values (util.cpp:454-486 block2dense) into one host buffer
-    double* dblocks = arena_->alloc_n<double>(total);
-    std::vector<double> hb(total, 0.0);
-    for (auto& b : blks) {
-        const Cluster& c1 = cl_[b.n1];
-        const Cluster& c2 = cl_[b.n2];
-        double* dst = hb.data() + b.off;
-        for (int col = 0; col < c1.size; col++) {
-            int j = c1.start + col;
-            const int* rb = App.rowind.data() + App.colptr[j];
-            const int* re = App.rowind.data() + App.colptr[j + 1];
-            const int* it = std::lower_bound(rb, re, c2.start);
-            for (; it < re && *it < c2.start + c2.size; ++it)
-                dst[(*it - c2.start) + (size_t)col * c2.size] = App.val[it - App.rowind.data()];
-        }
-        int e = new_edge(b.n1, b.n2, dblocks + b.off, c2.size, true);
-        if (b.n1 == b.n2) cl_[b.n1].out.insert(cl_[b.n1].out.begin(), e);
-        else {
-            cl_[b.n1].out.push_back(e);
-            cl_[b.n2].in.push_back(e);
-        }
-    }
-    CK(cudaMemcpyAsync(dblocks, hb.data(), total * sizeof(double), cudaMemcpyHostToDevice, st_));
+    stager_.upload(d_perm_, ord.perm.data(), sizeof(int) * N, st_);
+    stager_.upload(d_csize_, h_csize_.data(), sizeof(int) * ncl, st_);
+    stager_.upload(d_xptr_, h_xptr_.data(), sizeof(double*) * ncl, st_);
+    stager_.upload(d_eptr_, h_eptr_.data(), sizeof(double*) * plan_.nleaf_edges, st_);
+    stager_.upload(d_eld_, h_eld_.data(), sizeof(int) * plan_.nleaf_edges, st_);
+    // values
+    double* d_val = scratch_->alloc_n<double>(A.nnz());
+    CK(cudaMemcpyAsync(d_val, A.val.data(), sizeof(double) * A.nnz(), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemsetAsync(dblocks, 0, leaf_total_ * sizeof(double), st_));
+    launch_scatter_values(d_val, d_valmap_, (size_t)A.nnz(), dblocks, st_);
     CK(cudaStreamSynchronize(st_));
     stager_.reset();
+    scratch_->reset();
+    assembled_ = true;
 }
 
 int Tree::ndofs_left() const {
@@ -349,12 +448,53 @@ int Tree::ndofs_left() const {
     return n;
 }
 
+int Tree::level_max_size() const {
+    int m = 0;
+    for (int c : bottoms_[current_bottom_])
+        if (!cl_[c].eliminated) m = std::max(m, h_csize_[c]);
+    return m;
+}
+
 void Tree::check_error() {
     int err = 0;
     CK(cudaMemcpyAsync(&err, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
     if (err & 1) throw std::runtime_error("Error: Non-SPD Pivot\n");
     if (err & 2) throw std::runtime_error("Error: Singular Pivot\n");
+}
+
+TrsmTask Tree::host_trsm(const SymTrsm& t, const double* diag) const {
+    TrsmTask r{};
+    r.B = h_eptr_[t.eB];
+    r.ldb = h_eld_[t.eB];
+    r.T = h_eptr_[t.eT];
+    r.ldt = h_eld_[t.eT];
+    r.m = h_csize_[t.cm];
+    r.n = h_csize_[t.cn];
+    r.diag = diag;
+    return r;
+}
+
+// Blocks of the edges [e0, e1) (fill-in of a level, or the parents' blocks of a merge) at the current sizes.
+void Tree::alloc_edges(int e0, int e1, bool zero, LevelLog& lg) {
+    if (e1 <= e0) return;
+    size_t total = 0;
+    for (int e = e0; e < e1; e++) {
+        const size_t rows = h_csize_[plan_.en2[e]], cols = h_csize_[plan_.en1[e]];
+        h_eld_[e] = (int)std::max<size_t>(1, rows);
+        h_eptr_[e] = (double*)total;  // offset for now
+        total += (rows * cols + 31) & ~(size_t)31;
+    }
+    double* base = arena_->alloc_n<double>(total + 32);
+    for (int e = e0; e < e1; e++) h_eptr_[e] = base + (size_t)h_eptr_[e];
+    if (zero) {
+        auto ev = fam_begin(F_COPY);
+        CK(cudaMemsetAsync(base, 0, total * sizeof(double), st_));
+        fam_end(F_COPY, ev);
+        lg.launches++;
+    }
+    stager_.upload(d_eptr_ + e0, h_eptr_.data() + e0, sizeof(double*) * (e1 - e0), st_);
+    stager_.upload(d_eld_ + e0, h_eld_.data() + e0, sizeof(int) * (e1 - e0), st_);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -492,175 +632,89 @@ void Tree::run_trsm(int mode, std::vector<TrsmTask>& all, LevelLog& lg) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// ELIMINATE — src/tree.cpp:895-967 for every cluster of level ilvl (mutually non-adjacent)
+// ELIMINATE — src/tree.cpp:895-967 for every cluster of level ilvl (mutually non-adjacent). The batches are the
+// id arrays of the plan; tasks with a dimension above SMALL_DIM go through the host-driven blocked path.
 // ------------------------------------------------------------------------------------------------
 void Tree::phase_eliminate(LevelLog& lg, SolveLevel& sl) {
     if (scale_kind == PLU) {
         phase_eliminate_plu(lg, sl);
         return;
     }
-    std::vector<int> E;
-    for (int c : bottoms_[current_bottom_])
-        if (cl_[c].level == ilvl_ && !cl_[c].eliminated) E.push_back(c);
-    if (E.empty()) return;
-    std::vector<PotrfTask> potrf;
-    std::vector<TrsmTask> trsm;
-    for (int s : E) {
-        const Cluster& cs = cl_[s];
-        const Edge& piv = ed_[cs.out[0]];
-        double n = cs.size;
-        potrf.push_back({piv.A, piv.ld, cs.size});
-        lg.fl_pivot += n * n * n / 3.0;
-        if (!cs.in.empty()) throw std::runtime_error("eliminate: unexpected in-edges on an SPD interior");
-        for (size_t k = 1; k < cs.out.size(); k++) {
-            const Edge& e = ed_[cs.out[k]];
-            TrsmTask t{};
-            t.B = e.A;
-            t.ldb = e.ld;
-            t.T = piv.A;
-            t.ldt = piv.ld;
-            t.m = cl_[e.n2].size;
-            t.n = cs.size;
-            trsm.push_back(t);
-            lg.fl_panel += (double)t.m * n * n;
-        }
+    const SymLevel& L = plan_.lv[ilvl_];
+    const DevLevel& D = dplan_[ilvl_];
+    if (L.E.empty()) return;
+    const bool big = level_max_size() > SMALL_DIM;
+    alloc_edges(L.fill0, L.fill1, false, lg);
+    // pivots
+    auto ev = fam_begin(F_POTRF);
+    launch_potrf_sym(tab_, D.E, D.e_piv, (int)L.E.size(), d_mid_, next_counter(), d_err_, st_);
+    fam_end(F_POTRF, ev);
+    lg.launches += 2;
+    if (big) {
+        std::vector<PotrfTask> bp;
+        for (size_t i = 0; i < L.E.size(); i++)
+            if (h_csize_[L.E[i]] > SMALL_DIM) bp.push_back({h_eptr_[L.e_piv[i]], h_eld_[L.e_piv[i]], h_csize_[L.E[i]]});
+        run_potrf(bp, lg);
     }
-    run_potrf(potrf, lg);
-    run_trsm(TRSM_RLT, trsm, lg);
-
-    // Schur complement: targets are found / created exactly in the reference's loop order (tree.cpp:862-869,
-    // gemm_edges :761-772) so that fill-in edges enter the out/in lists in the same sequence.
-    struct Triple { int target, e1, e2; };
-    std::vector<Triple> triples;
-    std::vector<int> task_of_edge;  // lazily sized
-    std::vector<int> targets;       // edge ids in first-seen order
-    std::vector<char> fresh;
-    for (int s : E) {
-        const std::vector<int>& out = cl_[s].out;
-        for (size_t a = 1; a < out.size(); a++) {
-            int e1 = out[a];
-            int n1 = ed_[e1].n2;
-            for (size_t b = 1; b < out.size(); b++) {
-                int e2 = out[b];
-                int n2 = ed_[e2].n2;
-                if (n1 < n2) continue;  // id == order
-                int tg = find_out(n2, n1);
-                bool is_new = false;
-                if (tg < 0) {
-                    double* A = arena_->alloc_n<double>((size_t)cl_[n1].size * cl_[n2].size);
-                    tg = new_edge(n2, n1, A, cl_[n1].size, false);
-                    cl_[n2].out.push_back(tg);
-                    cl_[n1].in.push_back(tg);
-                    is_new = true;
-                }
-                if ((int)task_of_edge.size() <= tg) task_of_edge.resize(ed_.size() + 1024, -1);
-                if (task_of_edge[tg] < 0) {
-                    task_of_edge[tg] = (int)targets.size();
-                    targets.push_back(tg);
-                    fresh.push_back(is_new);
-                }
-                triples.push_back({tg, e1, e2});
+    // panels
+    ev = fam_begin(F_TRSM);
+    launch_trsm_sym(TRSM_RLT, tab_, D.e_out, (int)L.e_out.size(), d_mid_, next_counter(), st_);
+    fam_end(F_TRSM, ev);
+    lg.launches += 2;
+    if (big) {
+        std::vector<TrsmTask> bt;
+        for (const SymTrsm& t : L.e_out) {
+            const int m = h_csize_[t.cm], n = h_csize_[t.cn];
+            if ((m > SMALL_DIM || n > SMALL_DIM) && m > 0 && n > 0) bt.push_back(host_trsm(t, nullptr));
+        }
+        run_trsm(TRSM_RLT, bt, lg);
+    }
+    // Schur complement
+    ev = fam_begin(F_GEMM);
+    launch_gemm_sym(tab_, D.e_gemm, (int)L.e_gemm.size(), D.e_con, d_mid_, next_counter(), st_);
+    fam_end(F_GEMM, ev);
+    lg.launches += 2;
+    if (big) {
+        std::vector<GemmTask> tasks;
+        std::vector<GemmContrib> con;
+        for (const SymGemm& g : L.e_gemm) {
+            const int m = h_csize_[plan_.en2[g.target]], n = h_csize_[plan_.en1[g.target]];
+            if (!(m > SMALL_DIM || n > SMALL_DIM) || m == 0 || n == 0) continue;
+            GemmTask t;
+            t.C = h_eptr_[g.target];
+            t.ldc = h_eld_[g.target];
+            t.m = m;
+            t.n = n;
+            t.c0 = (int)con.size();
+            t.nc = g.nc;
+            t.flags = g.flags;
+            for (int ci = 0; ci < g.nc; ci++) {
+                const SymCon& c = L.e_con[g.c0 + ci];
+                con.push_back({h_eptr_[c.e1], h_eptr_[c.e2], h_eld_[c.e1], h_eld_[c.e2], h_csize_[plan_.en1[c.e1]]});
             }
-        }
-    }
-    {
-        std::vector<GemmTask> tasks(targets.size());
-        std::vector<int> count(targets.size(), 0);
-        for (auto& t : triples) count[task_of_edge[t.target]]++;
-        int off = 0;
-        for (size_t i = 0; i < targets.size(); i++) {
-            const Edge& e = ed_[targets[i]];
-            GemmTask& g = tasks[i];
-            g.C = e.A;
-            g.ldc = e.ld;
-            g.m = cl_[e.n2].size;
-            g.n = cl_[e.n1].size;
-            g.c0 = off;
-            g.nc = 0;
-            g.flags = (e.n1 == e.n2 ? GEMM_LOWER : 0) | (fresh[i] ? GEMM_ZERO_INIT : 0);
-            off += count[i];
-        }
-        std::vector<GemmContrib> con(triples.size());
-        for (auto& t : triples) {
-            GemmTask& g = tasks[task_of_edge[t.target]];
-            const Edge& a = ed_[t.e1];
-            const Edge& b = ed_[t.e2];
-            int k = cl_[a.n1].size;
-            con[g.c0 + g.nc++] = {a.A, b.A, a.ld, b.ld, k};
-            if (a.n2 == b.n2) lg.fl_schur += (double)g.m * (g.m + 1) * k;
-            else lg.fl_schur += 2.0 * g.m * g.n * k;
+            tasks.push_back(t);
         }
         run_gemm(tasks, con, lg);
     }
-
-    // Record the operations (tree.cpp:909-910, :885-892) as solve batches, count nnz, drop the clusters.
-    std::vector<TrsvTask> trsv;
-    std::map<int, std::vector<GemvContrib>> fwd_by_target;  // x_n -= A[n,s] x_s, in s order
-    std::vector<GemvTask> bwd_tasks;
-    std::vector<GemvContrib> bwd_con;
-    for (int s : E) {
-        Cluster& cs = cl_[s];
-        const Edge& piv = ed_[cs.out[0]];
-        trsv.push_back({piv.A, cs.x, piv.ld, cs.size});
-        nnz_ += (long long)cs.size * (cs.size + 1) / 2;
-        GemvTask bt;
-        bt.y = cs.x;
-        bt.m = cs.size;
-        bt.c0 = (int)bwd_con.size();
-        bt.nc = 0;
-        for (size_t k = 1; k < cs.out.size(); k++) {
-            const Edge& e = ed_[cs.out[k]];
-            int nsz = cl_[e.n2].size;
-            nnz_ += (long long)cs.size * nsz;
-            if (nsz == 0 || cs.size == 0) continue;
-            fwd_by_target[e.n2].push_back({e.A, cs.x, e.ld, cs.size});
-            bwd_con.push_back({e.A, cl_[e.n2].x, e.ld, nsz});
-            bt.nc++;
-        }
-        if (bt.nc > 0) bwd_tasks.push_back(bt);
-    }
-    std::vector<GemvTask> fwd_tasks;
-    std::vector<GemvContrib> fwd_con;
-    for (auto& kv : fwd_by_target) {
-        GemvTask t;
-        t.y = cl_[kv.first].x;
-        t.m = cl_[kv.first].size;
-        t.c0 = (int)fwd_con.size();
-        t.nc = (int)kv.second.size();
-        fwd_con.insert(fwd_con.end(), kv.second.begin(), kv.second.end());
-        fwd_tasks.push_back(t);
-    }
-    sl.e_trsv = to_device(trsv, arena_);
-    sl.n_e_trsv = (int)trsv.size();
-    sl.e_gemv_f = to_device(fwd_tasks, arena_);
-    sl.e_gemv_fc = to_device(fwd_con, arena_);
-    sl.n_e_gemv_f = (int)fwd_tasks.size();
-    sl.e_gemv_b = to_device(bwd_tasks, arena_);
-    sl.e_gemv_bc = to_device(bwd_con, arena_);
-    sl.n_e_gemv_b = (int)bwd_tasks.size();
-
-    // set_eliminated (cluster.cpp:32-45)
-    std::vector<int> touched;
-    for (int s : E) {
-        Cluster& cs = cl_[s];
-        for (int e : cs.out) {
-            ed_[e].alive = false;
-            if (ed_[e].n2 != s) touched.push_back(ed_[e].n2);
-        }
-        cs.out.clear();
-        cs.in.clear();
-        cs.eliminated = true;
-    }
-    std::sort(touched.begin(), touched.end());
-    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
-    for (int n : touched) {
-        auto& in = cl_[n].in;
-        in.erase(std::remove_if(in.begin(), in.end(), [&](int e) { return !ed_[e].alive; }), in.end());
-    }
+    // recorded operations (tree.cpp:909-910, :885-892) as solve batches; sizes are captured now
+    sl.n_e_trsv = (int)L.E.size();
+    sl.e_trsv = arena_->alloc_n<TrsvTask>(L.E.size());
+    launch_expand_trsv(tab_, D.E, D.e_piv, sl.n_e_trsv, sl.e_trsv, st_);
+    sl.n_e_gemv_f = (int)L.e_gf.size();
+    sl.e_gemv_f = arena_->alloc_n<GemvTask>(L.e_gf.size());
+    sl.e_gemv_fc = arena_->alloc_n<GemvContrib>(L.e_gfc.size());
+    launch_expand_gemv(tab_, D.e_gf, sl.n_e_gemv_f, D.e_gfc, (int)L.e_gfc.size(), sl.e_gemv_f, sl.e_gemv_fc, st_);
+    sl.n_e_gemv_b = (int)L.e_gb.size();
+    sl.e_gemv_b = arena_->alloc_n<GemvTask>(L.e_gb.size());
+    sl.e_gemv_bc = arena_->alloc_n<GemvContrib>(L.e_gbc.size());
+    launch_expand_gemv(tab_, D.e_gb, sl.n_e_gemv_b, D.e_gbc, (int)L.e_gbc.size(), sl.e_gemv_b, sl.e_gemv_bc, st_);
+    lg.launches += 3;
+    for (int s : L.E) cl_[s].eliminated = true;
 }
 
 // ------------------------------------------------------------------------------------------------
-// GEN / PLU variants (src/tree.cpp:614-689, :735-742, :929-956, :838-853; src/util.cpp:183-227)
+// GEN / PLU variants (src/tree.cpp:614-689, :735-742, :929-956, :838-853; src/util.cpp:183-227): same plan,
+// pointer descriptors expanded on the host for every task
 // ------------------------------------------------------------------------------------------------
 void Tree::run_getrf(std::vector<GetrfTask>& tasks, LevelLog& lg) {
     if (tasks.empty()) return;
@@ -740,359 +794,197 @@ void Tree::run_rowperm(std::vector<RowPermTask>& tasks, LevelLog& lg) {
     lg.launches++;
 }
 
-void Tree::alloc_plu(Cluster& cs) {
-    size_t n = std::max(1, cs.size);
-    cs.ud = arena_->alloc_n<double>(n);
-    cs.ipiv = arena_->alloc_n<int>(n);
-    cs.perm = arena_->alloc_n<int>(n);
+void Tree::alloc_plu(int c) {
+    size_t n = std::max(1, h_csize_[c]);
+    h_ud_[c] = arena_->alloc_n<double>(n);
+    h_ipiv_[c] = arena_->alloc_n<int>(n);
+    h_pperm_[c] = arena_->alloc_n<int>(n);
 }
 
 void Tree::phase_eliminate_plu(LevelLog& lg, SolveLevel& sl) {
-    std::vector<int> E;
-    for (int c : bottoms_[current_bottom_])
-        if (cl_[c].level == ilvl_ && !cl_[c].eliminated) E.push_back(c);
-    if (E.empty()) return;
+    const SymLevel& L = plan_.lv[ilvl_];
+    const DevLevel& D = dplan_[ilvl_];
+    if (L.E.empty()) return;
+    alloc_edges(L.fill0, L.fill1, false, lg);
     std::vector<GetrfTask> getrf;
     std::vector<RowPermTask> rperm;
     std::vector<TrsmTask> left, right;
-    for (int s : E) {
-        Cluster& cs = cl_[s];
-        const Edge& piv = ed_[cs.out[0]];
-        double n = cs.size;
-        alloc_plu(cs);
-        getrf.push_back({piv.A, piv.ld, cs.size, cs.ud, cs.ipiv, cs.perm});
-        lg.fl_pivot += 2.0 * n * n * n / 3.0;
-        for (int eid : cs.in) {  // A[s,n] <- L^-1 P^T A[s,n]   (tree.cpp:668-676)
-            const Edge& e = ed_[eid];
-            int w = cl_[e.n1].size;
-            rperm.push_back({e.A, e.ld, cs.size, w, cs.perm});
-            TrsmTask t{};
-            t.B = e.A;
-            t.ldb = e.ld;
-            t.T = piv.A;
-            t.ldt = piv.ld;
-            t.m = w;
-            t.n = cs.size;
-            left.push_back(t);
-            lg.fl_panel += (double)w * n * n;
-        }
-        for (size_t k = 1; k < cs.out.size(); k++) {  // A[n,s] <- A[n,s] U^-1   (tree.cpp:681-689, Q = I)
-            const Edge& e = ed_[cs.out[k]];
-            TrsmTask t{};
-            t.B = e.A;
-            t.ldb = e.ld;
-            t.T = piv.A;
-            t.ldt = piv.ld;
-            t.m = cl_[e.n2].size;
-            t.n = cs.size;
-            t.diag = cs.ud;
-            right.push_back(t);
-            lg.fl_panel += (double)t.m * n * n;
-        }
+    std::vector<TrsvTask> trsv;
+    for (size_t i = 0; i < L.E.size(); i++) {
+        const int s = L.E[i], piv = L.e_piv[i];
+        alloc_plu(s);
+        getrf.push_back({h_eptr_[piv], h_eld_[piv], h_csize_[s], h_ud_[s], h_ipiv_[s], h_pperm_[s]});
+        trsv.push_back({h_eptr_[piv], h_xptr_[s], h_eld_[piv], h_csize_[s], h_ud_[s], h_pperm_[s]});
     }
+    for (const SymTrsm& t : L.e_in) {  // A[s,n] <- L^-1 P^T A[s,n]   (tree.cpp:668-676)
+        rperm.push_back({h_eptr_[t.eB], h_eld_[t.eB], h_csize_[t.cn], h_csize_[t.cm], h_pperm_[t.cn]});
+        left.push_back(host_trsm(t, nullptr));
+    }
+    for (const SymTrsm& t : L.e_out) right.push_back(host_trsm(t, h_ud_[t.cn]));  // A[n,s] <- A[n,s] U^-1 (tree.cpp:681-689)
     run_getrf(getrf, lg);
     run_rowperm(rperm, lg);
     run_trsm(TRSM_LLN, left, lg);
     run_trsm(TRSM_RUN, right, lg);
-
-    // Schur complement A[n1,n2] -= A[n1,s] A[s,n2] for every (out, in) pair in the reference's loop order
-    // (tree.cpp:943-947); fill-in edges are created where gemm_edges would create them (:761-772).
-    struct Triple { int target, e1, e2; };
-    std::vector<Triple> triples;
-    std::vector<int> task_of_edge, targets;
-    std::vector<char> fresh;
-    for (int s : E) {
-        const std::vector<int>& out = cl_[s].out;
-        const std::vector<int>& in = cl_[s].in;
-        for (size_t a = 1; a < out.size(); a++) {
-            int e1 = out[a];
-            int n1 = ed_[e1].n2;
-            for (size_t b = 0; b < in.size(); b++) {
-                int e2 = in[b];
-                int n2 = ed_[e2].n1;
-                int tg = find_out(n2, n1);
-                bool is_new = false;
-                if (tg < 0) {
-                    double* A = arena_->alloc_n<double>((size_t)cl_[n1].size * cl_[n2].size);
-                    tg = new_edge(n2, n1, A, std::max(1, cl_[n1].size), false);
-                    cl_[n2].out.push_back(tg);
-                    cl_[n1].in.push_back(tg);
-                    is_new = true;
-                }
-                if ((int)task_of_edge.size() <= tg) task_of_edge.resize(ed_.size() + 1024, -1);
-                if (task_of_edge[tg] < 0) {
-                    task_of_edge[tg] = (int)targets.size();
-                    targets.push_back(tg);
-                    fresh.push_back(is_new);
-                }
-                triples.push_back({tg, e1, e2});
-            }
-        }
-    }
+    // Schur complement A[n1,n2] -= A[n1,s] A[s,n2] (tree.cpp:943-947)
     {
-        std::vector<GemmTask> tasks(targets.size());
-        std::vector<int> count(targets.size(), 0);
-        for (auto& t : triples) count[task_of_edge[t.target]]++;
-        int off = 0;
-        for (size_t i = 0; i < targets.size(); i++) {
-            const Edge& e = ed_[targets[i]];
-            GemmTask& g = tasks[i];
-            g.C = e.A;
-            g.ldc = e.ld;
-            g.m = cl_[e.n2].size;
-            g.n = cl_[e.n1].size;
-            g.c0 = off;
-            g.nc = 0;
-            g.flags = GEMM_NN | (fresh[i] ? GEMM_ZERO_INIT : 0);
-            off += count[i];
-        }
-        std::vector<GemmContrib> con(triples.size());
-        for (auto& t : triples) {
-            GemmTask& g = tasks[task_of_edge[t.target]];
-            const Edge& a = ed_[t.e1];  // A[n1,s]
-            const Edge& b = ed_[t.e2];  // A[s,n2]
-            int k = cl_[a.n1].size;
-            con[g.c0 + g.nc++] = {a.A, b.A, a.ld, b.ld, k};
-            lg.fl_schur += 2.0 * g.m * g.n * k;
+        std::vector<GemmTask> tasks;
+        std::vector<GemmContrib> con;
+        for (const SymGemm& g : L.e_gemm) {
+            GemmTask t;
+            t.C = h_eptr_[g.target];
+            t.ldc = h_eld_[g.target];
+            t.m = h_csize_[plan_.en2[g.target]];
+            t.n = h_csize_[plan_.en1[g.target]];
+            t.c0 = (int)con.size();
+            t.nc = g.nc;
+            t.flags = g.flags;
+            for (int ci = 0; ci < g.nc; ci++) {
+                const SymCon& c = L.e_con[g.c0 + ci];
+                con.push_back({h_eptr_[c.e1], h_eptr_[c.e2], h_eld_[c.e1], h_eld_[c.e2], h_csize_[plan_.en1[c.e1]]});
+            }
+            tasks.push_back(t);
         }
         run_gemm(tasks, con, lg);
     }
-
     // recorded operations: ScalingPLUQ, GemmOut (forward only), GemmIn (backward only)
-    std::vector<TrsvTask> trsv;
-    std::map<int, std::vector<GemvContrib>> fwd_by_target;
-    std::vector<GemvTask> bwd_tasks;
-    std::vector<GemvContrib> bwd_con;
-    for (int s : E) {
-        Cluster& cs = cl_[s];
-        const Edge& piv = ed_[cs.out[0]];
-        trsv.push_back({piv.A, cs.x, piv.ld, cs.size, cs.ud, cs.perm});
-        nnz_ += (long long)cs.size * cs.size + 2LL * cs.size;
-        for (size_t k = 1; k < cs.out.size(); k++) {
-            const Edge& e = ed_[cs.out[k]];
-            int nsz = cl_[e.n2].size;
-            nnz_ += (long long)cs.size * nsz;
-            if (nsz == 0 || cs.size == 0) continue;
-            fwd_by_target[e.n2].push_back({e.A, cs.x, e.ld, cs.size});
-        }
-        GemvTask bt;
-        bt.y = cs.x;
-        bt.m = cs.size;
-        bt.c0 = (int)bwd_con.size();
-        bt.nc = 0;
-        for (int eid : cs.in) {
-            const Edge& e = ed_[eid];
-            int nsz = cl_[e.n1].size;
-            nnz_ += (long long)cs.size * nsz;
-            if (nsz == 0 || cs.size == 0) continue;
-            bwd_con.push_back({e.A, cl_[e.n1].x, e.ld, nsz});  // x_s -= A[s,n] x_n  (no transpose)
-            bt.nc++;
-        }
-        if (bt.nc > 0) bwd_tasks.push_back(bt);
-    }
-    std::vector<GemvTask> fwd_tasks;
-    std::vector<GemvContrib> fwd_con;
-    for (auto& kv : fwd_by_target) {
-        GemvTask t;
-        t.y = cl_[kv.first].x;
-        t.m = cl_[kv.first].size;
-        t.c0 = (int)fwd_con.size();
-        t.nc = (int)kv.second.size();
-        fwd_con.insert(fwd_con.end(), kv.second.begin(), kv.second.end());
-        fwd_tasks.push_back(t);
-    }
     sl.e_trsv = to_device(trsv, arena_);
     sl.n_e_trsv = (int)trsv.size();
-    sl.e_gemv_f = to_device(fwd_tasks, arena_);
-    sl.e_gemv_fc = to_device(fwd_con, arena_);
-    sl.n_e_gemv_f = (int)fwd_tasks.size();
-    sl.e_gemv_b = to_device(bwd_tasks, arena_);
-    sl.e_gemv_bc = to_device(bwd_con, arena_);
-    sl.n_e_gemv_b = (int)bwd_tasks.size();
-
-    // set_eliminated (cluster.cpp:32-45): drop the cluster's out-edges and in-edges from their other endpoints
-    std::vector<int> touched;
-    for (int s : E) {
-        Cluster& cs = cl_[s];
-        for (int e : cs.out) {
-            ed_[e].alive = false;
-            if (ed_[e].n2 != s) touched.push_back(ed_[e].n2);
-        }
-        for (int e : cs.in) {
-            ed_[e].alive = false;
-            touched.push_back(ed_[e].n1);
-        }
-        cs.out.clear();
-        cs.in.clear();
-        cs.eliminated = true;
-    }
-    std::sort(touched.begin(), touched.end());
-    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
-    for (int n : touched) {
-        auto& in = cl_[n].in;
-        in.erase(std::remove_if(in.begin(), in.end(), [&](int e) { return !ed_[e].alive; }), in.end());
-        auto& out = cl_[n].out;
-        out.erase(std::remove_if(out.begin(), out.end(), [&](int e) { return !ed_[e].alive; }), out.end());
-    }
+    sl.n_e_gemv_f = (int)L.e_gf.size();
+    sl.e_gemv_f = arena_->alloc_n<GemvTask>(L.e_gf.size());
+    sl.e_gemv_fc = arena_->alloc_n<GemvContrib>(L.e_gfc.size());
+    launch_expand_gemv(tab_, D.e_gf, sl.n_e_gemv_f, D.e_gfc, (int)L.e_gfc.size(), sl.e_gemv_f, sl.e_gemv_fc, st_);
+    sl.n_e_gemv_b = (int)L.e_gb.size();
+    sl.e_gemv_b = arena_->alloc_n<GemvTask>(L.e_gb.size());
+    sl.e_gemv_bc = arena_->alloc_n<GemvContrib>(L.e_gbc.size());
+    launch_expand_gemv(tab_, D.e_gb, sl.n_e_gemv_b, D.e_gbc, (int)L.e_gbc.size(), sl.e_gemv_b, sl.e_gemv_bc, st_);
+    lg.launches += 2;
+    for (int s : L.E) cl_[s].eliminated = true;
 }
 
 void Tree::phase_scale_plu(LevelLog& lg, SolveLevel& sl) {
+    const SymLevel& L = plan_.lv[ilvl_];
+    if (L.S.empty()) return;
     std::vector<GetrfTask> getrf;
     std::vector<RowPermTask> rperm;
     std::vector<TrsmTask> right, left;
     std::vector<TrsvTask> trsv;
-    const std::vector<int>& bottom = bottoms_[current_bottom_];
-    for (int c : bottom) {
-        Cluster& cs = cl_[c];
-        if (cs.eliminated || cs.level <= ilvl_) continue;
-        alloc_plu(cs);
+    for (size_t i = 0; i < L.S.size(); i++) {
+        const int c = L.S[i], piv = L.s_piv[i];
+        alloc_plu(c);
+        getrf.push_back({h_eptr_[piv], h_eld_[piv], h_csize_[c], h_ud_[c], h_ipiv_[c], h_pperm_[c]});
+        trsv.push_back({h_eptr_[piv], h_xptr_[c], h_eld_[piv], h_csize_[c], h_ud_[c], h_pperm_[c]});
     }
-    for (int c : bottom) {
-        Cluster& cs = cl_[c];
-        if (cs.eliminated || cs.level <= ilvl_) continue;
-        Edge& piv = ed_[cs.out[0]];
-        double n = cs.size;
-        getrf.push_back({piv.A, piv.ld, cs.size, cs.ud, cs.ipiv, cs.perm});
-        trsv.push_back({piv.A, cs.x, piv.ld, cs.size, cs.ud, cs.perm});
-        nnz_ += (long long)cs.size * cs.size + 2LL * cs.size;
-        lg.fl_pivot += 2.0 * n * n * n / 3.0;
-        lg.by_scale += 16.0 * n * n;
-        for (size_t k = 1; k < cs.out.size(); k++) {
-            const Edge& e = ed_[cs.out[k]];
-            const Cluster& c2 = cl_[e.n2];
-            const Edge& piv2 = ed_[c2.out[0]];
-            // block A[n2,n1] (|n2| x |n1|): out-edge of n1 -> B U_n1^-1 ; in-edge of n2 -> L_n2^-1 P_n2^T B
-            TrsmTask r{};
-            r.B = e.A;
-            r.ldb = e.ld;
-            r.T = piv.A;
-            r.ldt = piv.ld;
-            r.m = c2.size;
-            r.n = cs.size;
-            r.diag = cs.ud;
-            right.push_back(r);
-            rperm.push_back({e.A, e.ld, c2.size, cs.size, c2.perm});
-            TrsmTask l{};
-            l.B = e.A;
-            l.ldb = e.ld;
-            l.T = piv2.A;
-            l.ldt = piv2.ld;
-            l.m = cs.size;
-            l.n = c2.size;
-            left.push_back(l);
-            lg.fl_panel += (double)c2.size * n * n + (double)cs.size * c2.size * c2.size;
-            lg.by_scale += 16.0 * c2.size * n;
-        }
+    for (size_t i = 0; i < L.s_right.size(); i++) {
+        // block A[n2,n1] (|n2| x |n1|): out-edge of n1 -> B U_n1^-1 ; in-edge of n2 -> L_n2^-1 P_n2^T B
+        const SymTrsm& r = L.s_right[i];
+        const SymTrsm& l = L.s_left[i];
+        right.push_back(host_trsm(r, h_ud_[r.cn]));
+        rperm.push_back({h_eptr_[l.eB], h_eld_[l.eB], h_csize_[l.cn], h_csize_[l.cm], h_pperm_[l.cn]});
+        left.push_back(host_trsm(l, nullptr));
     }
     run_getrf(getrf, lg);
     run_trsm(TRSM_RUN, right, lg);
     run_rowperm(rperm, lg);
     run_trsm(TRSM_LLN, left, lg);
-    for (int c : bottom) {
-        Cluster& cs = cl_[c];
-        if (cs.eliminated || cs.level <= ilvl_) continue;
-        ed_[cs.out[0]].identity = true;  // tree.cpp:848 — never materialised
-    }
     sl.s_trsv = to_device(trsv, arena_);
     sl.n_s_trsv = (int)trsv.size();
 }
 
 // ------------------------------------------------------------------------------------------------
 // SCALE — src/tree.cpp:796-856 for every remaining cluster: pivot = L L^T, every incident block
-// A[n2,n1] <- L_n2^-1 A[n2,n1] L_n1^-T, pivot := I (kept implicit)
+// A[n2,n1] <- L_n2^-1 A[n2,n1] L_n1^-T in one pass, pivot := I (kept implicit)
 // ------------------------------------------------------------------------------------------------
 void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
     if (scale_kind == PLU) {
         phase_scale_plu(lg, sl);
         return;
     }
-    std::vector<PotrfTask> potrf;
-    std::vector<TrsmTask> right, left;
-    std::vector<TrsvTask> trsv;
-    for (int c : bottoms_[current_bottom_]) {
-        Cluster& cs = cl_[c];
-        if (cs.eliminated || cs.level <= ilvl_) continue;
-        Edge& piv = ed_[cs.out[0]];
-        double n = cs.size;
-        potrf.push_back({piv.A, piv.ld, cs.size});
-        trsv.push_back({piv.A, cs.x, piv.ld, cs.size});
-        nnz_ += (long long)cs.size * (cs.size + 1) / 2;
-        lg.fl_pivot += n * n * n / 3.0;
-        lg.by_scale += 16.0 * n * n;
-        for (size_t k = 1; k < cs.out.size(); k++) {
-            const Edge& e = ed_[cs.out[k]];
-            const Cluster& c2 = cl_[e.n2];
-            const Edge& piv2 = ed_[c2.out[0]];
-            // right: B (|n2| x |n1|) <- B L_n1^-T ; left: B <- L_n2^-1 B
-            right.push_back({e.A, piv.A, e.ld, piv.ld, c2.size, cs.size});
-            left.push_back({e.A, piv2.A, e.ld, piv2.ld, cs.size, c2.size});
-            lg.fl_panel += (double)c2.size * n * n + (double)cs.size * c2.size * c2.size;
-            lg.by_scale += 16.0 * c2.size * n;
+    const SymLevel& L = plan_.lv[ilvl_];
+    const DevLevel& D = dplan_[ilvl_];
+    if (L.S.empty()) return;
+    const bool big = level_max_size() > SMALL_DIM;
+    auto ev = fam_begin(F_POTRF);
+    launch_potrf_sym(tab_, D.S, D.s_piv, (int)L.S.size(), d_mid_, next_counter(), d_err_, st_);
+    fam_end(F_POTRF, ev);
+    lg.launches += 2;
+    if (big) {
+        std::vector<PotrfTask> bp;
+        for (size_t i = 0; i < L.S.size(); i++)
+            if (h_csize_[L.S[i]] > SMALL_DIM) bp.push_back({h_eptr_[L.s_piv[i]], h_eld_[L.s_piv[i]], h_csize_[L.S[i]]});
+        run_potrf(bp, lg);
+    }
+    ev = fam_begin(F_TRSM);
+    launch_scale_sym(tab_, D.s_right, D.s_left, (int)L.s_right.size(), d_mid_, next_counter(), st_);
+    fam_end(F_TRSM, ev);
+    lg.launches += 2;
+    if (big) {
+        std::vector<TrsmTask> right, left;
+        for (size_t i = 0; i < L.s_right.size(); i++) {
+            const SymTrsm& r = L.s_right[i];
+            const int m = h_csize_[r.cm], n = h_csize_[r.cn];
+            if ((m > SMALL_DIM || n > SMALL_DIM) && m > 0 && n > 0) {
+                right.push_back(host_trsm(r, nullptr));
+                left.push_back(host_trsm(L.s_left[i], nullptr));
+            }
         }
+        run_trsm(TRSM_RLT, right, lg);
+        run_trsm(TRSM_LLN, left, lg);
     }
-    run_potrf(potrf, lg);
-    run_trsm(TRSM_RLT, right, lg);
-    run_trsm(TRSM_LLN, left, lg);
-    for (int c : bottoms_[current_bottom_]) {
-        Cluster& cs = cl_[c];
-        if (cs.eliminated || cs.level <= ilvl_) continue;
-        ed_[cs.out[0]].identity = true;  // tree.cpp:811,853 — never materialised
-    }
-    sl.s_trsv = to_device(trsv, arena_);
-    sl.n_s_trsv = (int)trsv.size();
+    sl.n_s_trsv = (int)L.S.size();
+    sl.s_trsv = arena_->alloc_n<TrsvTask>(L.S.size());
+    launch_expand_trsv(tab_, D.S, D.s_piv, sl.n_s_trsv, sl.s_trsv, st_);
+    lg.launches++;
 }
 
 // ------------------------------------------------------------------------------------------------
 // SPARSIFY — src/tree.cpp:1417-1433 -> 1292-1347. The reference sweeps the clusters in list order
 // (Gauss-Seidel: a cluster sees the already-shrunk blocks of earlier neighbours). The same result is
-// obtained by wavefronts of the dependency DAG; clusters of one wavefront are mutually non-adjacent.
+// obtained by wavefronts of the dependency DAG (colours of the plan); clusters of one wavefront are mutually
+// non-adjacent.
 // ------------------------------------------------------------------------------------------------
 void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
     const double plan0 = wtime();
+    const SymLevel& L = plan_.lv[ilvl_];
+    const DevLevel& D = dplan_[ilvl_];
     const std::vector<int>& bottom = bottoms_[current_bottom_];
-    std::vector<int> S;
-    for (int c : bottom) {
-        const Cluster& cs = cl_[c];
-        if (cs.eliminated || cs.level <= ilvl_) continue;
-        bool want = use_want_sparsify ? cs.sparsify : true;
-        if (want) S.push_back(c);
-        else lg.ignored++;
-    }
-    int first = bottom.empty() ? 0 : bottom.front();
-    int span = bottom.empty() ? 0 : bottom.back() - first + 1;
-    std::vector<int> color(span, -1);
-    std::vector<int> old_size(span, 0);
-    int ncolors = 0;
-    if (!S.empty()) {
-        std::vector<QrTask> tasks;
-        std::vector<QrSrc> srcs;
-        std::vector<int> task_color;
-        for (int s : S) {
-            const Cluster& cs = cl_[s];
-            int col = 0;
-            QrTask t;
-            t.cluster = s;
-            t.rows = cs.size;
-            t.src0 = (int)srcs.size();
+    const int first = bottom.empty() ? 0 : bottom.front();
+    const int span = bottom.empty() ? 0 : bottom.back() - first + 1;
+    lg.ignored = L.ignored;
+    const int ncolors = L.ncolors;
+    if (!L.q.empty()) {
+        const size_t nq = L.q.size();
+        QrSrc* ds = scratch_->alloc_n<QrSrc>(L.qs.size());
+        launch_expand_qsrc(tab_, D.qs, (int)L.qs.size(), ds, st_);
+        lg.launches++;
+        std::vector<QrTask> tasks(nq);
+        std::vector<int> task_color(nq);
+        size_t vtotal = 0, ttotal = 0;
+        std::vector<size_t> voff(nq), toff(nq);
+        for (size_t i = 0; i < nq; i++) {
+            const SymQr& q = L.q[i];
+            QrTask& t = tasks[i];
+            t.cluster = q.cluster;
+            t.rows = h_csize_[q.cluster];
+            t.src0 = q.src0;
+            t.nsrc = q.nsrc;
             int maxcols = 0;
-            auto visit = [&](int nbr, const Edge& e, int transposed) {
-                int cn = color[nbr - first];
-                if (cn >= 0) col = std::max(col, cn + 1);  // earlier in list order and sparsified
-                srcs.push_back({e.A, e.ld, nbr, transposed});
-                maxcols += cl_[nbr].size;
-            };
-            for (int e : cs.in) visit(ed_[e].n1, ed_[e], 0);
-            for (size_t k = 1; k < cs.out.size(); k++) visit(ed_[cs.out[k]].n2, ed_[cs.out[k]], 1);
-            t.nsrc = (int)srcs.size() - t.src0;
+            for (int k = 0; k < q.nsrc; k++) maxcols += h_csize_[L.qs[q.src0 + k].nbr];
             t.maxcols = maxcols;
-            color[s - first] = col;
-            ncolors = std::max(ncolors, col + 1);
             t.W = nullptr;
-            int kmax = std::min(t.rows, maxcols);
-            t.V = arena_->alloc_n<double>((size_t)t.rows * kmax);
-            t.tau = arena_->alloc_n<double>(kmax);
-            tasks.push_back(t);
-            task_color.push_back(col);
+            const size_t kmax = std::min(t.rows, maxcols);
+            voff[i] = vtotal;
+            toff[i] = ttotal;
+            vtotal += ((size_t)t.rows * kmax + 31) & ~(size_t)31;
+            ttotal += (kmax + 31) & ~(size_t)31;
+            task_color[i] = q.color;
+        }
+        {
+            double* vbase = arena_->alloc_n<double>(vtotal + 32);
+            double* tbase = arena_->alloc_n<double>(ttotal + 32);
+            for (size_t i = 0; i < nq; i++) {
+                tasks[i].V = vbase + voff[i];
+                tasks[i].tau = tbase + toff[i];
+            }
         }
         // Launch classes: (threads, cluster size G, shared-memory bucket). The panel stays resident in (distributed)
         // shared memory whenever it fits in 16 CTAs; otherwise it lives in the (L2-resident) scratch arena.
@@ -1102,26 +994,26 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         auto pow2ceil = [](int x) { int p = 1; while (p < x) p *= 2; return p; };
         // class = (mode << 8) | (log2 G << 4) | bucket; mode 0: 128 threads (G = 1), 1: 256 threads, 2: panel in the
         // global scratch (512 threads, G = 8), 3: 512 threads
-        std::vector<int> klass(tasks.size());
-        std::vector<int> smem_need(tasks.size());
+        std::vector<int> klass(nq);
+        std::vector<int> smem_need(nq);
         const int kNB = 6;
         // test hooks: force every task through one kernel shape (tests/test_gpu_parity.py)
         const bool force_global = getenv("SPAND_RRQR_FORCE_GLOBAL") != nullptr;
         const int force_g = getenv("SPAND_RRQR_FORCE_G") ? atoi(getenv("SPAND_RRQR_FORCE_G")) : 0;
-        std::vector<int> per_color(ncolors, 0);
+        std::vector<int> per_color(std::max(1, ncolors), 0);
         for (int c : task_color) per_color[c]++;
-        for (size_t i = 0; i < tasks.size(); i++) {
+        for (size_t i = 0; i < nq; i++) {
             QrTask& t = tasks[i];
             int mn = std::max(1, std::min(t.rows, t.maxcols));
             t.nb = std::min(QR_NB, mn);
             auto config = [&](int NT, int G, bool in_smem) {
                 int cpcm = std::max(1, (t.maxcols + G - 1) / G);
-                int L = in_smem ? std::min(32, std::max(1, pow2floor(NT / cpcm))) : 32;
-                L = std::min(L, pow2ceil(std::max(1, (t.rows + 1) / 2)));  // a lane works on pairs of rows
+                int Ln = in_smem ? std::min(32, std::max(1, pow2floor(NT / cpcm))) : 32;
+                Ln = std::min(Ln, pow2ceil(std::max(1, (t.rows + 1) / 2)));  // a lane works on pairs of rows
                 int ld = (t.rows + 1) & ~1;
-                if (in_smem && L < 8)
-                    while (ld % 16 != (2 * L) % 16) ld += 2;  // conflict-free 128-bit shared loads
-                t.L = L;
+                if (in_smem && Ln < 8)
+                    while (ld % 16 != (2 * Ln) % 16) ld += 2;  // conflict-free 128-bit shared loads
+                t.L = Ln;
                 t.ld = ld;
                 t.in_smem = in_smem ? 1 : 0;
                 return (long)rrqr_smem_bytes(t.rows, t.maxcols, G, t.nb, t.ld, in_smem);
@@ -1171,21 +1063,20 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             smem_need[i] = (int)nd;
         }
         // order tasks by (colour, class), stable
-        std::vector<int> idx(tasks.size());
-        for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+        std::vector<int> idx(nq);
+        for (size_t i = 0; i < nq; i++) idx[i] = (int)i;
         std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
             if (task_color[a] != task_color[b]) return task_color[a] < task_color[b];
             return klass[a] < klass[b];
         });
-        std::vector<QrTask> sorted(tasks.size());
-        for (size_t i = 0; i < idx.size(); i++) sorted[i] = tasks[idx[i]];
+        std::vector<QrTask> sorted(nq);
+        for (size_t i = 0; i < nq; i++) sorted[i] = tasks[idx[i]];
         QrTask* dt = to_device(sorted, scratch_);
-        QrSrc* ds = to_device(srcs, scratch_);
         // One launch per (colour, class). The classes of a colour are independent: they run concurrently on side
         // streams forked from / joined into the factorization stream.
-        for (size_t b = 0; b < idx.size();) {
+        for (size_t b = 0; b < nq;) {
             size_t cend = b;
-            while (cend < idx.size() && task_color[idx[cend]] == task_color[idx[b]]) cend++;
+            while (cend < nq && task_color[idx[cend]] == task_color[idx[b]]) cend++;
             auto ev = fam_begin(F_RRQR);
             CK(cudaEventRecord(ev_fork_, st_));
             int nside = 0;
@@ -1216,47 +1107,24 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             fam_end(F_RRQR, ev);
         }
         lg.wavefronts = ncolors;
+        // Orthogonal ops (tree.cpp:1322-1331): one entry per task, no-ops where the rank did not drop
+        sl.n_house = (int)nq;
+        sl.house = arena_->alloc_n<HouseTask>(nq);
+        launch_expand_house(tab_, dt, (int)nq, sl.house, st_);
+        lg.launches++;
         lg.t_plan_spars = wtime() - plan0;
         // ranks back to the host: the one synchronisation of the level
-        for (int c : bottom) old_size[c - first] = cl_[c].size;
         CK(cudaMemcpyAsync(h_csize_.data() + first, d_csize_ + first, sizeof(int) * span, cudaMemcpyDeviceToHost, st_));
         check_error();
-        std::vector<HouseTask> house;
-        FILE* dump = nullptr;
-        if (const char* fn = getenv("SPAND_DUMP_QR")) dump = fopen(fn, "a");
-        for (size_t i = 0; i < tasks.size(); i++) {
-            const QrTask& t = tasks[i];
-            Cluster& cs = cl_[t.cluster];
-            int rank = h_csize_[t.cluster];
-            if (dump) fprintf(dump, "%d %d %d %d %d %d\n", ilvl_, t.cluster, t.rows, t.maxcols, rank, task_color[i]);
-            // columns actually seen by this cluster (earlier sparsified neighbours had already shrunk)
-            long cols = 0;
-            for (int k = 0; k < t.nsrc; k++) {
-                int nbr = srcs[t.src0 + k].nbr;
-                // position in list order == id order inside one bottom
-                cols += (color[nbr - first] >= 0 && nbr < t.cluster) ? h_csize_[nbr] : old_size[nbr - first];
+        if (const char* fn = getenv("SPAND_DUMP_QR")) {
+            if (FILE* dump = fopen(fn, "a")) {
+                for (size_t i = 0; i < nq; i++)
+                    fprintf(dump, "%d %d %d %d %d %d\n", ilvl_, tasks[i].cluster, tasks[i].rows, tasks[i].maxcols,
+                            h_csize_[tasks[i].cluster], task_color[i]);
+                fclose(dump);
             }
-            double r = t.rows, cc = (double)cols, rf = std::min<double>(t.rows, cols), rk = rank;
-            if (tol >= 1.0 || cols == 0) rf = 0;
-            lg.rank_before += t.rows;
-            lg.nspars++;
-            lg.nbrs += cols;
-            lg.fl_rrqr_full += 4 * r * cc * rf - 2 * (r + cc) * rf * rf + (4.0 / 3.0) * rf * rf * rf;
-            lg.fl_rrqr_rank += 4 * r * cc * rk - 2 * (r + cc) * rk * rk + (4.0 / 3.0) * rk * rk * rk;
-            lg.by_rrqr += 8 * r * cc + 8 * rk * cc + 8 * r * rk;
-            if (rank < t.rows) {
-                house.push_back({t.V, t.tau, cs.x, t.rows, rank});
-                nnz_ += (long long)t.rows * t.rows;  // Orthogonal (operations.cpp:159-161)
-                long long m = t.rows - rank;
-                // Scaling op of the dropped sibling (tree.cpp:1342): ScalingLLT(I) or ScalingPLUQ(I, I, id, id)
-                nnz_ += scale_kind == PLU ? m * m + 2 * m : m * (m + 1) / 2;
-                cs.size = rank;
-            }
-            lg.rank_after += cs.size;
         }
-        if (dump) fclose(dump);
-        sl.house = to_device(house, arena_);
-        sl.n_house = (int)house.size();
+        for (const SymQr& q : L.q) cl_[q.cluster].size = h_csize_[q.cluster];
     } else {
         check_error();
     }
@@ -1269,18 +1137,21 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
 // MERGE — src/tree.cpp:1435-1445 (reset_size :1106-1131, update_edges :1133-1184)
 // ------------------------------------------------------------------------------------------------
 void Tree::phase_merge(LevelLog& lg, SolveLevel& sl) {
+    const SymLevel& L = plan_.lv[ilvl_];
+    const DevLevel& D = dplan_[ilvl_];
+    const std::vector<int>& children = bottoms_[current_bottom_];
     current_bottom_++;
     const std::vector<int>& parents = bottoms_[current_bottom_];
     if (parents.empty()) return;
-    std::vector<int> pos(ord.norders, 0);
-    std::vector<XCopyTask> mf, mb;
     size_t xtotal = 0;
+    int maxchild = 0;
     for (int p : parents) {
         Cluster& cp = cl_[p];
         int size = 0;
         for (int c = cp.child_begin; c < cp.child_end; c++) {
-            pos[c] = size;
-            size += cl_[c].size;
+            h_pos_[c] = size;
+            size += h_csize_[c];
+            maxchild = std::max(maxchild, h_csize_[c]);
         }
         cp.size = cp.orig_size = size;
         h_csize_[p] = size;
@@ -1290,110 +1161,51 @@ void Tree::phase_merge(LevelLog& lg, SolveLevel& sl) {
     {
         size_t off = 0;
         for (int p : parents) {
-            Cluster& cp = cl_[p];
-            cp.x = xbase + off;
-            off += cp.size;
-            for (int c = cp.child_begin; c < cp.child_end; c++) {
-                if (cl_[c].size == 0) continue;
-                mf.push_back({cl_[c].x, cp.x + pos[c], cl_[c].size});
-                mb.push_back({cp.x + pos[c], cl_[c].x, cl_[c].size});
-            }
+            h_xptr_[p] = xbase + off;
+            off += cl_[p].size;
         }
     }
-    int pfirst = parents.front();
-    stager_.upload(d_csize_ + pfirst, h_csize_.data() + pfirst, sizeof(int) * parents.size(), st_);
-    sl.m_fwd = to_device(mf, arena_);
-    sl.m_bwd = to_device(mb, arena_);
-    sl.n_merge = (int)mf.size();
-
-    // new edges: structure first, then one zero-filled allocation, then the block copies
-    struct NewEdge { int n1, n2; size_t off; bool original; };
-    std::vector<NewEdge> ne;
-    std::vector<CopyTask> copies;
-    struct PendingCopy { int edge_old; int newidx; };
-    std::vector<PendingCopy> pend;
-    size_t total = 0;
-    std::vector<int> slot(ord.norders, -1);
-    std::vector<int> tlist;
-    for (int p : parents) {
-        Cluster& cp = cl_[p];
-        tlist.clear();
-        for (int c = cp.child_begin; c < cp.child_end; c++)
-            for (int e : cl_[c].out) {
-                int q = cl_[ed_[e].n2].parent;
-                if (slot[q] == -1) {
-                    slot[q] = -2;
-                    tlist.push_back(q);
-                }
-            }
-        std::sort(tlist.begin(), tlist.end());
-        // pivot first, then by increasing order
-        size_t base = ne.size();
-        ne.push_back({p, p, 0, false});
-        slot[p] = (int)base;
-        for (int q : tlist)
-            if (q != p) {
-                slot[q] = (int)ne.size();
-                ne.push_back({p, q, 0, false});
-            }
-        for (size_t i = base; i < ne.size(); i++) {
-            ne[i].off = total;
-            total += (size_t)cl_[ne[i].n2].size * cp.size;
-        }
-        for (int c = cp.child_begin; c < cp.child_end; c++)
-            for (int e : cl_[c].out) {
-                int q = cl_[ed_[e].n2].parent;
-                if (ed_[e].original) ne[slot[q]].original = true;
-                pend.push_back({e, slot[q]});
-            }
-        for (int q : tlist) slot[q] = -1;
-        slot[p] = -1;
+    const int pfirst = parents.front(), np = parents.back() - pfirst + 1;
+    stager_.upload(d_csize_ + pfirst, h_csize_.data() + pfirst, sizeof(int) * np, st_);
+    stager_.upload(d_xptr_ + pfirst, h_xptr_.data() + pfirst, sizeof(double*) * np, st_);
+    if (!children.empty()) {
+        const int cfirst = children.front(), nc = children.back() - cfirst + 1;
+        stager_.upload(d_pos_ + cfirst, h_pos_.data() + cfirst, sizeof(int) * nc, st_);
     }
-    double* nb = arena_->alloc_n<double>(total + 1);
-    auto evz = fam_begin(F_COPY);
-    CK(cudaMemsetAsync(nb, 0, total * sizeof(double), st_));
-    fam_end(F_COPY, evz);
-    lg.by_merge += 8.0 * total;
-    std::vector<int> new_ids(ne.size());
-    for (size_t i = 0; i < ne.size(); i++) {
-        int ld = std::max(1, cl_[ne[i].n2].size);
-        int e = new_edge(ne[i].n1, ne[i].n2, nb + ne[i].off, ld, ne[i].original);
-        new_ids[i] = e;
-        if (ne[i].n1 == ne[i].n2) cl_[ne[i].n1].out.insert(cl_[ne[i].n1].out.begin(), e);
-        else {
-            cl_[ne[i].n1].out.push_back(e);
-            cl_[ne[i].n2].in.push_back(e);
-        }
-    }
-    const int CHUNK = 4096;
-    for (auto& pc : pend) {
-        Edge& eo = ed_[pc.edge_old];
-        const Edge& en = ed_[new_ids[pc.newidx]];
-        int rows = cl_[eo.n2].size, cols = cl_[eo.n1].size;
-        eo.alive = false;
-        if (rows == 0 || cols == 0) continue;
-        double* dst = en.A + pos[eo.n2] + (size_t)pos[eo.n1] * en.ld;
-        lg.by_merge += 8.0 * rows * cols;
-        if (eo.identity) {
-            copies.push_back({nullptr, dst, 0, en.ld, rows, cols});
-            continue;
-        }
-        int cstep = std::max(1, CHUNK / rows);
-        for (int c0 = 0; c0 < cols; c0 += cstep) {
-            int w = std::min(cstep, cols - c0);
-            copies.push_back({eo.A + (size_t)c0 * eo.ld, dst + (size_t)c0 * en.ld, eo.ld, en.ld, rows, w});
-        }
-    }
-    for (int p : parents)
-        for (int c = cl_[p].child_begin; c < cl_[p].child_end; c++) {
-            cl_[c].out.clear();
-            cl_[c].in.clear();
-        }
-    CopyTask* dc = to_device(copies, scratch_);
+    alloc_edges(L.medge0, L.medge1, true, lg);
+    const bool ident = ilvl_ >= skip;  // children were scaled at this level: their pivots are I (tree.cpp:811)
     auto evc = fam_begin(F_COPY);
-    launch_copy(dc, (int)copies.size(), st_);
+    launch_copy_sym(tab_, D.m_copy, (int)L.m_copy.size(), ident ? 1 : 0, st_);
     fam_end(F_COPY, evc);
-    lg.launches += 2;
+    lg.launches++;
+    if ((long)maxchild * maxchild > COPY_SMALL) {
+        std::vector<CopyTask> copies;
+        const int CHUNK = 4096;
+        for (const SymCopy& t : L.m_copy) {
+            const int rows = h_csize_[t.c2], cols = h_csize_[t.c1];
+            if ((long)rows * cols <= COPY_SMALL || (ident && t.c1 == t.c2)) continue;
+            const int ldn = h_eld_[t.enew], lds = h_eld_[t.eold];
+            double* dst = h_eptr_[t.enew] + h_pos_[t.c2] + (size_t)h_pos_[t.c1] * ldn;
+            const double* src = h_eptr_[t.eold];
+            int cstep = std::max(1, CHUNK / rows);
+            for (int c0 = 0; c0 < cols; c0 += cstep) {
+                int w = std::min(cstep, cols - c0);
+                copies.push_back({src + (size_t)c0 * lds, dst + (size_t)c0 * ldn, lds, ldn, rows, w});
+            }
+        }
+        if (!copies.empty()) {
+            CopyTask* dc = to_device(copies, scratch_);
+            evc = fam_begin(F_COPY);
+            launch_copy(dc, (int)copies.size(), st_);
+            fam_end(F_COPY, evc);
+            lg.launches++;
+        }
+    }
+    sl.n_merge = D.n_children;
+    sl.m_fwd = arena_->alloc_n<XCopyTask>(std::max(1, D.n_children));
+    sl.m_bwd = arena_->alloc_n<XCopyTask>(std::max(1, D.n_children));
+    launch_expand_xcopy(tab_, D.children, D.n_children, sl.m_fwd, sl.m_bwd, st_);
+    lg.launches++;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1403,7 +1215,9 @@ void Tree::factorize() {
     if (symm_kind == SPD && scale_kind != LLT) throw std::runtime_error("SPD requires LLT scaling");
     if (symm_kind == GEN && scale_kind != PLU) throw std::runtime_error("GEN requires PLU scaling (PLUQ is out of scope)");
     if (symm_kind == SYM) throw std::runtime_error("SYM/LDLT is out of scope (SURVEY.md section 2)");
-    if (ed_.empty() || factorized_) throw std::runtime_error("factorize: call assemble first");
+    if (!assembled_ || factorized_ || state_level_ >= 0) throw std::runtime_error("factorize: call assemble first");
+    if (plan_.symmetric != symmetry() || plan_.want_flag != use_want_sparsify)
+        throw std::runtime_error("factorize: symm_kind / use_sparsify changed after assemble");
     ensure_device();
     CK(cudaMemsetAsync(d_err_, 0, sizeof(int), st_));
     for (int f = 0; f < F_COUNT; f++) {
@@ -1418,15 +1232,30 @@ void Tree::factorize() {
     CK(cudaEventRecord(ev_begin, st_));
     bool stopped = false;
     int last_level = -1;
+    logs_final_ = false;
+    auto snapshot = [&](std::vector<int>& dst) {
+        const std::vector<int>& bottom = bottoms_[current_bottom_];
+        if (bottom.empty()) {
+            dst.clear();
+            return;
+        }
+        dst.assign(h_csize_.begin() + bottom.front(), h_csize_.begin() + bottom.back() + 1);
+    };
     for (ilvl_ = 0; ilvl_ < nlevels && !stopped; ilvl_++) {
         LevelLog& lg = log[ilvl_];
         SolveLevel& sl = solve_[ilvl_];
         last_level = ilvl_;
         double h0 = wtime();
         if (verb) printf("Level %d, %d dofs left\n", ilvl_, ndofs_left());
+        cnt_next_ = 0;
+        CK(cudaMemsetAsync(d_cnt_, 0, sizeof(int) * 64, st_));
+        snapshot(size_pre_[ilvl_]);
         CK(cudaEventRecord(ev[ilvl_ * 5 + 0], st_));
         double p0 = wtime();
         phase_eliminate(lg, sl);
+        phases_done_[ilvl_] |= 1;
+        state_level_ = ilvl_;
+        state_phase_ = 0;
         lg.t_plan_elim = wtime() - p0;
         CK(cudaEventRecord(ev[ilvl_ * 5 + 1], st_));
         lg.dofs_left_elim = ndofs_left();
@@ -1434,11 +1263,15 @@ void Tree::factorize() {
         if (!stopped && ilvl_ >= skip) {
             p0 = wtime();
             phase_scale(lg, sl);
+            phases_done_[ilvl_] |= 2;
+            state_phase_ = 1;
             lg.t_plan_scale = wtime() - p0;
             CK(cudaEventRecord(ev[ilvl_ * 5 + 2], st_));
             if (ilvl_ == stop_level && stop_phase == 1) stopped = true;
             if (!stopped) {
                 phase_sparsify(lg, sl);
+                phases_done_[ilvl_] |= 4;
+                state_phase_ = 2;
                 if (ilvl_ == stop_level && stop_phase == 2) stopped = true;
             }
         } else {
@@ -1447,13 +1280,17 @@ void Tree::factorize() {
             stager_.reset();
             scratch_->reset();
         }
+        snapshot(size_post_[ilvl_]);
         CK(cudaEventRecord(ev[ilvl_ * 5 + 3], st_));
         p0 = wtime();
-        if (!stopped && ilvl_ < nlevels - 1) phase_merge(lg, sl);
+        if (!stopped && ilvl_ < nlevels - 1) {
+            phase_merge(lg, sl);
+            phases_done_[ilvl_] |= 8;
+            state_phase_ = 3;
+        }
         lg.t_plan_merge = wtime() - p0;
         CK(cudaEventRecord(ev[ilvl_ * 5 + 4], st_));
         lg.dofs_left_spars = ndofs_left();
-        lg.fact_nnz = nnz_;
         lg.t_host = wtime() - h0;
         if (ilvl_ == stop_level && stop_phase == 3) stopped = true;
     }
@@ -1488,6 +1325,121 @@ void Tree::factorize() {
     factorized_ = !stopped;
 }
 
+// Flop / byte / nnz model of SURVEY.md 8(d) and the reference's Log (util.h:366-401), evaluated after the fact from
+// the plan and the cluster sizes recorded before the elimination and after the sparsification of every level.
+void Tree::finalize_logs() {
+    if (logs_final_) return;
+    logs_final_ = true;
+    const bool plu = scale_kind == PLU;
+    nnz_ = 0;
+    for (int l = 0; l < nlevels; l++) {
+        if (!phases_done_[l]) break;
+        LevelLog& lg = log[l];
+        const SymLevel& L = plan_.lv[l];
+        const std::vector<int>& bottom = bottoms_[l];
+        if (bottom.empty()) continue;
+        const int first = bottom.front();
+        const std::vector<int>& pre = size_pre_[l];
+        const std::vector<int>& post = size_post_[l];
+        auto P = [&](int c) { return (double)pre[c - first]; };
+        auto Q = [&](int c) { return (double)post[c - first]; };
+        lg.fl_pivot = lg.fl_panel = lg.fl_schur = lg.fl_rrqr_rank = lg.fl_rrqr_full = 0;
+        lg.by_scale = lg.by_rrqr = lg.by_merge = 0;
+        lg.rank_before = lg.rank_after = 0;
+        lg.nspars = 0;
+        lg.nbrs = 0;
+        long long nz = 0;
+        // eliminate
+        for (int s : L.E) {
+            const double n = P(s);
+            lg.fl_pivot += (plu ? 2.0 : 1.0) * n * n * n / 3.0;
+            nz += plu ? (long long)(n * n + 2 * n) : (long long)(n * (n + 1) / 2);
+        }
+        for (const SymTrsm& t : L.e_out) {
+            lg.fl_panel += P(t.cm) * P(t.cn) * P(t.cn);
+            nz += (long long)(P(t.cm) * P(t.cn));
+        }
+        for (const SymTrsm& t : L.e_in) {
+            lg.fl_panel += P(t.cm) * P(t.cn) * P(t.cn);
+            nz += (long long)(P(t.cm) * P(t.cn));
+        }
+        for (const SymGemm& g : L.e_gemm) {
+            const double m = P(plan_.en2[g.target]), n = P(plan_.en1[g.target]);
+            for (int ci = 0; ci < g.nc; ci++) {
+                const SymCon& c = L.e_con[g.c0 + ci];
+                const double k = P(plan_.en1[c.e1]);
+                if (plan_.symmetric && plan_.en2[c.e1] == plan_.en2[c.e2]) lg.fl_schur += m * (m + 1) * k;
+                else lg.fl_schur += 2.0 * m * n * k;
+            }
+        }
+        // scale
+        if (phases_done_[l] & 2) {
+            for (int c : L.S) {
+                const double n = P(c);
+                lg.fl_pivot += (plu ? 2.0 : 1.0) * n * n * n / 3.0;
+                nz += plu ? (long long)(n * n + 2 * n) : (long long)(n * (n + 1) / 2);
+                lg.by_scale += 16.0 * n * n;
+            }
+            for (const SymTrsm& t : L.s_right) {
+                const double rows = P(t.cm), cols = P(t.cn);
+                lg.fl_panel += rows * cols * cols + cols * rows * rows;
+                lg.by_scale += 16.0 * rows * cols;
+            }
+        }
+        // sparsify
+        if (phases_done_[l] & 4) {
+            std::vector<char> is_task(pre.size(), 0);
+            for (const SymQr& q : L.q) is_task[q.cluster - first] = 1;
+            for (const SymQr& q : L.q) {
+                const double r = P(q.cluster), rk = Q(q.cluster);
+                double cc = 0;  // columns seen: earlier sparsified neighbours had already shrunk (tree.cpp:1194-1200)
+                for (int k = 0; k < q.nsrc; k++) {
+                    const int nbr = L.qs[q.src0 + k].nbr;
+                    cc += (is_task[nbr - first] && nbr < q.cluster) ? Q(nbr) : P(nbr);
+                }
+                double rf = std::min(r, cc);
+                if (tol >= 1.0 || cc == 0) rf = 0;
+                lg.rank_before += (long long)r;
+                lg.nspars++;
+                lg.nbrs += (long long)cc;
+                lg.fl_rrqr_full += 4 * r * cc * rf - 2 * (r + cc) * rf * rf + (4.0 / 3.0) * rf * rf * rf;
+                lg.fl_rrqr_rank += 4 * r * cc * rk - 2 * (r + cc) * rk * rk + (4.0 / 3.0) * rk * rk * rk;
+                lg.by_rrqr += 8 * r * cc + 8 * rk * cc + 8 * r * rk;
+                if (rk < r) {
+                    nz += (long long)(r * r);  // Orthogonal (operations.cpp:159-161)
+                    const double m = r - rk;
+                    // Scaling op of the dropped sibling (tree.cpp:1342): ScalingLLT(I) or ScalingPLUQ(I, I, id, id)
+                    nz += plu ? (long long)(m * m + 2 * m) : (long long)(m * (m + 1) / 2);
+                }
+                lg.rank_after += (long long)rk;
+            }
+        }
+        // merge
+        if (phases_done_[l] & 8) {
+            for (const SymCopy& t : L.m_copy) lg.by_merge += 8.0 * Q(t.c1) * Q(t.c2);
+            // parent blocks (zero fill included): sizes of the parents = sums of the children's sizes
+            const std::vector<int>& parents = bottoms_[l + 1];
+            std::vector<double> psize(parents.empty() ? 0 : parents.back() - parents.front() + 1, 0.0);
+            for (int p : parents)
+                for (int c = cl_[p].child_begin; c < cl_[p].child_end; c++) psize[p - parents.front()] += Q(c);
+            for (int e = L.medge0; e < L.medge1; e++)
+                lg.by_merge += 8.0 * psize[plan_.en1[e] - parents.front()] * psize[plan_.en2[e] - parents.front()];
+        }
+        nnz_ += nz;
+        lg.fact_nnz = nnz_;
+    }
+}
+
+const std::vector<LevelLog>& Tree::logs() {
+    finalize_logs();
+    return log;
+}
+
+long long Tree::nnz() {
+    finalize_logs();
+    return nnz_;
+}
+
 int Tree::get_stop() const {
     int stop = N;
     for (auto& l : log) {
@@ -1502,7 +1454,7 @@ int Tree::get_stop() const {
 // ------------------------------------------------------------------------------------------------
 void Tree::solve_device(double* x_dev) {
     if (!factorized_) throw std::runtime_error("solve: call factorize first");
-    double* xleaf = cl_[bottoms_[0][0]].x - cl_[bottoms_[0][0]].start;
+    double* xleaf = d_xleaf_;
     launch_gather(N, d_perm_, x_dev, xleaf, st_);  // b = P^T x
     for (int l = 0; l < nlevels; l++) {
         SolveLevel& s = solve_[l];
@@ -1616,41 +1568,53 @@ int Tree::cg(const SpMat& A, const double* rhs, double* x, int iters, double tol
     return result;
 }
 
-// src/tree.cpp:1730-1763 (permuted ordering; both triangles for symmetric kinds)
+// src/tree.cpp:1730-1763 (permuted ordering; both triangles for symmetric kinds). The live blocks at the point
+// where factorize() stopped (parity-test hook) are read off the plan.
 SpMat Tree::trailing_mat() {
     std::vector<Triplet> t;
     std::vector<double> hb;
+    if (!assembled_) throw std::runtime_error("trailing_mat: call assemble first");
     CK(cudaStreamSynchronize(st_));
-    for (int s : bottoms_[current_bottom_]) {
-        const Cluster& cs = cl_[s];
-        if (cs.eliminated) continue;
-        for (int eid : cs.out) {
-            const Edge& e = ed_[eid];
-            const Cluster& c2 = cl_[e.n2];
-            int rows = c2.size, cols = cs.size;
-            hb.assign((size_t)rows * cols, 0.0);
-            if (e.identity) {
-                for (int i = 0; i < rows; i++) hb[i + (size_t)i * rows] = 1.0;
-            } else if (rows > 0 && cols > 0) {
-                CK(cudaMemcpy2D(hb.data(), sizeof(double) * rows, e.A, sizeof(double) * e.ld, sizeof(double) * rows,
-                                cols, cudaMemcpyDeviceToHost));
-            }
-            for (int j = 0; j < cols; j++)
-                for (int i = 0; i < rows; i++) {
-                    int gi = c2.start + i, gj = cs.start + j;
-                    double v = hb[i + (size_t)j * rows];
-                    if (symmetry()) {
-                        if (gi > gj) {
-                            t.push_back({gj, gi, v});
-                            t.push_back({gi, gj, v});
-                        } else if (gi == gj) {
-                            t.push_back({gi, gi, v});
-                        }
-                    } else {
-                        t.push_back({gi, gj, v});
-                    }
-                }
+    std::vector<int> live;
+    bool piv_identity = false;
+    if (state_level_ < 0) {
+        for (int e = 0; e < plan_.nleaf_edges; e++) live.push_back(e);
+    } else if (state_phase_ == 3) {
+        const SymLevel& L = plan_.lv[state_level_];
+        for (int e = L.medge0; e < L.medge1; e++) live.push_back(e);
+    } else {
+        const SymLevel& L = plan_.lv[state_level_];
+        for (int e : L.s_piv) live.push_back(e);
+        for (const SymTrsm& r : L.s_right) live.push_back(r.eB);
+        piv_identity = state_phase_ >= 1;
+    }
+    for (int e : live) {
+        const int n1 = plan_.en1[e], n2 = plan_.en2[e];
+        const Cluster& cs = cl_[n1];
+        const Cluster& c2 = cl_[n2];
+        int rows = c2.size, cols = cs.size;
+        hb.assign((size_t)rows * cols, 0.0);
+        if (n1 == n2 && piv_identity) {
+            for (int i = 0; i < rows; i++) hb[i + (size_t)i * rows] = 1.0;
+        } else if (rows > 0 && cols > 0) {
+            CK(cudaMemcpy2D(hb.data(), sizeof(double) * rows, h_eptr_[e], sizeof(double) * h_eld_[e], sizeof(double) * rows,
+                            cols, cudaMemcpyDeviceToHost));
         }
+        for (int j = 0; j < cols; j++)
+            for (int i = 0; i < rows; i++) {
+                int gi = c2.start + i, gj = cs.start + j;
+                double v = hb[i + (size_t)j * rows];
+                if (symmetry()) {
+                    if (gi > gj) {
+                        t.push_back({gj, gi, v});
+                        t.push_back({gi, gj, v});
+                    } else if (gi == gj) {
+                        t.push_back({gi, gi, v});
+                    }
+                } else {
+                    t.push_back({gi, gj, v});
+                }
+            }
     }
     return from_triplets(N, N, t);
 }

@@ -105,7 +105,7 @@ class Tree {
     void solve(double* x_host);       // in place, host vector of length N
     void solve_device(double* x_dev); // in place, device vector of length N (natural ordering)
     int cg(const SpMat& A, const double* rhs, double* x, int iters, double tol, bool verb, double* seconds);
-    long long nnz() const { return nnz_; }
+    long long nnz();
     int get_stop() const;
     SpMat trailing_mat();
     void stats(std::vector<int>& id, std::vector<int>& size, std::vector<int>& rank) const;
@@ -113,7 +113,9 @@ class Tree {
     int nlevels;
     int N = 0;
     Ordering ord;
-    std::vector<LevelLog> log;
+    std::vector<LevelLog> log;   // call logs() for the completed flop / byte / nnz model
+    const std::vector<LevelLog>& logs();
+    double analyze_seconds() const { return t_analyze_; }
     double t_factorize_device = 0;  // seconds, CUDA events
     size_t arena_bytes() const { return arena_ ? arena_->used() : 0; }
     long long launches_total = 0;
@@ -125,18 +127,6 @@ class Tree {
         int parent;                  // cluster id or -1
         int child_begin, child_end;  // cluster ids [begin,end)
         int hlevel;                  // hierarchy level at which it lives
-        std::vector<int> out;        // edge ids, pivot first
-        std::vector<int> in;         // edge ids
-        double* x = nullptr;         // device solution segment (orig_size)
-        double* ud = nullptr;        // PLU: diag(U), swap sequence and permutation of the current pivot
-        int* ipiv = nullptr;
-        int* perm = nullptr;
-    };
-    struct Edge {
-        int n1, n2;       // block A[rows of n2, cols of n1]
-        double* A;        // device
-        int ld;
-        bool original, alive, identity;
     };
     struct SolveLevel {
         // forward order: elim trsv -> elim gemv -> scale trsv -> house -> merge copy
@@ -147,15 +137,43 @@ class Tree {
         HouseTask* house = nullptr; int n_house = 0;
         XCopyTask* m_fwd = nullptr; XCopyTask* m_bwd = nullptr; int n_merge = 0;
     };
+    // device copies of the id arrays of one SymLevel (symbolic.hpp), resident in sym_arena_
+    struct DevLevel {
+        int *E = nullptr, *e_piv = nullptr, *S = nullptr, *s_piv = nullptr, *children = nullptr;
+        SymTrsm *e_out = nullptr, *e_in = nullptr, *s_right = nullptr, *s_left = nullptr;
+        SymGemm* e_gemm = nullptr;
+        SymCon* e_con = nullptr;
+        SymGemv *e_gf = nullptr, *e_gb = nullptr;
+        SymGemvCon *e_gfc = nullptr, *e_gbc = nullptr;
+        SymQrSrc* qs = nullptr;
+        SymCopy* m_copy = nullptr;
+        int n_children = 0;
+    };
 
     DenseMat Xcoo_;
     bool have_coords_ = false;
     std::vector<Cluster> cl_;               // index == order id
     std::vector<std::vector<int>> bottoms_; // cluster ids per hierarchy level
-    std::vector<Edge> ed_;
     int current_bottom_ = 0, ilvl_ = 0;
     long long nnz_ = 0;
     bool factorized_ = false;
+    bool assembled_ = false;
+    int state_level_ = -1, state_phase_ = -1;  // last completed (level, phase) of factorize(); -1: just assembled
+    std::vector<int> phases_done_;             // per level, bit p = phase p ran
+
+    // symbolic plan: built by the first assemble() of a (partition, pattern) pair, reused afterwards
+    SymbolicPlan plan_;
+    bool plan_valid_ = false;
+    int ord_serial_ = 0, plan_ord_serial_ = -1;
+    std::vector<int> pat_colptr_, pat_rowind_;  // pattern the plan and the value map were built for
+    std::vector<size_t> leaf_off_;              // element offset of every leaf block in the assembled buffer
+    size_t leaf_total_ = 0;
+    double t_analyze_ = 0;
+    DeviceArena* sym_arena_ = nullptr;          // plan arrays + value map (persistent across assemble calls)
+    std::vector<DevLevel> dplan_;
+    unsigned* d_valmap_ = nullptr;
+    int *d_en1_ = nullptr, *d_en2_ = nullptr, *d_parent_ = nullptr;
+    void analyze(const SpMat& A);
 
     cudaStream_t st_ = nullptr;
     static constexpr int kSide = 4;  // side streams for independent launches of one wavefront
@@ -164,20 +182,36 @@ class Tree {
     DeviceArena* arena_ = nullptr;    // blocks, factors, solve descriptors, x
     DeviceArena* scratch_ = nullptr;  // per-level descriptors + RRQR workspaces
     Stager stager_;
-    int* d_csize_ = nullptr;
     int* d_err_ = nullptr;
     double* d_xnat_ = nullptr;  // N, natural-order staging for solve
+    double* d_xleaf_ = nullptr;
     int* d_perm_ = nullptr;
     std::vector<SolveLevel> solve_;
-    std::vector<int> h_csize_;
+    // numeric tables (host mirror + device): current cluster sizes, block pointers / leading dimensions, solution
+    // segments, offsets of children inside their parents
+    std::vector<int> h_csize_, h_eld_, h_pos_;
+    std::vector<double*> h_eptr_, h_xptr_;
+    int *d_csize_ = nullptr, *d_eld_ = nullptr, *d_pos_ = nullptr;
+    double **d_eptr_ = nullptr, **d_xptr_ = nullptr;
+    int *d_mid_ = nullptr, *d_cnt_ = nullptr;  // device work lists of the plan-driven kernels
+    int cnt_next_ = 0;
+    DevTables tab_{};
+    // PLU: diag(U), swap sequence and permutation of the current pivot of every cluster
+    std::vector<double*> h_ud_;
+    std::vector<int*> h_ipiv_, h_pperm_;
+    // cluster sizes before the elimination and after the sparsification of every level: the flop / byte / nnz
+    // model is evaluated from these after the factorization (finalize_logs), off the critical path
+    std::vector<std::vector<int>> size_pre_, size_post_;
+    std::vector<std::vector<int>> qr_cols_;  // columns seen by every RRQR task (reference: Asn.cols())
+    bool logs_final_ = true;
+    void finalize_logs();
 
     bool symmetry() const { return symm_kind == SPD || symm_kind == SYM; }
     void ensure_device();
     void free_device();
-    int find_out(int c, int n2) const;
-    int new_edge(int n1, int n2, double* A, int ld, bool original);
     template <class T>
     T* to_device(const std::vector<T>& v, DeviceArena* where);
+    int* next_counter();
 
     void phase_eliminate(LevelLog& lg, SolveLevel& sl);
     void phase_scale(LevelLog& lg, SolveLevel& sl);
@@ -185,14 +219,17 @@ class Tree {
     void phase_merge(LevelLog& lg, SolveLevel& sl);
     void phase_eliminate_plu(LevelLog& lg, SolveLevel& sl);
     void phase_scale_plu(LevelLog& lg, SolveLevel& sl);
+    void alloc_edges(int e0, int e1, bool zero, LevelLog& lg);
     void run_getrf(std::vector<GetrfTask>& tasks, LevelLog& lg);
     void run_rowperm(std::vector<RowPermTask>& tasks, LevelLog& lg);
-    void alloc_plu(Cluster& cs);
+    void alloc_plu(int c);
     void run_potrf(std::vector<PotrfTask>& tasks, LevelLog& lg);
     void run_trsm(int mode, std::vector<TrsmTask>& tasks, LevelLog& lg);
     void run_gemm(std::vector<GemmTask>& tasks, std::vector<GemmContrib>& contribs, LevelLog& lg);
     void check_error();
     int ndofs_left() const;
+    int level_max_size() const;
+    TrsmTask host_trsm(const SymTrsm& t, const double* diag) const;
     struct FamEvent { int fam; cudaEvent_t a, b; };
     std::vector<FamEvent> fam_events_;
     std::vector<cudaEvent_t> ev_pool_;
