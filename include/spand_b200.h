@@ -83,6 +83,10 @@ const char* spand_log_field_name(int i);
 int spand_get_log(spand_tree* t, double* out);
 /* device time of the last factorize(), CUDA events on the factorization stream, seconds */
 double spand_factorize_seconds(spand_tree* t);
+/* host seconds of the symbolic analysis done by the first spand_assemble() of a (partition, pattern) pair; later
+ * spand_assemble() calls with the same pattern reuse the plan (no counterpart in the reference, whose list
+ * manipulations src/tree.cpp:748-793, :1133-1184 are replayed inside every factorize) */
+double spand_analyze_seconds(spand_tree* t);
 long long spand_kernel_launches(spand_tree* t);
 long long spand_arena_bytes(spand_tree* t);
 

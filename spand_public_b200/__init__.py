@@ -28,7 +28,7 @@ EXPORTS = [
     "spand_set_coords", "spand_set_stop", "spand_partition", "spand_get_partition", "spand_get_perm", "spand_get_N",
     "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_nnz", "spand_get_stop",
     "spand_get_nlevels", "spand_num_clusters", "spand_get_stats", "spand_log_fields", "spand_log_field_name",
-    "spand_get_log", "spand_factorize_seconds", "spand_kernel_launches", "spand_arena_bytes", "spand_trailing",
+    "spand_get_log", "spand_factorize_seconds", "spand_analyze_seconds", "spand_kernel_launches", "spand_arena_bytes", "spand_trailing",
     "spand_util_random", "spand_util_linspace_nd", "spand_util_neglapl", "spand_util_aniso", "spand_util_mm_read",
     "spand_util_mm_read_dense", "spand_set_profile", "spand_num_families", "spand_family_name", "spand_get_family_stats",
 ]
@@ -82,6 +82,8 @@ def lib():
     L.spand_get_log.argtypes = [_p, _dp]
     L.spand_factorize_seconds.restype = _d
     L.spand_factorize_seconds.argtypes = [_p]
+    L.spand_analyze_seconds.restype = _d
+    L.spand_analyze_seconds.argtypes = [_p]
     L.spand_kernel_launches.restype = C.c_longlong
     L.spand_kernel_launches.argtypes = [_p]
     L.spand_arena_bytes.restype = C.c_longlong
@@ -259,6 +261,7 @@ class Tree:
     def get_stop(self): return self._l.spand_get_stop(self._h)
     def get_N(self): return self._l.spand_get_N(self._h)
     def factorize_seconds(self): return self._l.spand_factorize_seconds(self._h)
+    def analyze_seconds(self): return self._l.spand_analyze_seconds(self._h)
     def kernel_launches(self): return self._l.spand_kernel_launches(self._h)
     def arena_bytes(self): return self._l.spand_arena_bytes(self._h)
 

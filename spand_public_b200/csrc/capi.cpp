@@ -143,6 +143,7 @@ int spand_get_log(spand_tree* t, double* out) {
     return 0;
 }
 double spand_factorize_seconds(spand_tree* t) { return t->t.t_factorize_device; }
+double spand_analyze_seconds(spand_tree* t) { return t->t.analyze_seconds(); }
 long long spand_kernel_launches(spand_tree* t) { return t->t.launches_total; }
 long long spand_arena_bytes(spand_tree* t) { return (long long)t->t.arena_bytes(); }
 int spand_trailing(spand_tree* t, int* colptr, int* rowind, double* val) {

@@ -434,7 +434,7 @@ __device__ __forceinline__ void gemm_tile64(double* C, int ldc, int m, int n, in
             }
         }
     }
-    bool zero = (flags & GEMM_ZERO_INIT) != 0, lower = (flags & GEMM_LOWER) != 0;
+    bool zero = (flags & GEMM_ZERO_INIT) != 0, lower = (flags & GEMM_LOWER) != 0, pos = (flags & GEMM_POS) != 0;
 #pragma unroll
     for (int mi = 0; mi < 2; mi++)
 #pragma unroll
@@ -445,7 +445,8 @@ __device__ __forceinline__ void gemm_tile64(double* C, int ldc, int m, int n, in
                 int gj = col0 + wn * 32 + ni * 8 + 2 * (lane & 3) + e;
                 if (gi < m && gj < n && (!lower || gi >= gj)) {
                     double* p = C + gi + (size_t)gj * ldc;
-                    *p = (zero ? 0.0 : *p) - acc[mi][ni][e];
+                    const double v = zero ? 0.0 : *p;
+                    *p = pos ? v + acc[mi][ni][e] : v - acc[mi][ni][e];
                 }
             }
     __syncthreads();
@@ -468,6 +469,82 @@ __global__ void __launch_bounds__(256) gemm_tiled_kernel(const GemmTask* __restr
     if ((t.flags & GEMM_LOWER) && tile_c > tile_r) return;
     const GemmContrib* cc = contribs + t.c0;
     gemm_tile64(t.C, t.ldc, t.m, t.n, t.flags, tile_r * GT, tile_c * GT, t.nc, [cc](int ci) { return cc[ci]; });
+}
+
+
+// Inverse of every 64 x 64 diagonal block of a lower triangle (thread c: column c by forward substitution); the
+// blocks are stored 64 x 64 column-major, zero outside the triangle.
+__global__ void __launch_bounds__(NB) trtri_kernel(const TrtriTask* __restrict__ tasks) {
+    const TrtriTask t = tasks[blockIdx.x];
+    const int j0 = blockIdx.y * NB;
+    if (j0 >= t.n) return;
+    const int nb = min(NB, t.n - j0);
+    __shared__ double S[NB * LDS];  // S[p * LDS + i] = L(i, p)
+    const int c = threadIdx.x;
+    const double* T = t.T + j0 + (size_t)j0 * t.ldt;
+    for (int p = 0; p < nb; p++)
+        if (c >= p && c < nb) S[p * LDS + c] = T[c + (size_t)p * t.ldt];
+    __syncthreads();
+    double* out = t.inv + (size_t)blockIdx.y * NB * NB + (size_t)c * NB;
+    double x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) x[i] = 0.0;
+    if (c < nb) {
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            if (i >= c && i < nb) {
+                double v = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int p = 0; p < NB; p++)
+                    if (p >= c && p < i) v -= S[p * LDS + i] * x[p];
+                x[i] = v / S[i * LDS + i];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) out[i] = x[i];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) trsm_strip_kernel(const TrsmTask* __restrict__ tasks, int nt,
+                                                         const int* __restrict__ strip_prefix) {
+    int b = blockIdx.x;
+    int lo = 0, hi = nt - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (strip_prefix[mid] <= b) lo = mid;
+        else hi = mid - 1;
+    }
+    const TrsmTask t = tasks[lo];
+    const int f0 = (b - strip_prefix[lo]) * NB;
+    const int fw = min(NB, t.m - f0);
+    const int nblk = (t.n + NB - 1) / NB;
+    for (int j = 0; j < nblk; j++) {
+        const int j0 = j * NB, nb = min(NB, t.n - j0);
+        GemmContrib c;
+        const double* inv = t.inv + (size_t)j * NB * NB;
+        if (MODE == TRSM_RLT) {
+            // X_j = (B_j - X_{0:j} L_{j,0:j}^T) inv(L_jj)^T on the row strip [f0, f0 + fw)
+            double* Bs = t.B + f0;
+            double* C = Bs + (size_t)j0 * t.ldb;
+            if (j > 0) {
+                c = GemmContrib{Bs, t.T + j0, t.ldb, t.ldt, j0};
+                gemm_tile64(C, t.ldb, fw, nb, 0, 0, 0, 1, [c](int) { return c; });
+            }
+            c = GemmContrib{C, inv, t.ldb, NB, nb};
+            gemm_tile64(C, t.ldb, fw, nb, GEMM_ZERO_INIT | GEMM_POS, 0, 0, 1, [c](int) { return c; });
+        } else {
+            // X_j = inv(L_jj) (B_j - L_{j,0:j} X_{0:j}) on the column strip [f0, f0 + fw)
+            double* Bs = t.B + (size_t)f0 * t.ldb;
+            double* C = Bs + j0;
+            if (j > 0) {
+                c = GemmContrib{t.T + j0, Bs, t.ldt, t.ldb, j0};
+                gemm_tile64(C, t.ldb, nb, fw, GEMM_NN, 0, 0, 1, [c](int) { return c; });
+            }
+            c = GemmContrib{inv, C, NB, t.ldb, nb};
+            gemm_tile64(C, t.ldb, nb, fw, GEMM_NN | GEMM_ZERO_INIT | GEMM_POS, 0, 0, 1, [c](int) { return c; });
+        }
+    }
 }
 
 // Tiny targets: one warp per target, plain FMAs out of L1/L2.
@@ -1124,6 +1201,17 @@ void launch_trsm_step(int mode, const TrsmTask* t, int nt, int j0, int max_m, cu
     else if (mode == TRSM_LLN) trsm_step_kernel<TRSM_LLN><<<grid, NB, smem, st>>>(t, j0);
     else if (mode == TRSM_LLU) trsm_step_kernel<TRSM_LLU><<<grid, NB, smem, st>>>(t, j0);
     else trsm_step_kernel<TRSM_RUN><<<grid, NB, smem, st>>>(t, j0);
+}
+
+void launch_trtri(const TrtriTask* t, int nt, int max_n, cudaStream_t st) {
+    if (nt <= 0 || max_n <= 0) return;
+    dim3 grid(nt, (max_n + NB - 1) / NB);
+    trtri_kernel<<<grid, NB, 0, st>>>(t);
+}
+void launch_trsm_strip(int mode, const TrsmTask* t, int nt, const int* strip_prefix, int total_strips, cudaStream_t st) {
+    if (nt <= 0 || total_strips <= 0) return;
+    if (mode == TRSM_RLT) trsm_strip_kernel<TRSM_RLT><<<total_strips, 256, 0, st>>>(t, nt, strip_prefix);
+    else trsm_strip_kernel<TRSM_LLN><<<total_strips, 256, 0, st>>>(t, nt, strip_prefix);
 }
 
 void launch_getrf_small(const GetrfTask* t, int nt, int* err, cudaStream_t st) {

@@ -40,6 +40,13 @@ struct TrsmTask {
     int m;  // free dimension of B
     int n;  // triangle dimension
     const double* diag;  // nullptr: diagonal of T; else the n diagonal entries (PLU keeps diag(U) beside the block)
+    const double* inv;   // strip kernels only: inverses of the 64 x 64 diagonal blocks of T, 4096 doubles each
+};
+
+struct TrtriTask {  // inverses of the diagonal blocks of one triangle
+    const double* T;
+    int ldt, n;
+    double* inv;
 };
 
 // PLU pivot (src/util.cpp:183-227): on exit A holds L (lower, with its non-unit diagonal |d|^1/2) and the strictly
@@ -64,7 +71,7 @@ struct GemmContrib {
     int lda, ldb, k;
 };
 
-enum GemmFlags { GEMM_LOWER = 1, GEMM_ZERO_INIT = 2, GEMM_NN = 4 };
+enum GemmFlags { GEMM_LOWER = 1, GEMM_ZERO_INIT = 2, GEMM_NN = 4, GEMM_POS = 8 };  // POS: C = (0|C) + sum
 
 struct GemmTask {
     double* C;  // m x n, C = (ZERO_INIT ? 0 : C) - sum_c A_c op(B_c)
@@ -81,6 +88,7 @@ struct QrSrc {
 };
 
 constexpr int QR_NB = 16;   // block size of the blocked QRCP (dlaqps-like)
+constexpr int QR_NBS = 8;   // block size of the streaming shape (panel in global memory, 64 registers per thread)
 constexpr int QR_FLD = 17;  // row stride of the F block in shared memory (odd: conflict-free)
 
 struct QrTask {
@@ -138,6 +146,11 @@ struct XCopyTask {
 // All launchers are asynchronous on `st`. `err` is a device int: bit 0 = non-SPD pivot.
 void launch_potrf_step(const PotrfTask* t, int nt, int j0, int* err, cudaStream_t st);
 void launch_trsm_step(int mode, const TrsmTask* t, int nt, int j0, int max_m, cudaStream_t st);
+// Whole triangular solves as DMMA GEMMs (TRSM_RLT / TRSM_LLN): one CTA per 64-wide strip of the free dimension sweeps
+// the 64-wide blocks of the triangle, X_j = (B_j - sum_{p<j} X_p T_jp^T) inv(T_jj)^T. strip_prefix: nt + 1 exclusive
+// prefix of ceil(m / 64).
+void launch_trtri(const TrtriTask* t, int nt, int max_n, cudaStream_t st);
+void launch_trsm_strip(int mode, const TrsmTask* t, int nt, const int* strip_prefix, int total_strips, cudaStream_t st);
 // GETRF with partial pivoting. n <= 64: one launch does everything (factor, split_LU, perm). Larger: right-looking
 // over 64-wide panels: launch_getrf_panel (pivoting inside the panel) -> launch_getrf_laswp (row swaps outside the
 // panel) -> TRSM_LLU + GEMM from the host driver -> launch_getrf_finish (split_LU + swap2perm) at the end.

@@ -82,9 +82,10 @@ __device__ __forceinline__ Cand warp_best(Cand b, int width) {
 
 __host__ __device__ constexpr int ceil_pow2(int x) { int p = 1; while (p < x) p *= 2; return p; }
 
-template <int G, int NT, bool SMEM_PANEL>
-__global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrqr_blocked_kernel(const QrTask* __restrict__ tasks,
-                                                          const QrSrc* __restrict__ srcs, int* csize, double tol) {
+// QNB: compile-time bound of the block size (t.nb <= QNB); MINB: CTAs per SM the register budget is sized for
+template <int G, int NT, bool SMEM_PANEL, int QNB, int MINB>
+__global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __restrict__ tasks,
+                                                                const QrSrc* __restrict__ srcs, int* csize, double tol) {
     constexpr int NW = NT / 32;
     constexpr int NC = 2;  // columns a lane group works on at once (shares the v loads)
     const int task_id = blockIdx.x / G;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrq
     __shared__ double alpha_s[2];
     __shared__ Cand redc[2][NW];
     __shared__ CandRec rec[2][G];
-    __shared__ double aux[QR_NB];
+    __shared__ double aux[QNB];
     extern __shared__ __align__(16) double dsm[];
 
     int cols = 0;
@@ -319,47 +320,73 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrq
         const double2* v2 = reinterpret_cast<const double2*>(vj);
         if constexpr (!SMEM_PANEL) {
             // Panel in global memory (L == 32): a warp takes WB columns at once. All loads of the batch are in flight
-            // together, the WB x 32 partial sums are transpose-reduced with WB + 1 shuffles, and the scalar epilogue of
-            // the WB columns runs lane-parallel (column c on lanes 4c..4c+3).
-            constexpr int WB = 8;
-            for (int base = 0; base < ncl; base += WB * NW) {
-                const int myc = lane >> 2;
-                int my_cl = base + myc * NW + warp, my_p = -1;
+            // together, the WB x 32 partial sums are transpose-reduced with shuffles, and the scalar epilogue of the WB
+            // columns runs lane-parallel (column c on lanes c * LPC .. c * LPC + LPC - 1).
+            // WB consecutive columns per warp pass (one base pointer + WB small offsets, so that the WB loads of a
+            // row chunk are issued back to back into distinct registers: the memory-level parallelism of this loop
+            // is what bounds the kernel). Columns already pivoted are streamed too (a fraction k / cols).
+            constexpr int WB = (MINB == 1) ? 8 : 4;
+            constexpr int LPC = 32 / WB;  // lanes per column in the scalar epilogue
+            const int ld2 = ld >> 1;
+            for (int first = warp * WB; first < ncl; first += WB * NW) {
+                const int myc = lane / LPC;
+                int my_cl = first + myc, my_p = -1;
                 const bool my_valid = my_cl < ncl;
                 if (my_valid) {
                     my_p = pos[my_cl];
                     if (c_lo + my_cl == pcol) {
                         my_p = k;
-                        if ((lane & 3) == 0) pos[my_cl] = k;
+                        if ((lane & (LPC - 1)) == 0) pos[my_cl] = k;
                     } else if (my_p == k) {
                         my_p = ppos;
-                        if ((lane & 3) == 0) pos[my_cl] = ppos;
+                        if ((lane & (LPC - 1)) == 0) pos[my_cl] = ppos;
                     }
                 }
                 const bool my_act = my_valid && my_p > k;
                 if (!my_act) my_cl = 0;
-                const unsigned actmask = __ballot_sync(FULL, my_act);
-                if (actmask == 0) continue;
+                if (__ballot_sync(FULL, my_act) == 0) continue;
                 double s[WB];
-                const double2* c2[WB];
+                int coff[WB];
+                const int nhere = min(WB, ncl - first);
 #pragma unroll
                 for (int c = 0; c < WB; c++) {
                     s[c] = 0.0;
-                    const int clc = (actmask >> (4 * c)) & 1 ? base + c * NW + warp : 0;
-                    c2[c] = reinterpret_cast<const double2*>(P + (size_t)clc * ld);
+                    coff[c] = min(c, nhere - 1) * ld2;  // clamp: columns past the slab re-read the last one
                 }
-                for (int i2 = (k >> 1) + lane; i2 < npair; i2 += 32) {
-                    const double2 vv = v2[i2];
+                const double2* cb = reinterpret_cast<const double2*>(P) + (size_t)first * ld2;
+                int i2 = (k >> 1) + lane;
+                if constexpr (MINB == 1) {
+                    for (; i2 + 32 < npair; i2 += 64) {
+                        const double2 v0 = v2[i2], v1 = v2[i2 + 32];
+                        double2 a0[WB], a1[WB];
 #pragma unroll
-                    for (int c = 0; c < WB; c++)
-                        if ((actmask >> (4 * c)) & 1) {
-                            const double2 a = c2[c][i2];
-                            s[c] = fma(a.x, vv.x, s[c]);
-                            s[c] = fma(a.y, vv.y, s[c]);
+                        for (int c = 0; c < WB; c++) {
+                            a0[c] = cb[coff[c] + i2];
+                            a1[c] = cb[coff[c] + i2 + 32];
                         }
-                }
 #pragma unroll
-                for (int h = WB / 2, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+                        for (int c = 0; c < WB; c++) {
+                            s[c] = fma(a0[c].x, v0.x, s[c]);
+                            s[c] = fma(a0[c].y, v0.y, s[c]);
+                            s[c] = fma(a1[c].x, v1.x, s[c]);
+                            s[c] = fma(a1[c].y, v1.y, s[c]);
+                        }
+                    }
+                }
+                for (; i2 < npair; i2 += 32) {
+                    const double2 vv = v2[i2];
+                    double2 a0[WB];
+#pragma unroll
+                    for (int c = 0; c < WB; c++) a0[c] = cb[coff[c] + i2];
+#pragma unroll
+                    for (int c = 0; c < WB; c++) {
+                        s[c] = fma(a0[c].x, vv.x, s[c]);
+                        s[c] = fma(a0[c].y, vv.y, s[c]);
+                    }
+                }
+                int bit = 16;
+#pragma unroll
+                for (int h = WB / 2; h >= 1; h >>= 1, bit >>= 1) {
                     const bool up = (lane & bit) != 0;
 #pragma unroll
                     for (int i = 0; i < h; i++) {
@@ -369,8 +396,8 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrq
                     }
                 }
                 double tot = s[0];
-                tot += __shfl_xor_sync(FULL, tot, 2);
-                tot += __shfl_xor_sync(FULL, tot, 1);
+#pragma unroll
+                for (int o = LPC / 2; o >= 1; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
                 double my_f = 0.0, my_ak = 0.0, my_n1 = 0.0, my_newn = 0.0;
                 bool my_need = false;
                 if (my_act) {
@@ -390,7 +417,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrq
                         my_need = my_newn <= tol3z * nq2[my_cl];
                     }
                 }
-                unsigned nm = __ballot_sync(FULL, my_need && (lane & 3) == 0);
+                unsigned nm = __ballot_sync(FULL, my_need && (lane & (LPC - 1)) == 0);
                 while (nm) {
                     const int srcl = __ffs(nm) - 1;
                     nm &= nm - 1;
@@ -406,9 +433,9 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrq
                         q += u * u;
                     }
                     q = group_sum(q, 32);
-                    if ((lane >> 2) == (srcl >> 2)) my_newn = q;
+                    if ((lane / LPC) == (srcl / LPC)) my_newn = q;
                 }
-                if (my_act && (lane & 3) == 0) {
+                if (my_act && (lane & (LPC - 1)) == 0) {
                     Fs[(size_t)my_cl * FLD + j] = my_f;
                     P[k + (size_t)my_cl * ld] = my_ak;
                     if (my_n1 != 0.0) {
@@ -525,13 +552,13 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrq
                 const int cl = base + grp;
                 if (cl >= ncl || pos[cl] < kend) continue;
                 double* cj = P + (size_t)cl * ld;
-                double f[QR_NB];
+                double f[QNB];
 #pragma unroll
-                for (int tt = 0; tt < QR_NB; tt++) f[tt] = (tt < nb) ? Fs[(size_t)cl * FLD + tt] : 0.0;
+                for (int tt = 0; tt < QNB; tt++) f[tt] = (tt < nb) ? Fs[(size_t)cl * FLD + tt] : 0.0;
                 for (int i = kend + lig; i < rows; i += L) {
                     double a = cj[i];
 #pragma unroll
-                    for (int tt = 0; tt < QR_NB; tt++)
+                    for (int tt = 0; tt < QNB; tt++)
                         if (tt < nb) a -= Vs[i + (size_t)tt * ldv] * f[tt];
                     cj[i] = a;
                 }
@@ -581,9 +608,9 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) rrq
     if (crank == 0 && tid == 0) csize[t.cluster] = rank;
 }
 
-template <int G, int NT, bool SP>
+template <int G, int NT, bool SP, int QNB = QR_NB, int MINB = (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))>
 void launch_one(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int smem, cudaStream_t st) {
-    auto kern = rrqr_blocked_kernel<G, NT, SP>;
+    auto kern = rrqr_blocked_kernel<G, NT, SP, QNB, MINB>;
     static int configured_smem = -1;
     if (smem > configured_smem) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -622,8 +649,19 @@ void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol
                  int smem, cudaStream_t st) {
     if (nt <= 0) return;
     if (!in_smem) {
-        if (G <= 8) launch_one<8, 512, false>(t, nt, s, csize, tol, smem, st);
-        else launch_one<16, 512, false>(t, nt, s, csize, tol, smem, st);
+        if (nthreads >= 512) {
+            if (G <= 8) launch_one<8, 512, false>(t, nt, s, csize, tol, smem, st);
+            else launch_one<16, 512, false>(t, nt, s, csize, tol, smem, st);
+            return;
+        }
+        // streaming shape: panel in global memory, small CTAs, several per SM
+        switch (G) {
+            case 1: launch_one<1, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
+            case 2: launch_one<2, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
+            case 4: launch_one<4, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
+            case 8: launch_one<8, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
+            default: launch_one<16, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
+        }
         return;
     }
     if (nthreads <= 128) {

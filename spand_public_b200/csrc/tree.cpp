@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <stdexcept>
 
 namespace spand {
@@ -576,6 +577,38 @@ void Tree::run_potrf(std::vector<PotrfTask>& tasks, LevelLog& lg) {
 
 void Tree::run_trsm(int mode, std::vector<TrsmTask>& all, LevelLog& lg) {
     if (all.empty()) return;
+    if (mode == TRSM_RLT || mode == TRSM_LLN) {
+        // GEMM-only solves: invert the 64 x 64 diagonal blocks of every distinct triangle, then one CTA per strip
+        std::unordered_map<const double*, double*> invs;
+        std::vector<TrtriTask> tt;
+        std::vector<TrsmTask> tasks;
+        std::vector<int> prefix(1, 0);
+        int max_n = 0;
+        for (auto& t : all) {
+            if (t.m == 0 || t.n == 0) continue;
+            auto it = invs.find(t.T);
+            if (it == invs.end()) {
+                int nblk = (t.n + NB - 1) / NB;
+                double* inv = scratch_->alloc_n<double>((size_t)nblk * NB * NB);
+                it = invs.emplace(t.T, inv).first;
+                tt.push_back({t.T, t.ldt, t.n, inv});
+                max_n = std::max(max_n, t.n);
+            }
+            t.inv = it->second;
+            tasks.push_back(t);
+            prefix.push_back(prefix.back() + (t.m + NB - 1) / NB);
+        }
+        if (tasks.empty()) return;
+        TrtriTask* dtt = to_device(tt, scratch_);
+        TrsmTask* dt = to_device(tasks, scratch_);
+        int* dp = to_device(prefix, scratch_);
+        auto ev = fam_begin(F_TRSM);
+        launch_trtri(dtt, (int)tt.size(), max_n, st_);
+        launch_trsm_strip(mode, dt, (int)tasks.size(), dp, prefix.back(), st_);
+        fam_end(F_TRSM, ev);
+        lg.launches += 2;
+        return;
+    }
     // bin by the free dimension so that the 2-D grid is not dominated by empty strips
     std::vector<TrsmTask> bins[2];
     for (auto& t : all) {
@@ -1000,6 +1033,12 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         // test hooks: force every task through one kernel shape (tests/test_gpu_parity.py)
         const bool force_global = getenv("SPAND_RRQR_FORCE_GLOBAL") != nullptr;
         const int force_g = getenv("SPAND_RRQR_FORCE_G") ? atoi(getenv("SPAND_RRQR_FORCE_G")) : 0;
+        const char* mode_env = getenv("SPAND_RRQR_MODE");  // "smem": cluster kernels with the panel in shared memory
+        const bool smem_mode = mode_env != nullptr && std::string(mode_env) == "smem";
+        const int stream_tmin = getenv("SPAND_RRQR_TMIN") ? atoi(getenv("SPAND_RRQR_TMIN")) : 48;
+        const int stream_ctas = getenv("SPAND_RRQR_CTAS") ? atoi(getenv("SPAND_RRQR_CTAS")) : 1184;
+        const long smem1_max = (getenv("SPAND_RRQR_SMEM1KB") ? atol(getenv("SPAND_RRQR_SMEM1KB")) : 200) * 1024;
+        const double l2_budget = (getenv("SPAND_RRQR_L2MB") ? atof(getenv("SPAND_RRQR_L2MB")) : 128.0) * 1048576.0;
         std::vector<int> per_color(std::max(1, ncolors), 0);
         for (int c : task_color) per_color[c]++;
         for (size_t i = 0; i < nq; i++) {
@@ -1026,6 +1065,35 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             long nd = config(128, 1, true);
             if (!force_global && force_g == 0 && t.rows <= 64 && nd <= kBuckets[2]) {
                 klass[i] = bucket_of(nd);
+                smem_need[i] = (int)nd;
+                continue;
+            }
+            bool stream = !smem_mode && !force_global && force_g == 0 && per_color[task_color[i]] >= stream_tmin;
+            if (stream && config(256, 1, true) <= smem1_max) stream = false;  // fits one CTA's shared memory
+            if (stream) {
+                // Streaming shape: the panel lives in the scratch arena and is read once per Householder step by
+                // small CTAs (256 threads, 64 registers, several per SM); the cluster is as wide as needed for the
+                // wavefront to put about four CTAs on every SM and for the per-CTA state to stay small.
+                t.nb = std::min(QR_NBS, mn);
+                int G = 1;
+                while (G < 16 && per_color[task_color[i]] * G < stream_ctas) G *= 2;
+                // keep the panels of the CTAs resident at the same time (about 592) inside the L2
+                const double panel_bytes = 8.0 * t.rows * t.maxcols;
+                while (G < 16 && ((double)stream_ctas / G) * panel_bytes > l2_budget) G *= 2;
+                nd = config(256, G, false);
+                while (G < 16 && nd > (56 << 10)) {
+                    G *= 2;
+                    nd = config(256, G, false);
+                }
+                while (nd > MAXS && t.nb > 2) {
+                    t.nb /= 2;
+                    nd = config(256, G, false);
+                }
+                if (nd > MAXS) throw std::runtime_error("sparsify: interface cluster too large for the RRQR kernel");
+                int g = 0;
+                while ((1 << g) < G) g++;
+                t.W = scratch_->alloc_n<double>((size_t)t.ld * t.maxcols);
+                klass[i] = (4 << 8) | (g << 4) | bucket_of(nd);
                 smem_need[i] = (int)nd;
                 continue;
             }
@@ -1092,8 +1160,8 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 smem = (smem + 1023) & ~1023;
                 cudaStream_t s = side_[nside % kSide];
                 CK(cudaStreamWaitEvent(s, ev_fork_, 0));
-                launch_rrqr(dt + b, (int)(e - b), ds, d_csize_, tol, G, mode == 0 ? 128 : (mode == 1 ? 256 : 512),
-                            mode != 2, smem, s);
+                launch_rrqr(dt + b, (int)(e - b), ds, d_csize_, tol, G,
+                            mode == 0 ? 128 : ((mode == 1 || mode == 4) ? 256 : 512), mode != 2 && mode != 4, smem, s);
                 nside++;
                 lg.launches++;
                 family_launches[F_RRQR]++;
