@@ -75,6 +75,9 @@ int spand_get_nlevels(spand_tree* t);
  *                                                   include/tree.h:242-251, src/tree.cpp:44-57 */
 int spand_num_clusters(spand_tree* t);
 int spand_get_stats(spand_tree* t, int* id, int* size, int* rank);
+/* first row/column (permuted ordering) and hierarchy level of every cluster, same order as spand_get_stats
+ * (Cluster::get_start(), include/cluster.h:16-116) */
+int spand_get_cluster_layout(spand_tree* t, int* start, int* hlevel);
 
 /* Tree::log / Tree::tprof                           include/tree.h:163-165, include/util.h:262-401
  * spand_log_fields() doubles per level, see spand_log_field_name(i) */
@@ -87,6 +90,15 @@ double spand_factorize_seconds(spand_tree* t);
  * spand_assemble() calls with the same pattern reuse the plan (no counterpart in the reference, whose list
  * manipulations src/tree.cpp:748-793, :1133-1184 are replayed inside every factorize) */
 double spand_analyze_seconds(spand_tree* t);
+/* The symbolic plan on the host only (no device needed): replays the list manipulations of Tree::factorize
+ * (src/tree.cpp:748-793 gemm_edges fill-in, :1133-1184 update_edges) on integers. spand_plan_live_edges returns the
+ * blocks alive after `phase` (0 eliminate, 1 scale, 2 sparsify, 3 merge) of `level` (< 0: as assembled) as
+ * (column cluster, row cluster) ids; pass NULL to get the count. spand_plan_counts fills 12 numbers per level:
+ * eliminated clusters, out-panels, in-panels, fill-in blocks, Schur targets, Schur contributions, scaled clusters,
+ * scaled blocks, RRQR tasks, RRQR wavefronts, merged blocks, merge copies. */
+int spand_plan_analyze(spand_tree* t, int N, const int* colptr, const int* rowind);
+int spand_plan_live_edges(spand_tree* t, int level, int phase, int* n1, int* n2);
+int spand_plan_counts(spand_tree* t, int level, long long* out);
 long long spand_kernel_launches(spand_tree* t);
 long long spand_arena_bytes(spand_tree* t);
 

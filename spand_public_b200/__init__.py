@@ -28,7 +28,8 @@ EXPORTS = [
     "spand_set_coords", "spand_set_stop", "spand_partition", "spand_get_partition", "spand_get_perm", "spand_get_N",
     "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_nnz", "spand_get_stop",
     "spand_get_nlevels", "spand_num_clusters", "spand_get_stats", "spand_log_fields", "spand_log_field_name",
-    "spand_get_log", "spand_factorize_seconds", "spand_analyze_seconds", "spand_kernel_launches", "spand_arena_bytes", "spand_trailing",
+    "spand_get_log", "spand_factorize_seconds", "spand_analyze_seconds", "spand_plan_analyze", "spand_plan_live_edges",
+    "spand_plan_counts", "spand_get_cluster_layout", "spand_kernel_launches", "spand_arena_bytes", "spand_trailing",
     "spand_util_random", "spand_util_linspace_nd", "spand_util_neglapl", "spand_util_aniso", "spand_util_mm_read",
     "spand_util_mm_read_dense", "spand_set_profile", "spand_num_families", "spand_family_name", "spand_get_family_stats",
 ]
@@ -84,6 +85,10 @@ def lib():
     L.spand_factorize_seconds.argtypes = [_p]
     L.spand_analyze_seconds.restype = _d
     L.spand_analyze_seconds.argtypes = [_p]
+    L.spand_plan_analyze.argtypes = [_p, _i, _ip, _ip]
+    L.spand_plan_live_edges.argtypes = [_p, _i, _i, _p, _p]
+    L.spand_plan_counts.argtypes = [_p, _i, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
+    L.spand_get_cluster_layout.argtypes = [_p, _ip, _ip]
     L.spand_kernel_launches.restype = C.c_longlong
     L.spand_kernel_launches.argtypes = [_p]
     L.spand_arena_bytes.restype = C.c_longlong
@@ -262,6 +267,35 @@ class Tree:
     def get_N(self): return self._l.spand_get_N(self._h)
     def factorize_seconds(self): return self._l.spand_factorize_seconds(self._h)
     def analyze_seconds(self): return self._l.spand_analyze_seconds(self._h)
+
+    # ---- symbolic plan on the host only (no device needed) ----
+    def plan_analyze(self, A):
+        N, cp, ri, _ = _csc(A)
+        self._check(self._l.spand_plan_analyze(self._h, N, cp, ri))
+
+    def plan_live_edges(self, level, phase):
+        """(column cluster, row cluster) of the blocks alive after `phase` of `level` (level < 0: as assembled)."""
+        n = self._l.spand_plan_live_edges(self._h, level, phase, None, None)
+        if n < 0:
+            raise RuntimeError(self._l.spand_last_error(self._h).decode())
+        a, b = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        self._l.spand_plan_live_edges(self._h, level, phase, a.ctypes.data, b.ctypes.data)
+        return a, b
+
+    PLAN_COUNTS = ("eliminated", "out_panels", "in_panels", "fill_blocks", "schur_targets", "schur_contribs",
+                   "scaled_clusters", "scaled_blocks", "rrqr_tasks", "rrqr_wavefronts", "merged_blocks", "merge_copies")
+
+    def plan_counts(self, level):
+        out = np.zeros(12, dtype=np.int64)
+        self._check(self._l.spand_plan_counts(self._h, level, out))
+        return dict(zip(self.PLAN_COUNTS, (int(v) for v in out)))
+
+    def cluster_layout(self):
+        """(start, hierarchy level) of every cluster, same order as stats()."""
+        n = self._l.spand_num_clusters(self._h)
+        a, b = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        self._l.spand_get_cluster_layout(self._h, a, b)
+        return a, b
     def kernel_launches(self): return self._l.spand_kernel_launches(self._h)
     def arena_bytes(self): return self._l.spand_arena_bytes(self._h)
 

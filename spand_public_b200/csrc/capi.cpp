@@ -127,6 +127,13 @@ int spand_get_stats(spand_tree* t, int* id, int* size, int* rank) {
     std::memcpy(rank, c.data(), sizeof(int) * c.size());
     return 0;
 }
+int spand_get_cluster_layout(spand_tree* t, int* start, int* hlevel) {
+    std::vector<int> a, b;
+    t->t.cluster_layout(a, b);
+    std::memcpy(start, a.data(), sizeof(int) * a.size());
+    std::memcpy(hlevel, b.data(), sizeof(int) * b.size());
+    return 0;
+}
 int spand_log_fields(void) { return kLogFields; }
 const char* spand_log_field_name(int i) { return (i >= 0 && i < kLogFields) ? kLogNames[i] : ""; }
 int spand_get_log(spand_tree* t, double* out) {
@@ -144,6 +151,25 @@ int spand_get_log(spand_tree* t, double* out) {
 }
 double spand_factorize_seconds(spand_tree* t) { return t->t.t_factorize_device; }
 double spand_analyze_seconds(spand_tree* t) { return t->t.analyze_seconds(); }
+int spand_plan_analyze(spand_tree* t, int N, const int* colptr, const int* rowind) {
+    return guarded(t, [&] { t->t.analyze_only(from_csc(N, colptr, rowind, nullptr)); });
+}
+int spand_plan_live_edges(spand_tree* t, int level, int phase, int* n1, int* n2) {
+    int n = -1;
+    guarded(t, [&] {
+        std::vector<int> a, b;
+        t->t.plan_live_edges(level, phase, a, b);
+        if (n1) {
+            std::memcpy(n1, a.data(), sizeof(int) * a.size());
+            std::memcpy(n2, b.data(), sizeof(int) * b.size());
+        }
+        n = (int)a.size();
+    });
+    return n;
+}
+int spand_plan_counts(spand_tree* t, int level, long long* out) {
+    return guarded(t, [&] { t->t.plan_counts(level, out); });
+}
 long long spand_kernel_launches(spand_tree* t) { return t->t.launches_total; }
 long long spand_arena_bytes(spand_tree* t) { return (long long)t->t.arena_bytes(); }
 int spand_trailing(spand_tree* t, int* colptr, int* rowind, double* val) {

@@ -217,8 +217,7 @@ void Tree::partition(const SpMat& A) {
 // Symbolic analysis (once per partition + pattern): leaf block structure (src/tree.cpp:505-575), the map from the
 // non-zeros of A to their position inside the dense leaf blocks (util.cpp:454-486 block2dense), and the plan of
 // every level (symbolic.hpp). Everything is uploaded into sym_arena_ and reused by later assemble() calls.
-void Tree::analyze(const SpMat& A) {
-    const double t0 = wtime();
+void Tree::analyze_host(const SpMat& A, std::vector<unsigned>& valmap) {
     const bool symm = symmetry();
     const int ncl = ord.norders;
     std::vector<int> pinv(N), cmap(N);
@@ -270,7 +269,7 @@ void Tree::analyze(const SpMat& A) {
     if (total >= 0xffffffffull) throw std::runtime_error("assemble: leaf blocks exceed the 32-bit value map");
     leaf_total_ = total;
     // pass 2: value map
-    std::vector<unsigned> valmap(A.nnz(), 0xffffffffu);
+    valmap.assign(A.nnz(), 0xffffffffu);
     for (int s : bottoms_[0]) {
         const Cluster& cs = cl_[s];
         const int b0 = blk_begin[s], b1 = blk_begin[s + 1];
@@ -291,6 +290,18 @@ void Tree::analyze(const SpMat& A) {
     for (int c = 0; c < ncl; c++)
         sc[c] = SymCluster{cl_[c].level, cl_[c].hlevel, cl_[c].parent, cl_[c].child_begin, cl_[c].child_end, cl_[c].sparsify};
     build_symbolic(sc, bottoms_, leaf_n1, leaf_n2, symm, use_want_sparsify, plan_);
+    pat_colptr_ = A.colptr;
+    pat_rowind_ = A.rowind;
+    plan_ord_serial_ = ord_serial_;
+    plan_host_valid_ = true;
+}
+
+void Tree::analyze(const SpMat& A) {
+    const double t0 = wtime();
+    const int ncl = ord.norders;
+    std::vector<unsigned> valmap;
+    plan_valid_ = false;
+    analyze_host(A, valmap);
     // upload
     CK(cudaStreamSynchronize(st_));
     sym_arena_->reset();
@@ -335,13 +346,80 @@ void Tree::analyze(const SpMat& A) {
     d_mid_ = sym_arena_->alloc_n<int>(maxlist);
     CK(cudaStreamSynchronize(st_));
     stager_.reset();
-    pat_colptr_ = A.colptr;
-    pat_rowind_ = A.rowind;
-    plan_ord_serial_ = ord_serial_;
     plan_valid_ = true;
     t_analyze_ = wtime() - t0;
     if (verb)
         printf("symbolic analysis: %zu edges, plan %.1f MB, %.3f s\n", plan_.en1.size(), plan_.bytes() / 1e6, t_analyze_);
+}
+
+// clusters from the ordering; id == order (src/tree.cpp:360-415)
+void Tree::build_clusters() {
+    cl_.assign(ord.norders, Cluster());
+    bottoms_.assign(nlevels, {});
+    std::vector<int> first_id(nlevels, 0);
+    for (int h = 0; h < nlevels; h++) {
+        first_id[h] = ord.levels[h].empty() ? 0 : ord.levels[h][0].order;
+        for (auto& cn : ord.levels[h]) {
+            Cluster& c = cl_[cn.order];
+            c.start = cn.start;
+            c.size = c.orig_size = cn.size;
+            c.level = cn.level;
+            c.sparsify = cn.sparsify;
+            c.eliminated = false;
+            c.parent = -1;
+            c.hlevel = h;
+            c.child_begin = c.child_end = 0;
+            if (h > 0) {
+                c.child_begin = first_id[h - 1] + cn.child_begin;
+                c.child_end = first_id[h - 1] + cn.child_end;
+                for (int k = c.child_begin; k < c.child_end; k++) cl_[k].parent = cn.order;
+            }
+            bottoms_[h].push_back(cn.order);
+        }
+    }
+}
+
+
+// Host-only symbolic analysis (no device needed): used by the CPU tests of the planner.
+void Tree::analyze_only(const SpMat& A) {
+    if (N == 0 || A.rows != N) throw std::runtime_error("analyze: call partition first with a matrix of the same size");
+    build_clusters();
+    std::vector<unsigned> valmap;
+    plan_valid_ = false;
+    analyze_host(A, valmap);
+}
+
+// Blocks alive after phase `phase` of level `level` (0: eliminate, 1: scale, 2: sparsify, 3: merge; level < 0: as
+// assembled), as (column cluster, row cluster) pairs.
+void Tree::plan_live_edges(int level, int phase, std::vector<int>& n1, std::vector<int>& n2) const {
+    if (!plan_host_valid_) throw std::runtime_error("plan_live_edges: no plan");
+    std::vector<int> live;
+    if (level < 0) {
+        for (int e = 0; e < plan_.nleaf_edges; e++) live.push_back(e);
+    } else if (phase == 3) {
+        const SymLevel& L = plan_.lv[level];
+        for (int e = L.medge0; e < L.medge1; e++) live.push_back(e);
+    } else {
+        const SymLevel& L = plan_.lv[level];
+        for (int e : L.s_piv) live.push_back(e);
+        for (const SymTrsm& r : L.s_right) live.push_back(r.eB);
+    }
+    n1.clear();
+    n2.clear();
+    for (int e : live) {
+        n1.push_back(plan_.en1[e]);
+        n2.push_back(plan_.en2[e]);
+    }
+}
+
+void Tree::plan_counts(int level, long long out[12]) const {
+    if (!plan_host_valid_) throw std::runtime_error("plan_counts: no plan");
+    const SymLevel& L = plan_.lv[level];
+    long long v[12] = {(long long)L.E.size(), (long long)L.e_out.size(), (long long)L.e_in.size(), L.fill1 - L.fill0,
+                       (long long)L.e_gemm.size(), (long long)L.e_con.size(), (long long)L.S.size(),
+                       (long long)L.s_right.size(), (long long)L.q.size(), L.ncolors, L.medge1 - L.medge0,
+                       (long long)L.m_copy.size()};
+    for (int i = 0; i < 12; i++) out[i] = v[i];
 }
 
 // src/tree.cpp:505-575 — the values go to the device as they are (CSC order) and are scattered into the dense
@@ -367,30 +445,7 @@ void Tree::assemble(const SpMat& A) {
         fresh.dofs_left_nd = l.dofs_left_nd;
         l = fresh;
     }
-    // clusters from the ordering; id == order
-    cl_.assign(ord.norders, Cluster());
-    bottoms_.assign(nlevels, {});
-    std::vector<int> first_id(nlevels, 0);
-    for (int h = 0; h < nlevels; h++) {
-        first_id[h] = ord.levels[h].empty() ? 0 : ord.levels[h][0].order;
-        for (auto& cn : ord.levels[h]) {
-            Cluster& c = cl_[cn.order];
-            c.start = cn.start;
-            c.size = c.orig_size = cn.size;
-            c.level = cn.level;
-            c.sparsify = cn.sparsify;
-            c.eliminated = false;
-            c.parent = -1;
-            c.hlevel = h;
-            c.child_begin = c.child_end = 0;
-            if (h > 0) {
-                c.child_begin = first_id[h - 1] + cn.child_begin;
-                c.child_end = first_id[h - 1] + cn.child_end;
-                for (int k = c.child_begin; k < c.child_end; k++) cl_[k].parent = cn.order;
-            }
-            bottoms_[h].push_back(cn.order);
-        }
-    }
+    build_clusters();
     const bool reuse = plan_valid_ && plan_ord_serial_ == ord_serial_ && plan_.symmetric == symmetry() &&
                        plan_.want_flag == use_want_sparsify && pat_colptr_ == A.colptr && pat_rowind_ == A.rowind;
     if (!reuse) analyze(A);
@@ -1036,7 +1091,7 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         const char* mode_env = getenv("SPAND_RRQR_MODE");  // "smem": cluster kernels with the panel in shared memory
         const bool smem_mode = mode_env != nullptr && std::string(mode_env) == "smem";
         const int stream_tmin = getenv("SPAND_RRQR_TMIN") ? atoi(getenv("SPAND_RRQR_TMIN")) : 48;
-        const int stream_ctas = getenv("SPAND_RRQR_CTAS") ? atoi(getenv("SPAND_RRQR_CTAS")) : 1184;
+        const int stream_ctas = getenv("SPAND_RRQR_CTAS") ? atoi(getenv("SPAND_RRQR_CTAS")) : 2368;
         const long smem1_max = (getenv("SPAND_RRQR_SMEM1KB") ? atol(getenv("SPAND_RRQR_SMEM1KB")) : 200) * 1024;
         const double l2_budget = (getenv("SPAND_RRQR_L2MB") ? atof(getenv("SPAND_RRQR_L2MB")) : 128.0) * 1048576.0;
         std::vector<int> per_color(std::max(1, ncolors), 0);
@@ -1685,6 +1740,16 @@ SpMat Tree::trailing_mat() {
             }
     }
     return from_triplets(N, N, t);
+}
+
+void Tree::cluster_layout(std::vector<int>& start, std::vector<int>& hlevel) const {
+    start.clear();
+    hlevel.clear();
+    for (int h = 0; h < nlevels; h++)
+        for (int c : bottoms_[h]) {
+            start.push_back(cl_[c].start);
+            hlevel.push_back(h);
+        }
 }
 
 void Tree::stats(std::vector<int>& id, std::vector<int>& size, std::vector<int>& rank) const {

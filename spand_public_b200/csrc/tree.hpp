@@ -109,6 +109,7 @@ class Tree {
     int get_stop() const;
     SpMat trailing_mat();
     void stats(std::vector<int>& id, std::vector<int>& size, std::vector<int>& rank) const;
+    void cluster_layout(std::vector<int>& start, std::vector<int>& hlevel) const;  // same order as stats()
 
     int nlevels;
     int N = 0;
@@ -116,6 +117,10 @@ class Tree {
     std::vector<LevelLog> log;   // call logs() for the completed flop / byte / nnz model
     const std::vector<LevelLog>& logs();
     double analyze_seconds() const { return t_analyze_; }
+    // symbolic plan without a device (CPU tests of the planner)
+    void analyze_only(const SpMat& A);
+    void plan_live_edges(int level, int phase, std::vector<int>& n1, std::vector<int>& n2) const;
+    void plan_counts(int level, long long out[12]) const;
     double t_factorize_device = 0;  // seconds, CUDA events
     size_t arena_bytes() const { return arena_ ? arena_->used() : 0; }
     long long launches_total = 0;
@@ -174,6 +179,9 @@ class Tree {
     unsigned* d_valmap_ = nullptr;
     int *d_en1_ = nullptr, *d_en2_ = nullptr, *d_parent_ = nullptr;
     void analyze(const SpMat& A);
+    void analyze_host(const SpMat& A, std::vector<unsigned>& valmap);
+    void build_clusters();
+    bool plan_host_valid_ = false;
 
     cudaStream_t st_ = nullptr;
     static constexpr int kSide = 4;  // side streams for independent launches of one wavefront

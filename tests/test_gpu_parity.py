@@ -166,11 +166,15 @@ def test_full_factorization_vs_oracle(n, d, L, tol, coords):
 
 
 @pytest.mark.parametrize("env", [{"SPAND_RRQR_FORCE_GLOBAL": "1"}, {"SPAND_RRQR_FORCE_G": "1"}, {"SPAND_RRQR_FORCE_G": "2"},
-                                 {"SPAND_RRQR_FORCE_G": "4"}, {"SPAND_RRQR_FORCE_G": "8"}, {"SPAND_RRQR_FORCE_G": "16"}])
+                                 {"SPAND_RRQR_FORCE_G": "4"}, {"SPAND_RRQR_FORCE_G": "8"}, {"SPAND_RRQR_FORCE_G": "16"},
+                                 {"SPAND_RRQR_MODE": "smem"},
+                                 {"SPAND_RRQR_TMIN": "1", "SPAND_RRQR_SMEM1KB": "0"},
+                                 {"SPAND_RRQR_TMIN": "1", "SPAND_RRQR_SMEM1KB": "0", "SPAND_RRQR_CTAS": "100000"}])
 def test_every_rrqr_kernel_shape_matches_oracle(env, monkeypatch):
     """The RRQR launch shape (warp team, CTA, 2..16-CTA cluster with the panel in distributed shared memory, 16-CTA
-    cluster streaming the panel from global scratch) is picked from the task size; force each shape on one problem and
-    compare ranks / trailing matrix / residual with the oracle."""
+    cluster streaming the panel from global scratch, 256-thread streaming CTAs with 1..16-CTA clusters) is picked from
+    the task size and the width of the wavefront; force each shape on one problem and compare ranks / trailing matrix
+    / residual with the oracle."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     n, d, L, tol = 20, 3, 6, 1e-2
@@ -193,6 +197,44 @@ def test_every_rrqr_kernel_shape_matches_oracle(env, monkeypatch):
     g.factorize()
     x = g.solve(b[:A.shape[0]])
     assert np.linalg.norm(A @ x - b[:A.shape[0]]) / np.linalg.norm(b[:A.shape[0]]) <= 1e-10
+
+
+def test_symbolic_plan_is_reused_and_refreshed():
+    """The block structure is analysed by the first assemble() of a (partition, pattern) pair and reused afterwards:
+    same values -> bit-identical solve; new values on the same pattern -> correct factorization without re-analysis;
+    another pattern -> re-analysis."""
+    n, d, L = 12, 3, 5
+    A = S.neglapl(n, d)
+    X = S.linspace_nd(n, d)
+    g = S.Tree(L)
+    g.set_tol(0.0)
+    g.set_use_geo(True)
+    g.set_Xcoo(X)
+    g.partition(A)
+    g.assemble(A)
+    t_first = g.analyze_seconds()
+    g.factorize()
+    b = S.random(A.shape[0], 11)
+    x1 = g.solve(b)
+    g.assemble(A)
+    assert g.analyze_seconds() == t_first          # plan reused: no new analysis
+    g.factorize()
+    assert np.array_equal(x1, g.solve(b))
+    B = A.copy()
+    B.data = B.data * 1.5                          # same pattern, other values
+    g.assemble(B)
+    assert g.analyze_seconds() == t_first
+    g.factorize()
+    x2 = g.solve(b)
+    assert np.linalg.norm(B @ x2 - b) / np.linalg.norm(b) < 1e-12
+    import scipy.sparse as sp
+    C = (A + sp.eye(A.shape[0], k=2, format="csc") * 1e-3 + sp.eye(A.shape[0], k=-2, format="csc") * 1e-3).tocsc()
+    C.sort_indices()
+    g.partition(S.symmetric_graph(C))
+    g.assemble(C)                                  # other pattern (and partition): analysed again
+    g.factorize()
+    x3 = g.solve(b)
+    assert np.linalg.norm(C @ x3 - b) / np.linalg.norm(b) < 1e-11
 
 
 def test_solve_matches_oracle_when_factors_match():

@@ -1,0 +1,100 @@
+"""CPU tests of the symbolic plan (spand_public_b200/csrc/symbolic.cpp): the block structure it predicts for every
+(level, phase) must be the structure the reference algorithm produces. The checker is the oracle's trailing matrix
+at the same stop point (reference Tree::get_trailing_mat, src/tree.cpp:1730-1763): in exact configurations
+(tol = 0: no cluster shrinks) its non-zero pattern is the union of the live dense blocks. No GPU is needed: the plan
+is built on the host only (spand_plan_analyze)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import spand_public_b200 as S
+
+
+def _blocks_of_trailing(T, starts, sizes):
+    """Set of (column cluster, row cluster) index pairs (indices into the level's cluster list) touched by T."""
+    T = T.tocoo()
+    ends = starts + sizes
+    def owner(ix):
+        k = np.searchsorted(starts, ix, side="right") - 1
+        assert np.all((k >= 0) & (ix < ends[k]))
+        return k
+    return set(zip(owner(T.col).tolist(), owner(T.row).tolist()))
+
+
+@pytest.mark.parametrize("n,d,L,gen", [(12, 2, 4, False), (8, 3, 4, False), (10, 3, 5, False), (8, 3, 4, True)])
+def test_plan_structure_matches_oracle(n, d, L, gen):
+    A = S.neglapl(n, d)
+    if gen:
+        rng = np.random.RandomState(3)
+        A = A.copy()
+        A.data = A.data + rng.uniform(-0.1, 0.1, A.nnz)
+    X = S.linspace_nd(n, d)
+    g = S.Tree(L)
+    g.set_use_geo(True)
+    g.set_Xcoo(X)
+    if gen:
+        g.set_symm_kind(S.GEN)
+        g.set_scaling_kind(S.PLU)
+    g.partition(S.symmetric_graph(A))
+    g.plan_analyze(A)
+    ids, sizes, _ = g.stats()
+    starts, hlev = g.cluster_layout()
+    kw = dict(symm_kind=O.GEN, scaling_kind=O.PLU) if gen else {}
+    for lvl in range(L):
+        for phase in (0, 3):
+            if phase == 3 and lvl == L - 1:
+                continue
+            o = O.OracleTree(L, tol=0.0, **kw)
+            o.set_coords(X)
+            o.set_stop(lvl, phase)
+            o.partition(S.symmetric_graph(A))
+            o.assemble(A)
+            o.factorize()
+            h = lvl + (1 if phase == 3 else 0)          # hierarchy level of the live clusters
+            sel = np.nonzero(hlev == h)[0]
+            # sizes of merged clusters are only known to the oracle run: take them from its stats
+            osz = o.stats()[1][sel].astype(np.int64)
+            ref = _blocks_of_trailing(o.trailing_mat(), starts[sel].astype(np.int64), osz)
+            n1, n2 = g.plan_live_edges(lvl, phase)
+            base = ids[sel][0]
+            mine = set()
+            for a, b in zip(n1.tolist(), n2.tolist()):
+                if osz[a - base] == 0 or osz[b - base] == 0:
+                    continue
+                mine.add((a - base, b - base))
+                if not gen:
+                    mine.add((b - base, a - base))      # symmetric kinds store the lower blocks only
+            assert mine == ref, (lvl, phase, len(mine), len(ref))
+
+
+def test_plan_counts_and_wavefronts():
+    n, d, L = 10, 3, 5
+    A = S.neglapl(n, d)
+    g = S.Tree(L)
+    g.set_use_geo(True)
+    g.set_Xcoo(S.linspace_nd(n, d))
+    g.partition(A)
+    g.plan_analyze(A)
+    ids, sizes, _ = g.stats()
+    _, hlev = g.cluster_layout()
+    total_elim = 0
+    for lvl in range(L):
+        c = g.plan_counts(lvl)
+        total_elim += c["eliminated"]
+        assert c["schur_contribs"] >= c["schur_targets"] >= 0
+        assert c["scaled_clusters"] + total_elim == np.count_nonzero(hlev == lvl)   # everything alive is scaled
+        assert c["rrqr_tasks"] <= c["scaled_clusters"]
+        assert (c["rrqr_wavefronts"] >= 1) == (c["rrqr_tasks"] > 0)
+        if lvl < L - 1:
+            assert c["merged_blocks"] <= c["merge_copies"]
+            # clusters alive at level lvl + 1 = the parents of the survivors
+            total_elim_next_base = np.count_nonzero(hlev == lvl + 1)
+            assert total_elim_next_base <= c["scaled_clusters"]
+            total_elim = 0  # the next hierarchy level lists only live clusters
+    assert g.plan_counts(L - 1)["scaled_clusters"] == 0
+
+
+def test_plan_needs_partition_first():
+    g = S.Tree(3)
+    with pytest.raises(RuntimeError):
+        g.plan_analyze(S.neglapl(5, 2))
