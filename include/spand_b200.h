@@ -97,6 +97,18 @@ double spand_analyze_seconds(spand_tree* t);
  * eliminated clusters, out-panels, in-panels, fill-in blocks, Schur targets, Schur contributions, scaled clusters,
  * scaled blocks, RRQR tasks, RRQR wavefronts, merged blocks, merge copies. */
 int spand_plan_analyze(spand_tree* t, int N, const int* colptr, const int* rowind);
+
+/* Sub-tree sharding over the GPUs of one node, one process per GPU (nothing of this exists in the reference, which is
+ * a single sequential process). Every rank calls, in this order: spand_set_device, spand_mg_setup
+ * (allocates the rank's shared arena: blocks, solution segments and cluster sizes that peers reach through NVLink),
+ * spand_mg_get_handle (64 bytes, a cudaIpcMemHandle_t), an all-gather of the handles in the caller's process group,
+ * spand_mg_set_peers (nranks * 64 bytes in rank order), then the usual partition / assemble / factorize / solve with
+ * identical arguments on every rank. Every rank ends up with the full solution. nranks must be a power of two.
+ * spand_mg_owner_map is host-only: the rank owning every cluster (order of spand_get_stats). SPD/LLT only. */
+int spand_mg_setup(spand_tree* t, int rank, int nranks, long long arena_bytes);
+int spand_mg_get_handle(spand_tree* t, void* out64);
+int spand_mg_set_peers(spand_tree* t, const void* handles);
+int spand_mg_owner_map(spand_tree* t, int nranks, int* owner);
 int spand_plan_live_edges(spand_tree* t, int level, int phase, int* n1, int* n2);
 int spand_plan_counts(spand_tree* t, int level, long long* out);
 long long spand_kernel_launches(spand_tree* t);

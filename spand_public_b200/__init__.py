@@ -29,7 +29,8 @@ EXPORTS = [
     "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_nnz", "spand_get_stop",
     "spand_get_nlevels", "spand_num_clusters", "spand_get_stats", "spand_log_fields", "spand_log_field_name",
     "spand_get_log", "spand_factorize_seconds", "spand_analyze_seconds", "spand_plan_analyze", "spand_plan_live_edges",
-    "spand_plan_counts", "spand_get_cluster_layout", "spand_kernel_launches", "spand_arena_bytes", "spand_trailing",
+    "spand_plan_counts", "spand_get_cluster_layout", "spand_mg_setup", "spand_mg_get_handle", "spand_mg_set_peers",
+    "spand_mg_owner_map", "spand_kernel_launches", "spand_arena_bytes", "spand_trailing",
     "spand_util_random", "spand_util_linspace_nd", "spand_util_neglapl", "spand_util_aniso", "spand_util_mm_read",
     "spand_util_mm_read_dense", "spand_set_profile", "spand_num_families", "spand_family_name", "spand_get_family_stats",
 ]
@@ -89,6 +90,10 @@ def lib():
     L.spand_plan_live_edges.argtypes = [_p, _i, _i, _p, _p]
     L.spand_plan_counts.argtypes = [_p, _i, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
     L.spand_get_cluster_layout.argtypes = [_p, _ip, _ip]
+    L.spand_mg_setup.argtypes = [_p, _i, _i, C.c_longlong]
+    L.spand_mg_get_handle.argtypes = [_p, C.c_char_p]
+    L.spand_mg_set_peers.argtypes = [_p, C.c_char_p]
+    L.spand_mg_owner_map.argtypes = [_p, _i, _ip]
     L.spand_kernel_launches.restype = C.c_longlong
     L.spand_kernel_launches.argtypes = [_p]
     L.spand_arena_bytes.restype = C.c_longlong
@@ -267,6 +272,31 @@ class Tree:
     def get_N(self): return self._l.spand_get_N(self._h)
     def factorize_seconds(self): return self._l.spand_factorize_seconds(self._h)
     def analyze_seconds(self): return self._l.spand_analyze_seconds(self._h)
+
+    # ---- sub-tree sharding over the GPUs of one node (one process per GPU) ----
+    def mg_init(self, dist, device=None, arena_gb=None):
+        """Collective over the default torch.distributed group: allocates this rank's shared arena and maps the
+        peers' arenas (CUDA IPC). Call before partition/assemble; afterwards every rank makes the same calls."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if device is not None:
+            self.set_device(device)
+        if arena_gb is None:
+            arena_gb = float(os.environ.get("SPAND_MG_ARENA_GB", "40"))
+        self._check(self._l.spand_mg_setup(self._h, rank, world, int(arena_gb * (1 << 30))))
+        if world == 1:
+            return
+        buf = C.create_string_buffer(64)
+        self._check(self._l.spand_mg_get_handle(self._h, buf))
+        handles = [None] * world
+        dist.all_gather_object(handles, buf.raw)
+        self._check(self._l.spand_mg_set_peers(self._h, b"".join(handles)))
+        dist.barrier()
+
+    def mg_owner_map(self, nranks):
+        """Rank owning every cluster (order of stats()); host only, valid after partition()."""
+        out = np.zeros(self._l.spand_num_clusters(self._h), dtype=np.int32)
+        self._check(self._l.spand_mg_owner_map(self._h, nranks, out))
+        return out
 
     # ---- symbolic plan on the host only (no device needed) ----
     def plan_analyze(self, A):

@@ -151,6 +151,21 @@ int spand_get_log(spand_tree* t, double* out) {
 }
 double spand_factorize_seconds(spand_tree* t) { return t->t.t_factorize_device; }
 double spand_analyze_seconds(spand_tree* t) { return t->t.analyze_seconds(); }
+int spand_mg_setup(spand_tree* t, int rank, int nranks, long long arena_bytes) {
+    return guarded(t, [&] { t->t.mg_setup(rank, nranks, (size_t)arena_bytes); });
+}
+int spand_mg_get_handle(spand_tree* t, void* out64) {
+    return guarded(t, [&] { t->t.mg_get_handle(out64); });
+}
+int spand_mg_set_peers(spand_tree* t, const void* handles) {
+    return guarded(t, [&] { t->t.mg_set_peers(handles); });
+}
+int spand_mg_owner_map(spand_tree* t, int nranks, int* owner) {
+    return guarded(t, [&] {
+        std::vector<int> o = t->t.owner_map(nranks);
+        std::memcpy(owner, o.data(), sizeof(int) * o.size());
+    });
+}
 int spand_plan_analyze(spand_tree* t, int N, const int* colptr, const int* rowind) {
     return guarded(t, [&] { t->t.analyze_only(from_csc(N, colptr, rowind, nullptr)); });
 }

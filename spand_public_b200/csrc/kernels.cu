@@ -827,6 +827,7 @@ __global__ void __launch_bounds__(128) potrf_sym_kernel(DevTables T, const int* 
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * 4 + w;
     if (ti >= nt) return;
+    if (T.rank >= 0 && T.owner[clusters[ti]] != T.rank) return;
     const int n = T.csize[clusters[ti]];
     if (n <= 0 || n > SMALL_DIM) return;
     if (n > 32) {
@@ -917,6 +918,7 @@ __global__ void __launch_bounds__(128) trsm_sym_kernel(DevTables T, const SymTrs
     const int ti = blockIdx.x * 4 + w;
     if (ti >= nt) return;
     const SymTrsm t = tasks[ti];
+    if (T.rank >= 0 && T.owner[T.en1[t.eB]] != T.rank) return;
     const int m = T.csize[t.cm], n = T.csize[t.cn];
     if (m <= 0 || n <= 0 || m > SMALL_DIM || n > SMALL_DIM) return;
     if (m > 32 || n > 32) {
@@ -963,6 +965,7 @@ __global__ void __launch_bounds__(128) scale_sym_kernel(DevTables T, const SymTr
     const int ti = blockIdx.x * 4 + w;
     if (ti >= nt) return;
     const SymTrsm r = right[ti];
+    if (T.rank >= 0 && T.owner[T.en1[r.eB]] != T.rank) return;
     const int rows = T.csize[r.cm], cols = T.csize[r.cn];
     if (rows <= 0 || cols <= 0 || rows > SMALL_DIM || cols > SMALL_DIM) return;
     if (rows > 32 || cols > 32) {
@@ -1014,6 +1017,7 @@ __global__ void __launch_bounds__(128) gemm_sym_small_kernel(DevTables T, const 
     if (ti >= nt) return;
     const int lane = threadIdx.x & 31;
     const SymGemm t = tasks[ti];
+    if (T.rank >= 0 && T.owner[T.en1[t.target]] != T.rank) return;
     const int m = T.csize[T.en2[t.target]], n = T.csize[T.en1[t.target]];
     if (m <= 0 || n <= 0 || m > SMALL_DIM || n > SMALL_DIM) return;
     if (m * n > 1024) {
@@ -1065,6 +1069,7 @@ __global__ void __launch_bounds__(128) copy_sym_kernel(DevTables T, const SymCop
     if (ti >= nt) return;
     const int lane = threadIdx.x & 31;
     const SymCopy t = tasks[ti];
+    if (T.rank >= 0 && T.owner[t.c1] != T.rank) return;
     const int rows = T.csize[t.c2], cols = T.csize[t.c1];
     if (rows <= 0 || cols <= 0) return;
     const int ldd = T.eld[t.enew];
@@ -1109,7 +1114,7 @@ __global__ void expand_trsv_kernel(DevTables T, const int* __restrict__ clusters
     o.T = T.eptr[e];
     o.x = T.xptr[c];
     o.ld = T.eld[e];
-    o.n = T.csize[c];
+    o.n = (T.rank >= 0 && T.owner[c] != T.rank) ? 0 : T.csize[c];
     o.diag = nullptr;
     o.perm = nullptr;
     out[i] = o;
@@ -1122,7 +1127,7 @@ __global__ void expand_gemv_kernel(DevTables T, const SymGemv* __restrict__ t, i
         SymGemv g = t[i];
         GemvTask o;
         o.y = T.xptr[g.cluster];
-        o.m = T.csize[g.cluster];
+        o.m = (T.rank >= 0 && T.owner[g.cluster] != T.rank) ? 0 : T.csize[g.cluster];
         o.c0 = g.c0;
         o.nc = g.nc;
         out[i] = o;
@@ -1144,7 +1149,7 @@ __global__ void expand_xcopy_kernel(DevTables T, const int* __restrict__ childre
     const int c = children[i];
     double* xc = T.xptr[c];
     double* xp = T.xptr[T.parent[c]] + T.pos[c];
-    const int sz = T.csize[c];
+    const int sz = (T.rank >= 0 && T.owner[c] != T.rank) ? 0 : T.csize[c];
     fwd[i] = XCopyTask{xc, xp, sz};
     bwd[i] = XCopyTask{xp, xc, sz};
 }
@@ -1170,6 +1175,35 @@ __global__ void scatter_values_kernel(const double* __restrict__ val, const unsi
         unsigned m = map[i];
         if (m != 0xffffffffu) dst[m] = val[i];
     }
+}
+
+
+__global__ void peer_barrier_kernel(PeerPtrs flags, int rank, int nranks, unsigned epoch) {
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        __threadfence_system();  // everything this GPU wrote before is visible to the peers first
+        volatile unsigned* theirs = reinterpret_cast<volatile unsigned*>(flags.p[r]) + rank;
+        *theirs = epoch;
+        volatile unsigned* mine = reinterpret_cast<volatile unsigned*>(flags.p[rank]) + r;
+        while ((int)(*mine - epoch) < 0) {}
+        __threadfence_system();
+    }
+}
+
+__global__ void csize_min_kernel(PeerPtrs csize, int rank, int nranks, int first, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int* mine = reinterpret_cast<int*>(csize.p[rank]) + first;
+    int v = mine[i];
+    for (int r = 0; r < nranks; r++)
+        if (r != rank) v = min(v, reinterpret_cast<const volatile int*>(csize.p[r])[first + i]);
+    mine[i] = v;
+}
+
+__global__ void scatter_owned_kernel(int n, const int* __restrict__ idx, PeerPtrs leaf,
+                                     const signed char* __restrict__ dof_owner, double* dst) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[idx[i]] = reinterpret_cast<const double*>(leaf.p[dof_owner[i]])[i];
 }
 
 inline int grid_for(size_t n, int bs, int maxb = 148 * 16) {
@@ -1353,6 +1387,17 @@ void launch_expand_house(const DevTables& T, const QrTask* q, int n, HouseTask* 
 }
 void launch_scatter_values(const double* val, const unsigned* map, size_t n, double* dst, cudaStream_t st) {
     if (n > 0) scatter_values_kernel<<<grid_for(n, 256), 256, 0, st>>>(val, map, n, dst);
+}
+
+void launch_peer_barrier(const PeerPtrs& flags, int rank, int nranks, unsigned epoch, cudaStream_t st) {
+    peer_barrier_kernel<<<1, 32, 0, st>>>(flags, rank, nranks, epoch);
+}
+void launch_csize_min(const PeerPtrs& csize, int rank, int nranks, int first, int n, cudaStream_t st) {
+    if (n > 0) csize_min_kernel<<<(n + 255) / 256, 256, 0, st>>>(csize, rank, nranks, first, n);
+}
+void launch_scatter_owned(int n, const int* idx, const PeerPtrs& leaf, const signed char* dof_owner, double* dst,
+                          cudaStream_t st) {
+    if (n > 0) scatter_owned_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, idx, leaf, dof_owner, dst);
 }
 
 }  // namespace spand

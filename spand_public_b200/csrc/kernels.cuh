@@ -194,6 +194,10 @@ struct DevTables {
     double* const* xptr;    // solution segment of every cluster
     const int* pos;         // offset of a cluster inside its parent (valid after the merge planning of its level)
     const int* parent;
+    // sub-tree sharding over several GPUs: rank owning every cluster (a block belongs to the owner of its column
+    // cluster, a task to the owner of the block / segment it writes); rank < 0: single GPU, nothing is filtered
+    const int* owner;
+    int rank;
 };
 constexpr int SMALL_DIM = 64;      // largest dimension served by the plan-driven kernels
 constexpr int COPY_SMALL = 4096;   // largest block (elements) copied by one warp in the merge
@@ -215,7 +219,22 @@ void launch_expand_gemv(const DevTables& T, const SymGemv* t, int nt, const SymG
                         GemvContrib* outc, cudaStream_t st);
 void launch_expand_xcopy(const DevTables& T, const int* children, int n, XCopyTask* fwd, XCopyTask* bwd, cudaStream_t st);
 void launch_expand_house(const DevTables& T, const QrTask* q, int n, HouseTask* out, cudaStream_t st);
+// Multi-GPU plumbing over peer-mapped memory (NVLink): `flags[r]` is rank r's array of nranks epoch counters.
+// launch_peer_barrier: every rank stores `epoch` into its slot on every peer, then waits until all of its own slots
+// have reached `epoch` (system-scope fences on both sides): all kernels enqueued before it on every rank are complete
+// and visible when the kernels enqueued after it start.
+constexpr int MG_MAX_RANKS = 16;
+struct PeerPtrs {
+    void* p[MG_MAX_RANKS];
+};
+void launch_peer_barrier(const PeerPtrs& flags, int rank, int nranks, unsigned epoch, cudaStream_t st);
+// csize[first, first + n) <- min over ranks (sizes only shrink: the replica that ran the RRQR holds the rank)
+void launch_csize_min(const PeerPtrs& csize, int rank, int nranks, int first, int n, cudaStream_t st);
+// x[idx[i]] = leaf_r[i] with r = dof_owner[i]: collects the solution segments from their owners
+void launch_scatter_owned(int n, const int* idx, const PeerPtrs& leaf, const signed char* dof_owner, double* dst,
+                          cudaStream_t st);
 // assembly: dst[map[k]] = val[k] for map[k] != 0xffffffff
+// (dst0: offset subtracted from the map, n: number of values; entries outside [0, dst_len) are skipped)
 void launch_scatter_values(const double* val, const unsigned* map, size_t n, double* dst, cudaStream_t st);
 
 // PCG building blocks (src/is.cpp:39-121)

@@ -124,6 +124,12 @@ void Tree::ensure_device() {
 void Tree::free_device() {
     if (!st_) return;
     cudaStreamSynchronize(st_);
+    for (int r = 0; r < mg_nranks; r++) {
+        if (!mg_base_[r]) continue;
+        if (r == mg_rank) cudaFree(mg_base_[r]);
+        else cudaIpcCloseMemHandle(mg_base_[r]);
+        mg_base_[r] = nullptr;
+    }
     delete arena_;
     delete scratch_;
     delete sym_arena_;
@@ -452,15 +458,48 @@ void Tree::assemble(const SpMat& A) {
 
     const int ncl = ord.norders;
     const size_t nedges = plan_.en1.size();
-    d_csize_ = arena_->alloc_n<int>(ncl);
     d_pos_ = arena_->alloc_n<int>(ncl);
     d_xptr_ = arena_->alloc_n<double*>(ncl);
     d_eptr_ = arena_->alloc_n<double*>(nedges);
     d_eld_ = arena_->alloc_n<int>(nedges);
     d_perm_ = arena_->alloc_n<int>(N);
     d_xnat_ = arena_->alloc_n<double>(N);
-    d_xleaf_ = arena_->alloc_n<double>(N);
-    tab_ = DevTables{d_csize_, d_eptr_, d_eld_, d_en1_, d_en2_, d_xptr_, d_pos_, d_parent_};
+    d_owner_ = nullptr;
+    d_dof_owner_ = nullptr;
+    double* leaf_base[MG_MAX_RANKS] = {};
+    if (!mg()) {
+        d_csize_ = arena_->alloc_n<int>(ncl);
+        d_xleaf_ = arena_->alloc_n<double>(N);
+        leaf_base[0] = arena_->alloc_n<double>(leaf_total_);
+    } else {
+        // Symmetric layout of every rank's shared arena: [flags | cluster sizes | leaf solution segments | the leaf
+        // blocks (every rank assembles all of them, only the owner's copy is used) | blocks created later].
+        if (!mg_peers_set_) throw std::runtime_error("assemble: mg_setup / mg_set_peers must be called first");
+        if (scale_kind == PLU) throw std::runtime_error("multi-GPU sharding is built for the SPD/LLT path only");
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        mg_off_csize_ = 4096;
+        const size_t off_xleaf = up(mg_off_csize_ + sizeof(int) * ncl);
+        mg_off_leaf_ = up(off_xleaf + sizeof(double) * N);
+        mg_off_blocks_ = up(mg_off_leaf_ + sizeof(double) * leaf_total_);
+        if (mg_off_blocks_ > mg_size_) throw std::runtime_error("multi-GPU shared arena too small (SPAND_MG_ARENA_GB)");
+        for (int r = 0; r < mg_nranks; r++) {
+            mg_top_[r] = mg_off_blocks_;
+            mg_csize_.p[r] = mg_base_[r] + mg_off_csize_;
+            mg_leaf_.p[r] = mg_base_[r] + off_xleaf;
+            leaf_base[r] = reinterpret_cast<double*>(mg_base_[r] + mg_off_leaf_);
+        }
+        d_csize_ = reinterpret_cast<int*>(mg_base_[mg_rank] + mg_off_csize_);
+        d_xleaf_ = reinterpret_cast<double*>(mg_base_[mg_rank] + off_xleaf);
+        h_owner_ = owner_map(mg_nranks);
+        d_owner_ = arena_->alloc_n<int>(ncl);
+        stager_.upload(d_owner_, h_owner_.data(), sizeof(int) * ncl, st_);
+        std::vector<signed char> dof_owner(N);
+        for (int c : bottoms_[0])
+            for (int k = cl_[c].start; k < cl_[c].start + cl_[c].size; k++) dof_owner[k] = (signed char)h_owner_[c];
+        d_dof_owner_ = reinterpret_cast<signed char*>(arena_->alloc(N));
+        stager_.upload(d_dof_owner_, dof_owner.data(), N, st_);
+    }
+    tab_ = DevTables{d_csize_, d_eptr_, d_eld_, d_en1_, d_en2_, d_xptr_, d_pos_, d_parent_, d_owner_, mg() ? mg_rank : -1};
     h_csize_.assign(ncl, 0);
     h_pos_.assign(ncl, 0);
     h_xptr_.assign(ncl, nullptr);
@@ -473,12 +512,12 @@ void Tree::assemble(const SpMat& A) {
     size_post_.assign(nlevels, {});
     phases_done_.assign(nlevels, 0);
     for (int c : bottoms_[0]) {
-        h_xptr_[c] = d_xleaf_ + cl_[c].start;
+        h_xptr_[c] = (mg() ? reinterpret_cast<double*>(mg_leaf_.p[h_owner_[c]]) : d_xleaf_) + cl_[c].start;
         h_csize_[c] = cl_[c].size;
     }
-    double* dblocks = arena_->alloc_n<double>(leaf_total_);
+    double* dblocks = leaf_base[mg() ? mg_rank : 0];
     for (int e = 0; e < plan_.nleaf_edges; e++) {
-        h_eptr_[e] = dblocks + leaf_off_[e];
+        h_eptr_[e] = leaf_base[mg() ? h_owner_[plan_.en1[e]] : 0] + leaf_off_[e];
         h_eld_[e] = std::max(1, cl_[plan_.en2[e]].size);
     }
     stager_.upload(d_perm_, ord.perm.data(), sizeof(int) * N, st_);
@@ -531,26 +570,117 @@ TrsmTask Tree::host_trsm(const SymTrsm& t, const double* diag) const {
     return r;
 }
 
+// A block that peers may touch: from this rank's arena on one GPU, from the owner's shared arena otherwise (every
+// rank replays every allocation, so that all pointer tables hold valid peer addresses).
+double* Tree::alloc_block(int owner, size_t doubles) {
+    if (!mg()) return arena_->alloc_n<double>(doubles);
+    size_t bytes = (doubles * sizeof(double) + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    if (mg_top_[owner] + bytes > mg_size_) throw std::runtime_error("multi-GPU shared arena too small (SPAND_MG_ARENA_GB)");
+    double* p = reinterpret_cast<double*>(mg_base_[owner] + mg_top_[owner]);
+    mg_top_[owner] += bytes;
+    return p;
+}
+
+void Tree::mg_barrier() {
+    if (!mg()) return;
+    launch_peer_barrier(mg_flags_, mg_rank, mg_nranks, ++mg_epoch_, st_);
+}
+
 // Blocks of the edges [e0, e1) (fill-in of a level, or the parents' blocks of a merge) at the current sizes.
 void Tree::alloc_edges(int e0, int e1, bool zero, LevelLog& lg) {
     if (e1 <= e0) return;
-    size_t total = 0;
-    for (int e = e0; e < e1; e++) {
-        const size_t rows = h_csize_[plan_.en2[e]], cols = h_csize_[plan_.en1[e]];
-        h_eld_[e] = (int)std::max<size_t>(1, rows);
-        h_eptr_[e] = (double*)total;  // offset for now
-        total += (rows * cols + 31) & ~(size_t)31;
-    }
-    double* base = arena_->alloc_n<double>(total + 32);
-    for (int e = e0; e < e1; e++) h_eptr_[e] = base + (size_t)h_eptr_[e];
-    if (zero) {
-        auto ev = fam_begin(F_COPY);
-        CK(cudaMemsetAsync(base, 0, total * sizeof(double), st_));
-        fam_end(F_COPY, ev);
-        lg.launches++;
+    if (mg()) {
+        const size_t top0 = mg_top_[mg_rank];
+        for (int e = e0; e < e1; e++) {
+            const size_t rows = h_csize_[plan_.en2[e]], cols = h_csize_[plan_.en1[e]];
+            h_eld_[e] = (int)std::max<size_t>(1, rows);
+            h_eptr_[e] = alloc_block(h_owner_[plan_.en1[e]], rows * cols);
+        }
+        if (zero && mg_top_[mg_rank] > top0) {
+            CK(cudaMemsetAsync(mg_base_[mg_rank] + top0, 0, mg_top_[mg_rank] - top0, st_));
+            lg.launches++;
+        }
+    } else {
+        size_t total = 0;
+        for (int e = e0; e < e1; e++) {
+            const size_t rows = h_csize_[plan_.en2[e]], cols = h_csize_[plan_.en1[e]];
+            h_eld_[e] = (int)std::max<size_t>(1, rows);
+            h_eptr_[e] = (double*)total;  // offset for now
+            total += (rows * cols + 31) & ~(size_t)31;
+        }
+        double* base = arena_->alloc_n<double>(total + 32);
+        for (int e = e0; e < e1; e++) h_eptr_[e] = base + (size_t)h_eptr_[e];
+        if (zero) {
+            auto ev = fam_begin(F_COPY);
+            CK(cudaMemsetAsync(base, 0, total * sizeof(double), st_));
+            fam_end(F_COPY, ev);
+            lg.launches++;
+        }
     }
     stager_.upload(d_eptr_ + e0, h_eptr_.data() + e0, sizeof(double*) * (e1 - e0), st_);
     stager_.upload(d_eld_ + e0, h_eld_.data() + e0, sizeof(int) * (e1 - e0), st_);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU setup (one process per GPU; the handles travel through the caller's process group)
+// ------------------------------------------------------------------------------------------------
+void Tree::mg_setup(int rank, int nranks, size_t arena_bytes) {
+    if (nranks < 1 || nranks > MG_MAX_RANKS || (nranks & (nranks - 1)) != 0)
+        throw std::runtime_error("mg_setup: the number of ranks must be a power of two <= 16");
+    if (nranks > 1 && nranks > (1 << (nlevels - 1))) throw std::runtime_error("mg_setup: more ranks than sub-trees");
+    ensure_device();
+    mg_rank = rank;
+    mg_nranks = nranks;
+    mg_peers_set_ = false;
+    if (nranks == 1) return;
+    if (mg_base_[rank]) cudaFree(mg_base_[rank]);
+    mg_size_ = arena_bytes;
+    CK(cudaMalloc((void**)&mg_base_[rank], mg_size_));
+    CK(cudaMemset(mg_base_[rank], 0, 4096));
+    mg_epoch_ = 0;
+}
+
+void Tree::mg_get_handle(void* out64) const {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, mg_base_[mg_rank]));
+    std::memcpy(out64, &h, 64);
+}
+
+void Tree::mg_set_peers(const void* handles) {
+    for (int r = 0; r < mg_nranks; r++) {
+        if (r == mg_rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)handles + 64 * r, 64);
+        CK(cudaIpcOpenMemHandle((void**)&mg_base_[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    for (int r = 0; r < mg_nranks; r++) mg_flags_.p[r] = mg_base_[r];
+    mg_peers_set_ = true;
+}
+
+// Owner of every cluster: the rank of the depth-g sub-tree (g = log2 ranks) its separator belongs to; the 2^g - 1
+// separators above the sub-trees go to distinct ranks (the middle sub-tree below them). Parents keep the owner of
+// their children (same separator), so merges and solution-segment copies are local.
+std::vector<int> Tree::owner_map(int nranks) const {
+    std::vector<int> own(ord.norders, 0);
+    if (nranks <= 1) return own;
+    int g = 0;
+    while ((1 << g) < nranks) g++;
+    const int Ls = nlevels - 1 - g;
+    if (Ls < 0) throw std::runtime_error("owner_map: more ranks than sub-trees");
+    for (int h = 0; h < nlevels; h++)
+        for (auto& cn : ord.levels[h]) {
+            const int lvl = cn.id.self.lvl, sep = cn.id.self.sep;
+            int o;
+            if (lvl <= Ls) o = sep >> (Ls - lvl);
+            else {
+                const int shift = lvl - Ls;
+                o = (sep << shift) + (1 << (shift - 1));
+            }
+            own[cn.order] = o;
+        }
+    return own;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -741,7 +871,8 @@ void Tree::phase_eliminate(LevelLog& lg, SolveLevel& sl) {
     if (big) {
         std::vector<PotrfTask> bp;
         for (size_t i = 0; i < L.E.size(); i++)
-            if (h_csize_[L.E[i]] > SMALL_DIM) bp.push_back({h_eptr_[L.e_piv[i]], h_eld_[L.e_piv[i]], h_csize_[L.E[i]]});
+            if (h_csize_[L.E[i]] > SMALL_DIM && mine(L.E[i]))
+                bp.push_back({h_eptr_[L.e_piv[i]], h_eld_[L.e_piv[i]], h_csize_[L.E[i]]});
         run_potrf(bp, lg);
     }
     // panels
@@ -753,11 +884,13 @@ void Tree::phase_eliminate(LevelLog& lg, SolveLevel& sl) {
         std::vector<TrsmTask> bt;
         for (const SymTrsm& t : L.e_out) {
             const int m = h_csize_[t.cm], n = h_csize_[t.cn];
-            if ((m > SMALL_DIM || n > SMALL_DIM) && m > 0 && n > 0) bt.push_back(host_trsm(t, nullptr));
+            if ((m > SMALL_DIM || n > SMALL_DIM) && m > 0 && n > 0 && mine(plan_.en1[t.eB]))
+                bt.push_back(host_trsm(t, nullptr));
         }
         run_trsm(TRSM_RLT, bt, lg);
     }
-    // Schur complement
+    // Schur complement: a target is updated by its owner, which reads the panels of other ranks through NVLink
+    mg_barrier();
     ev = fam_begin(F_GEMM);
     launch_gemm_sym(tab_, D.e_gemm, (int)L.e_gemm.size(), D.e_con, d_mid_, next_counter(), st_);
     fam_end(F_GEMM, ev);
@@ -767,7 +900,7 @@ void Tree::phase_eliminate(LevelLog& lg, SolveLevel& sl) {
         std::vector<GemmContrib> con;
         for (const SymGemm& g : L.e_gemm) {
             const int m = h_csize_[plan_.en2[g.target]], n = h_csize_[plan_.en1[g.target]];
-            if (!(m > SMALL_DIM || n > SMALL_DIM) || m == 0 || n == 0) continue;
+            if (!(m > SMALL_DIM || n > SMALL_DIM) || m == 0 || n == 0 || !mine(plan_.en1[g.target])) continue;
             GemmTask t;
             t.C = h_eptr_[g.target];
             t.ldc = h_eld_[g.target];
@@ -998,9 +1131,11 @@ void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
     if (big) {
         std::vector<PotrfTask> bp;
         for (size_t i = 0; i < L.S.size(); i++)
-            if (h_csize_[L.S[i]] > SMALL_DIM) bp.push_back({h_eptr_[L.s_piv[i]], h_eld_[L.s_piv[i]], h_csize_[L.S[i]]});
+            if (h_csize_[L.S[i]] > SMALL_DIM && mine(L.S[i]))
+                bp.push_back({h_eptr_[L.s_piv[i]], h_eld_[L.s_piv[i]], h_csize_[L.S[i]]});
         run_potrf(bp, lg);
     }
+    mg_barrier();  // a block needs the factor of its row cluster too, possibly from another rank
     ev = fam_begin(F_TRSM);
     launch_scale_sym(tab_, D.s_right, D.s_left, (int)L.s_right.size(), d_mid_, next_counter(), st_);
     fam_end(F_TRSM, ev);
@@ -1010,7 +1145,7 @@ void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
         for (size_t i = 0; i < L.s_right.size(); i++) {
             const SymTrsm& r = L.s_right[i];
             const int m = h_csize_[r.cm], n = h_csize_[r.cn];
-            if ((m > SMALL_DIM || n > SMALL_DIM) && m > 0 && n > 0) {
+            if ((m > SMALL_DIM || n > SMALL_DIM) && m > 0 && n > 0 && mine(plan_.en1[r.eB])) {
                 right.push_back(host_trsm(r, nullptr));
                 left.push_back(host_trsm(L.s_left[i], nullptr));
             }
@@ -1040,16 +1175,22 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
     lg.ignored = L.ignored;
     const int ncolors = L.ncolors;
     if (!L.q.empty()) {
-        const size_t nq = L.q.size();
         QrSrc* ds = scratch_->alloc_n<QrSrc>(L.qs.size());
         launch_expand_qsrc(tab_, D.qs, (int)L.qs.size(), ds, st_);
         lg.launches++;
+        // per_color counts the tasks of the whole wavefront (all ranks): the launch shapes are the single-GPU ones
+        std::vector<int> per_color(std::max(1, ncolors), 0);
+        for (const SymQr& q : L.q) per_color[q.color]++;
+        std::vector<const SymQr*> own;
+        for (const SymQr& q : L.q)
+            if (mine(q.cluster)) own.push_back(&q);
+        const size_t nq = own.size();
         std::vector<QrTask> tasks(nq);
         std::vector<int> task_color(nq);
         size_t vtotal = 0, ttotal = 0;
         std::vector<size_t> voff(nq), toff(nq);
         for (size_t i = 0; i < nq; i++) {
-            const SymQr& q = L.q[i];
+            const SymQr& q = *own[i];
             QrTask& t = tasks[i];
             t.cluster = q.cluster;
             t.rows = h_csize_[q.cluster];
@@ -1094,8 +1235,6 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         const int stream_ctas = getenv("SPAND_RRQR_CTAS") ? atoi(getenv("SPAND_RRQR_CTAS")) : 2368;
         const long smem1_max = (getenv("SPAND_RRQR_SMEM1KB") ? atol(getenv("SPAND_RRQR_SMEM1KB")) : 200) * 1024;
         const double l2_budget = (getenv("SPAND_RRQR_L2MB") ? atof(getenv("SPAND_RRQR_L2MB")) : 128.0) * 1048576.0;
-        std::vector<int> per_color(std::max(1, ncolors), 0);
-        for (int c : task_color) per_color[c]++;
         for (size_t i = 0; i < nq; i++) {
             QrTask& t = tasks[i];
             int mn = std::max(1, std::min(t.rows, t.maxcols));
@@ -1196,43 +1335,55 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         for (size_t i = 0; i < nq; i++) sorted[i] = tasks[idx[i]];
         QrTask* dt = to_device(sorted, scratch_);
         // One launch per (colour, class). The classes of a colour are independent: they run concurrently on side
-        // streams forked from / joined into the factorization stream.
-        for (size_t b = 0; b < nq;) {
+        // streams forked from / joined into the factorization stream. With several GPUs every colour ends with the
+        // exchange of the new ranks (min over the replicas of csize) between two peer barriers: the next colour reads
+        // the shrunk blocks and sizes of its earlier neighbours wherever they live.
+        mg_barrier();
+        size_t b = 0;
+        for (int color = 0; color < ncolors; color++) {
             size_t cend = b;
-            while (cend < nq && task_color[idx[cend]] == task_color[idx[b]]) cend++;
-            auto ev = fam_begin(F_RRQR);
-            CK(cudaEventRecord(ev_fork_, st_));
-            int nside = 0;
-            while (b < cend) {
-                size_t e = b;
-                int smem = 0;
-                while (e < cend && klass[idx[e]] == klass[idx[b]]) {
-                    smem = std::max(smem, smem_need[idx[e]]);
-                    e++;
+            while (cend < nq && task_color[idx[cend]] == color) cend++;
+            if (cend > b) {
+                auto ev = fam_begin(F_RRQR);
+                CK(cudaEventRecord(ev_fork_, st_));
+                int nside = 0;
+                while (b < cend) {
+                    size_t e = b;
+                    int smem = 0;
+                    while (e < cend && klass[idx[e]] == klass[idx[b]]) {
+                        smem = std::max(smem, smem_need[idx[e]]);
+                        e++;
+                    }
+                    int k = klass[idx[b]];
+                    int mode = k >> 8, G = 1 << ((k >> 4) & 15);
+                    smem = (smem + 1023) & ~1023;
+                    cudaStream_t s = side_[nside % kSide];
+                    CK(cudaStreamWaitEvent(s, ev_fork_, 0));
+                    launch_rrqr(dt + b, (int)(e - b), ds, d_csize_, tol, G,
+                                mode == 0 ? 128 : ((mode == 1 || mode == 4) ? 256 : 512), mode != 2 && mode != 4, smem, s);
+                    nside++;
+                    lg.launches++;
+                    family_launches[F_RRQR]++;
+                    b = e;
                 }
-                int k = klass[idx[b]];
-                int mode = k >> 8, G = 1 << ((k >> 4) & 15);
-                smem = (smem + 1023) & ~1023;
-                cudaStream_t s = side_[nside % kSide];
-                CK(cudaStreamWaitEvent(s, ev_fork_, 0));
-                launch_rrqr(dt + b, (int)(e - b), ds, d_csize_, tol, G,
-                            mode == 0 ? 128 : ((mode == 1 || mode == 4) ? 256 : 512), mode != 2 && mode != 4, smem, s);
-                nside++;
-                lg.launches++;
-                family_launches[F_RRQR]++;
-                b = e;
+                for (int i = 0; i < std::min(nside, kSide); i++) {
+                    CK(cudaEventRecord(ev_join_[i], side_[i]));
+                    CK(cudaStreamWaitEvent(st_, ev_join_[i], 0));
+                }
+                family_launches[F_RRQR]--;  // fam_begin counted the colour once
+                fam_end(F_RRQR, ev);
             }
-            for (int i = 0; i < std::min(nside, kSide); i++) {
-                CK(cudaEventRecord(ev_join_[i], side_[i]));
-                CK(cudaStreamWaitEvent(st_, ev_join_[i], 0));
+            if (mg()) {
+                mg_barrier();
+                launch_csize_min(mg_csize_, mg_rank, mg_nranks, first, span, st_);
+                mg_barrier();
+                lg.launches += 3;
             }
-            family_launches[F_RRQR]--;  // fam_begin counted the colour once
-            fam_end(F_RRQR, ev);
         }
         lg.wavefronts = ncolors;
         // Orthogonal ops (tree.cpp:1322-1331): one entry per task, no-ops where the rank did not drop
         sl.n_house = (int)nq;
-        sl.house = arena_->alloc_n<HouseTask>(nq);
+        sl.house = arena_->alloc_n<HouseTask>(std::max<size_t>(1, nq));
         launch_expand_house(tab_, dt, (int)nq, sl.house, st_);
         lg.launches++;
         lg.t_plan_spars = wtime() - plan0;
@@ -1280,13 +1431,15 @@ void Tree::phase_merge(LevelLog& lg, SolveLevel& sl) {
         h_csize_[p] = size;
         xtotal += size;
     }
-    double* xbase = arena_->alloc_n<double>(xtotal + 1);
-    {
+    if (!mg()) {
+        double* xbase = arena_->alloc_n<double>(xtotal + 1);
         size_t off = 0;
         for (int p : parents) {
             h_xptr_[p] = xbase + off;
             off += cl_[p].size;
         }
+    } else {
+        for (int p : parents) h_xptr_[p] = alloc_block(h_owner_[p], cl_[p].size);
     }
     const int pfirst = parents.front(), np = parents.back() - pfirst + 1;
     stager_.upload(d_csize_ + pfirst, h_csize_.data() + pfirst, sizeof(int) * np, st_);
@@ -1306,7 +1459,7 @@ void Tree::phase_merge(LevelLog& lg, SolveLevel& sl) {
         const int CHUNK = 4096;
         for (const SymCopy& t : L.m_copy) {
             const int rows = h_csize_[t.c2], cols = h_csize_[t.c1];
-            if ((long)rows * cols <= COPY_SMALL || (ident && t.c1 == t.c2)) continue;
+            if ((long)rows * cols <= COPY_SMALL || (ident && t.c1 == t.c2) || !mine(t.c1)) continue;
             const int ldn = h_eld_[t.enew], lds = h_eld_[t.eold];
             double* dst = h_eptr_[t.enew] + h_pos_[t.c2] + (size_t)h_pos_[t.c1] * ldn;
             const double* src = h_eptr_[t.eold];
@@ -1356,6 +1509,7 @@ void Tree::factorize() {
     bool stopped = false;
     int last_level = -1;
     logs_final_ = false;
+    mg_barrier();  // every rank has assembled
     auto snapshot = [&](std::vector<int>& dst) {
         const std::vector<int>& bottom = bottoms_[current_bottom_];
         if (bottom.empty()) {
@@ -1579,9 +1733,12 @@ void Tree::solve_device(double* x_dev) {
     if (!factorized_) throw std::runtime_error("solve: call factorize first");
     double* xleaf = d_xleaf_;
     launch_gather(N, d_perm_, x_dev, xleaf, st_);  // b = P^T x
+    // Several GPUs: every operation runs on the owner of the segment it writes; the two Gemm* sweeps read segments
+    // (and panels) of other ranks through NVLink after a peer barrier.
     for (int l = 0; l < nlevels; l++) {
         SolveLevel& s = solve_[l];
         launch_trsv(s.e_trsv, s.n_e_trsv, 0, st_);
+        mg_barrier();
         launch_gemv(s.e_gemv_f, s.n_e_gemv_f, s.e_gemv_fc, 0, st_);
         launch_trsv(s.s_trsv, s.n_s_trsv, 0, st_);
         launch_house(s.house, s.n_house, 1, st_);
@@ -1594,10 +1751,17 @@ void Tree::solve_device(double* x_dev) {
         // LLT: x <- L^-T x, x_s -= A[n,s]^T x_n ; PLU: x <- U^-1 x, x_s -= A[s,n] x_n   (operations.cpp bwd)
         const bool plu = scale_kind == PLU;
         launch_trsv(s.s_trsv, s.n_s_trsv, plu ? 2 : 1, st_);
+        mg_barrier();
         launch_gemv(s.e_gemv_b, s.n_e_gemv_b, s.e_gemv_bc, plu ? 0 : 1, st_);
         launch_trsv(s.e_trsv, s.n_e_trsv, plu ? 2 : 1, st_);
     }
-    launch_scatter(N, d_perm_, xleaf, x_dev, st_);  // x = P b
+    if (!mg()) {
+        launch_scatter(N, d_perm_, xleaf, x_dev, st_);  // x = P b
+    } else {
+        mg_barrier();
+        launch_scatter_owned(N, d_perm_, mg_leaf_, d_dof_owner_, x_dev, st_);
+        mg_barrier();  // nobody starts the next solve before all peers have read these segments
+    }
 }
 
 void Tree::solve(double* x_host) {

@@ -117,6 +117,14 @@ class Tree {
     std::vector<LevelLog> log;   // call logs() for the completed flop / byte / nnz model
     const std::vector<LevelLog>& logs();
     double analyze_seconds() const { return t_analyze_; }
+    // ---- sub-tree sharding over the GPUs of one node, one process per GPU ----
+    // mg_setup allocates this rank's shared arena (blocks, solution segments, cluster sizes: everything a peer may
+    // touch) and must be followed by an exchange of the IPC handles (mg_get_handle / mg_set_peers) before assemble().
+    int mg_rank = 0, mg_nranks = 1;
+    void mg_setup(int rank, int nranks, size_t arena_bytes);
+    void mg_get_handle(void* out64) const;
+    void mg_set_peers(const void* handles);
+    std::vector<int> owner_map(int nranks) const;  // host only: rank owning every cluster (valid after partition)
     // symbolic plan without a device (CPU tests of the planner)
     void analyze_only(const SpMat& A);
     void plan_live_edges(int level, int phase, std::vector<int>& n1, std::vector<int>& n2) const;
@@ -204,6 +212,21 @@ class Tree {
     int *d_mid_ = nullptr, *d_cnt_ = nullptr;  // device work lists of the plan-driven kernels
     int cnt_next_ = 0;
     DevTables tab_{};
+    // multi-GPU state: peer-mapped bases of the shared arenas, bump pointers of every rank's arena (all ranks
+    // simulate all allocations, so every pointer table holds valid peer addresses), barrier epoch
+    char* mg_base_[MG_MAX_RANKS] = {};
+    size_t mg_top_[MG_MAX_RANKS] = {};
+    size_t mg_size_ = 0, mg_off_csize_ = 0, mg_off_leaf_ = 0, mg_off_blocks_ = 0;
+    bool mg_peers_set_ = false;
+    unsigned mg_epoch_ = 0;
+    PeerPtrs mg_flags_{}, mg_csize_{}, mg_leaf_{};
+    std::vector<int> h_owner_;
+    int* d_owner_ = nullptr;
+    signed char* d_dof_owner_ = nullptr;
+    bool mg() const { return mg_nranks > 1; }
+    bool mine(int cluster) const { return mg_nranks == 1 || h_owner_[cluster] == mg_rank; }
+    double* alloc_block(int owner, size_t doubles);
+    void mg_barrier();
     // PLU: diag(U), swap sequence and permutation of the current pivot of every cluster
     std::vector<double*> h_ud_;
     std::vector<int*> h_ipiv_, h_pperm_;

@@ -1,0 +1,64 @@
+"""torchrun worker of tests/test_mg_gpu.py: factorize one matrix sharded over the ranks and compare, on every rank,
+with the same factorization done by this rank alone (single-GPU path). The sharded path runs the same kernels on
+the same tasks in the same order, only on different GPUs: ranks, nnz and the solve must be bit-identical."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import spand_public_b200 as S  # noqa: E402
+
+
+def run(n, d, L, tol, sharded, local_rank):
+    A = S.neglapl(n, d)
+    t = S.Tree(L)
+    t.set_device(local_rank)
+    if sharded:
+        t.mg_init(dist, device=local_rank, arena_gb=float(os.environ.get("SPAND_MG_ARENA_GB", "4")))
+    t.set_tol(tol)
+    t.set_use_geo(True)
+    t.set_Xcoo(S.linspace_nd(n, d))
+    t.partition(S.symmetric_graph(A))
+    t.assemble(A)
+    t.factorize()
+    b = S.random(A.shape[0], 2019)
+    x = t.solve(b)
+    x2 = t.solve(b)
+    it, xc = t.cg(A, b, 200, 1e-12)
+    return dict(A=A, b=b, x=x, x2=x2, ranks=t.stats()[2].copy(), nnz=t.nnz(), it=it, xc=xc,
+                tfact=t.factorize_seconds(), tree=t)
+
+
+def main():
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    out = []
+    for (n, d, L, tol) in [(16, 3, 6, 1e-2), (32, 2, 6, 0.0), (24, 3, 8, 1e-2)]:
+        sh = run(n, d, L, tol, True, local_rank)
+        one = run(n, d, L, tol, False, local_rank)
+        res = float(np.linalg.norm(sh["A"] @ sh["x"] - sh["b"]) / np.linalg.norm(sh["b"]))
+        rec = dict(cfg=[n, d, L, tol], rank=rank, world=world, same_ranks=bool(np.array_equal(sh["ranks"], one["ranks"])),
+                   same_nnz=bool(sh["nnz"] == one["nnz"]), same_x=bool(np.array_equal(sh["x"], one["x"])),
+                   repeat_x=bool(np.array_equal(sh["x"], sh["x2"])), same_cg=bool(sh["it"] == one["it"]),
+                   same_cg_x=bool(np.array_equal(sh["xc"], one["xc"])), residual=res,
+                   maxdiff=float(np.abs(sh["x"] - one["x"]).max()), t_sharded=sh["tfact"], t_single=one["tfact"])
+        out.append(rec)
+        del sh, one
+        dist.barrier()
+    allrec = [None] * world
+    dist.all_gather_object(allrec, out)
+    if rank == 0:
+        print("MG_RESULT " + json.dumps(allrec))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

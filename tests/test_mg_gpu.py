@@ -1,0 +1,31 @@
+"""GPU, 2 ranks (skipped on a single-GPU box): one factorization sharded by ND sub-trees over two GPUs must give the
+single-GPU result bit for bit (same kernels, same tasks, same accumulation order; only the placement differs)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_gpu_sharding_is_bit_identical_to_one_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29551", os.path.join(ROOT, "tests", "mg_worker.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("MG_RESULT ")][-1]
+    per_rank = json.loads(line[len("MG_RESULT "):])
+    assert len(per_rank) == 2
+    for recs in per_rank:
+        for rec in recs:
+            assert rec["same_ranks"] and rec["same_nnz"], rec
+            assert rec["same_x"] and rec["repeat_x"], rec
+            assert rec["same_cg"] and rec["same_cg_x"], rec
+            tol = rec["cfg"][3]
+            assert rec["residual"] <= max(200 * tol, 1e-10), rec
