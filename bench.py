@@ -7,7 +7,7 @@ configuration BASELINE.json quotes its metric on: the synthetic 3-D 7-point Lapl
 in HBM when the timed region starts (`value`); `e2e` times assemble (host CSC -> dense blocks -> HBM)
 + factorize + one solve with host vectors through the C ABI.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c4|c3|c2|c1|n,d,L,tol]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c4|c3|c2|c1|c5|c5s|n,d,L,tol]
 
 N > 1 (torchrun): the ranks factorize ONE matrix together, sharded by nested-dissection sub-trees; blocks of
 shared separators are read / written through peer-mapped memory over NVLink between peer barriers
@@ -35,7 +35,23 @@ CONFIGS = {
     "c4": (128, 3, 16, 1e-2, "3D Laplacian 128^3, tol 1e-2, 16 levels"),
     "s64": (64, 3, 13, 1e-2, "3D Laplacian 64^3, tol 1e-2, 13 levels"),
     "s48": (48, 3, 12, 1e-2, "3D Laplacian 48^3, tol 1e-2, 12 levels"),
+    # config C5: non-symmetric, GEN + PLU, GMRES(100); 16 = round(log2(N / 64)) (tests/spaND.cpp:137-140)
+    "c5": (160, 3, 16, 1e-2, "3D anisotropic variable-coefficient convection-diffusion 160^3 (non-symmetric, GEN+PLU), "
+                             "tol 1e-2, 16 levels"),
+    "c5s": (96, 3, 14, 1e-2, "3D anisotropic variable-coefficient convection-diffusion 96^3 (non-symmetric, GEN+PLU), "
+                             "tol 1e-2, 14 levels"),
+    "a48": (48, 3, 11, 1e-2, "3D anisotropic variable-coefficient convection-diffusion 48^3 (non-symmetric, GEN+PLU), "
+                             "tol 1e-2, 11 levels"),
 }
+ANISO = ("c5", "c5s", "a48")  # matrix family of these configurations: S.aniso_convdiff, GEN / PLU / GMRES
+
+
+def is_aniso(cfg):
+    return "convection-diffusion" in cfg[4]
+
+
+def matrix_of(S, cfg):
+    return S.aniso_convdiff(cfg[0]) if is_aniso(cfg) else S.neglapl(cfg[0], cfg[1])
 
 
 def parse_config(name):
@@ -133,13 +149,14 @@ def run_oracle(cfg, steps, warmup, threads):
     import spand_public_b200 as S
     n, d, L, tol, desc = cfg
     O.lib().orc_set_threads(threads)
-    A = S.neglapl(n, d)
+    A = matrix_of(S, cfg)
     X = S.linspace_nd(n, d)
     G = S.symmetric_graph(A)
+    gen = is_aniso(cfg)
     times = []
     info = {}
     for it in range(warmup + steps):
-        t = O.OracleTree(L, tol=tol)
+        t = O.OracleTree(L, tol=tol, symm_kind=O.GEN, scaling_kind=O.PLU) if gen else O.OracleTree(L, tol=tol)
         t.set_coords(X)
         t.partition(G)
         t.assemble(A)
@@ -154,7 +171,10 @@ def run_oracle(cfg, steps, warmup, threads):
             x = t.solve(b)
             info["tsolve_s"] = time.perf_counter() - ts
             info["residual"] = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
-            info["cg_iterations"] = int(t.cg(A, b, 500, 1e-12)[0])
+            if gen:
+                info["gmres_iterations"] = int(t.gmres(A, b, 500, 100, 1e-12)[0])
+            else:
+                info["cg_iterations"] = int(t.cg(A, b, 500, 1e-12)[0])
             info["gflop"] = flops_of(t.log()) / 1e9
             info["nnz_fact"] = int(t.nnz())
         del t
@@ -185,6 +205,8 @@ def main():
         sample_name = "s64" if args.steps + args.warmup <= 8 else "s48"
         if args.config in ("c1", "c2"):
             sample_name = args.config
+        if args.config in ANISO:
+            sample_name = "a48"
         scfg = CONFIGS[sample_name]
         ncpu = os.cpu_count() or 1
         # The reference is sequential C++ over BLAS/LAPACK (tests/Makefile links mkl_sequential); extra BLAS threads
@@ -217,9 +239,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the spaND B200 path has no CPU fallback")
     dist = None
+    stdout_fd = None
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
+        # NCCL prints its version banner on fd 1 at the first collective: keep stdout for the one JSON line
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -230,13 +257,19 @@ def main():
         torch.cuda.synchronize()
 
     fp64_peak = measure_fp64_peak(torch, dev) if rank == 0 else None
-    A = S.neglapl(n, d)
+    A = matrix_of(S, cfg)
     N = A.shape[0]
     X = S.linspace_nd(n, d)
     G = S.symmetric_graph(A)
     b = S.random(N, 2019)
+    gen = is_aniso(cfg)
     t = S.Tree(L)
     t.set_device(local_rank)
+    if gen:
+        if world > 1:
+            raise SystemExit("bench.py: sub-tree sharding covers the SPD/LLT path only; run C5 with --gpus 1")
+        t.set_symm_kind(S.GEN)
+        t.set_scaling_kind(S.PLU)
     if world > 1:
         # one factorization sharded by ND sub-trees over the ranks (blocks of shared separators reached through
         # peer memory over NVLink); every rank makes the same calls
@@ -293,8 +326,12 @@ def main():
     t.set_profile(False)
     cg_it, t_cg = None, None
     if not args.no_cg:  # collective when sharded: every rank runs the same PCG around the distributed solve
-        cg_it, _ = t.cg(A, b, 500, 1e-12)
-        t_cg = t.t_cg
+        if gen:  # tests/spaND.cpp:312-322: GMRES for non-symmetric problems
+            cg_it, _ = t.gmres(A, b, 500, 100, 1e-12)
+            t_cg = t.t_gmres
+        else:
+            cg_it, _ = t.cg(A, b, 500, 1e-12)
+            t_cg = t.t_cg
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -346,12 +383,13 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        scfg = CONFIGS["s64"] if args.config in ("c4", "c3") else cfg
+        scfg = CONFIGS["s64"] if args.config in ("c4", "c3") else (CONFIGS["a48"] if args.config in ANISO else cfg)
         Nc, times, info = run_oracle(scfg, 1, 0, 1)
         cpu = {"value": Nc / times[0] / 1e6, "unit": unit, "cores": 1, "kind": "port",
                "sample": f"one full factorize() of {scfg[4]} by the oracle port (OpenBLAS 1 thread, as the reference's "
                          f"mkl_sequential build); {times[0]:.2f} s",
-               "factorize_time_s": times[0], "cg_iterations": info["cg_iterations"], "residual": info["residual"]}
+               "factorize_time_s": times[0], "residual": info["residual"],
+               **{k: info[k] for k in ("cg_iterations", "gmres_iterations") if k in info}}
 
     out = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -370,12 +408,16 @@ def main():
                 "seconds_per_step": te2e / args.steps, "assemble_s": float(np.mean(tassm)),
                 "solve_s": float(np.mean(tsolve))},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        "residual_one_solve": res, "cg_iterations": cg_it, "cg_seconds": t_cg, "nnz_fact": int(t.nnz()),
+        "residual_one_solve": res, ("gmres_iterations" if gen else "cg_iterations"): cg_it,
+        ("gmres_seconds" if gen else "cg_seconds"): t_cg, "nnz_fact": int(t.nnz()),
         "arena_gb": t.arena_bytes() / 1e9,
         "per_level": {k: [float(v) for v in lg[k]] for k in ("t_elim", "t_scale", "t_spars", "t_merge", "t_host",
                                                                "launches", "wavefronts", "dofs_left_spars")},
     }
-    print(json.dumps(out))
+    if stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+    print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -102,7 +102,18 @@ inline int cg(const CscView& A, const double* rhs, double* x, const Tree& precon
     if (it < 0) throw std::runtime_error(spand_last_error(precond.handle()));
     return it;
 }
+// include/is.h:13 — Householder GMRES, left preconditioned; returns the reference's iteration count
+inline int gmres(const CscView& A, const double* rhs, double* x, const Tree& precond, int iters, int restart,
+                 double tol, bool verb, double* seconds = nullptr) {
+    int it = spand_gmres(precond.handle(), A.rows, A.colptr, A.rowind, A.val, rhs, x, iters, restart, tol, verb, seconds);
+    if (it < 0) throw std::runtime_error(spand_last_error(precond.handle()));
+    return it;
+}
 #ifdef SPAND_B200_HAVE_EIGEN
+inline int gmres(const Tree::SpMat& A, const Eigen::VectorXd& rhs, Eigen::VectorXd& x, const Tree& precond, int iters,
+                 int restart, double tol, bool verb) {
+    return gmres(Tree::view(A), rhs.data(), x.data(), precond, iters, restart, tol, verb);
+}
 inline int cg(const Tree::SpMat& A, const Eigen::VectorXd& rhs, Eigen::VectorXd& x, const Tree& precond, int iters,
               double tol, bool verb) {
     return cg(Tree::view(A), rhs.data(), x.data(), precond, iters, tol, verb);

@@ -66,6 +66,11 @@ int spand_solve_device(spand_tree* t, double* x_device);
 int spand_cg(spand_tree* t, int N, const int* colptr, const int* rowind, const double* val, const double* rhs,
              double* x, int iters, double tol, int verb, double* seconds);
 
+/* gmres(A, rhs, x, precond, iters, restart, tol, verb)   include/is.h:13, src/is.cpp:123-300
+ * Householder GMRES, left preconditioned; returns the reference's iteration count or a negative error */
+int spand_gmres(spand_tree* t, int N, const int* colptr, const int* rowind, const double* val, const double* rhs,
+                double* x, int iters, int restart, double tol, int verb, double* seconds);
+
 /* Tree::nnz / get_stop / get_nlevels                include/tree.h:158-160 */
 long long spand_nnz(spand_tree* t);
 int spand_get_stop(spand_tree* t);

@@ -83,6 +83,13 @@ int orc_cg(void* h_, int N, const int* colptr, const int* rowind, const double* 
     guarded(h, [&] { it = cg(spand::from_csc(N, colptr, rowind, val), rhs, x, h->t, iters, tol, verb != 0); });
     return it;
 }
+int orc_gmres(void* h_, int N, const int* colptr, const int* rowind, const double* val, const double* rhs, double* x,
+              int iters, int restart, double tol, int verb) {
+    Handle* h = (Handle*)h_;
+    int it = -1;
+    guarded(h, [&] { it = gmres(spand::from_csc(N, colptr, rowind, val), rhs, x, h->t, iters, restart, tol, verb != 0); });
+    return it;
+}
 long long orc_nnz(void* h_) { return ((Handle*)h_)->t.nnz(); }
 int orc_get_stop(void* h_) { return ((Handle*)h_)->t.get_stop(); }
 int orc_get_N(void* h_) { return ((Handle*)h_)->t.N; }

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <set>
 #include <stdexcept>
@@ -885,6 +886,149 @@ int cg(const SpMat& A, const double* rhs, double* x, OTree& precond, int iters, 
         i++;
     }
     return i + 1;
+}
+
+
+// ---- Householder GMRES, src/is.cpp:123-300. The reference leans on Eigen 3.3 for three primitives; they are
+// restated here from Eigen's published definitions (Householder.h makeHouseholder / applyHouseholderOnTheLeft,
+// Jacobi.h makeGivens for real scalars).
+namespace {
+
+// x = [c0; tail] (length n): H x = beta e_1 with H = I - tau [1; ess][1; ess]^T
+void make_householder(const double* x, int n, double* ess, double& tau, double& beta) {
+    double tail2 = 0;
+    for (int i = 1; i < n; i++) tail2 += x[i] * x[i];
+    const double c0 = x[0];
+    if (n == 1 || tail2 <= std::numeric_limits<double>::min()) {
+        tau = 0;
+        beta = c0;
+        for (int i = 1; i < n; i++) ess[i - 1] = 0;
+    } else {
+        beta = std::sqrt(c0 * c0 + tail2);
+        if (c0 >= 0) beta = -beta;
+        for (int i = 1; i < n; i++) ess[i - 1] = x[i] / (c0 - beta);
+        tau = (beta - c0) / beta;
+    }
+}
+
+void apply_householder_left(double* v, int n, const double* ess, double tau) {
+    if (n == 1) {
+        v[0] *= 1 - tau;
+    } else if (tau != 0) {
+        double tmp = 0;
+        for (int i = 1; i < n; i++) tmp += ess[i - 1] * v[i];
+        tmp += v[0];
+        v[0] -= tau * tmp;
+        for (int i = 1; i < n; i++) v[i] -= tau * ess[i - 1] * tmp;
+    }
+}
+
+struct Givens {
+    double c = 1, s = 0;
+    void make(double p, double q) {
+        if (q == 0) {
+            c = p < 0 ? -1 : 1;
+            s = 0;
+        } else if (p == 0) {
+            c = 0;
+            s = q < 0 ? 1 : -1;
+        } else if (std::fabs(p) > std::fabs(q)) {
+            double t = q / p, u = std::sqrt(1 + t * t);
+            if (p < 0) u = -u;
+            c = 1 / u;
+            s = -t * c;
+        } else {
+            double t = p / q, u = std::sqrt(1 + t * t);
+            if (q < 0) u = -u;
+            s = -1 / u;
+            c = -t * s;
+        }
+    }
+    // v.applyOnTheLeft(p, q, G.adjoint()): [x_p; x_q] <- [c -s; s c] [x_p; x_q]
+    void apply_adjoint(double& xp, double& xq) const {
+        double a = c * xp - s * xq, b = s * xp + c * xq;
+        xp = a;
+        xq = b;
+    }
+};
+
+}  // namespace
+
+int gmres(const SpMat& A, const double* rhs, double* x, OTree& precond, int iters, int restart, double tol, bool verb) {
+    const int m = A.rows;
+    double rn = 0;
+    for (int i = 0; i < m; i++) rn += rhs[i] * rhs[i];
+    if (std::sqrt(rn) <= std::numeric_limits<double>::min()) {
+        std::fill(x, x + m, 0.0);
+        return 1;  // the reference returns `true`
+    }
+    const int maxIters = iters;
+    iters = 0;
+    std::vector<double> r0(m), t(m), v(m), x_new(m);
+    auto residual = [&]() {
+        spand::spmv(A, x, t.data());
+        for (int i = 0; i < m; i++) r0[i] = rhs[i] - t[i];
+        precond.solve(r0.data());
+    };
+    residual();
+    double r0Norm = 0;
+    for (int i = 0; i < m; i++) r0Norm += r0[i] * r0[i];
+    r0Norm = std::sqrt(r0Norm);
+    if (r0Norm == 0) return 1;
+    std::vector<double> H((size_t)m * (restart + 1), 0.0), w(restart + 1, 0.0), tau(restart + 1, 0.0);
+    std::vector<Givens> G(restart);
+    auto Hcol = [&](int i) { return H.data() + (size_t)i * m; };
+    double beta;
+    make_householder(r0.data(), m, Hcol(0) + 1, tau[0], beta);
+    w[0] = beta;
+    for (int k = 1; k <= restart; ++k) {
+        ++iters;
+        std::fill(v.begin(), v.end(), 0.0);
+        v[k - 1] = 1.0;
+        for (int i = k - 1; i >= 0; --i) apply_householder_left(v.data() + i, m - i, Hcol(i) + i + 1, tau[i]);
+        spand::spmv(A, v.data(), t.data());
+        v = t;
+        precond.solve(v.data());
+        for (int i = 0; i < k; ++i) apply_householder_left(v.data() + i, m - i, Hcol(i) + i + 1, tau[i]);
+        double tn = 0;
+        for (int i = k; i < m; i++) tn += v[i] * v[i];
+        if (m - k > 0 && std::sqrt(tn) != 0.0) {
+            make_householder(v.data() + k, m - k, Hcol(k) + k + 1, tau[k], beta);
+            apply_householder_left(v.data() + k, m - k, Hcol(k) + k + 1, tau[k]);
+        }
+        for (int i = 0; i < k - 1; ++i) G[i].apply_adjoint(v[i], v[i + 1]);
+        if (k < m && v[k] != 0.0) {
+            G[k - 1].make(v[k - 1], v[k]);
+            G[k - 1].apply_adjoint(v[k - 1], v[k]);
+            G[k - 1].apply_adjoint(w[k - 1], w[k]);
+        }
+        for (int i = 0; i < k; i++) Hcol(k - 1)[i] = v[i];
+        double tol_error = std::fabs(w[k]) / r0Norm;
+        bool stop = (k == m || tol_error < tol || iters == maxIters);
+        if (verb) printf("%d: |Ax-b|/|b| = %3.2e <? %3.2e\n", iters, tol_error, tol);
+        if (stop || k == restart) {
+            std::vector<double> y(w.begin(), w.begin() + k);
+            for (int i = k - 1; i >= 0; --i) {  // upper-triangular solve with H(0:k, 0:k)
+                for (int j = i + 1; j < k; j++) y[i] -= Hcol(j)[i] * y[j];
+                y[i] /= Hcol(i)[i];
+            }
+            std::fill(x_new.begin(), x_new.end(), 0.0);
+            for (int i = k - 1; i >= 0; --i) {
+                x_new[i] += y[i];
+                apply_householder_left(x_new.data() + i, m - i, Hcol(i) + i + 1, tau[i]);
+            }
+            for (int i = 0; i < m; i++) x[i] += x_new[i];
+            if (stop) return iters;
+            k = 0;
+            residual();
+            std::fill(H.begin(), H.end(), 0.0);
+            std::fill(w.begin(), w.end(), 0.0);
+            std::fill(tau.begin(), tau.end(), 0.0);
+            make_householder(r0.data(), m, Hcol(0) + 1, tau[0], beta);
+            w[0] = beta;
+        }
+    }
+    return iters;
 }
 
 }  // namespace spand_oracle

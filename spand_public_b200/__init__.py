@@ -26,7 +26,7 @@ EXPORTS = [
     "spand_create", "spand_destroy", "spand_last_error", "spand_set_tol", "spand_set_skip", "spand_set_symm_kind",
     "spand_set_scaling_kind", "spand_set_use_geo", "spand_set_verb", "spand_set_use_sparsify", "spand_set_device",
     "spand_set_coords", "spand_set_stop", "spand_partition", "spand_get_partition", "spand_get_perm", "spand_get_N",
-    "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_nnz", "spand_get_stop",
+    "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_gmres", "spand_nnz", "spand_get_stop",
     "spand_get_nlevels", "spand_num_clusters", "spand_get_stats", "spand_log_fields", "spand_log_field_name",
     "spand_get_log", "spand_factorize_seconds", "spand_analyze_seconds", "spand_plan_analyze", "spand_plan_live_edges",
     "spand_plan_counts", "spand_get_cluster_layout", "spand_mg_setup", "spand_mg_get_handle", "spand_mg_set_peers",
@@ -72,6 +72,7 @@ def lib():
     L.spand_solve.argtypes = [_p, _dp]
     L.spand_solve_device.argtypes = [_p, _p]
     L.spand_cg.argtypes = [_p, _i, _ip, _ip, _dp, _dp, _dp, _i, _d, _i, C.POINTER(_d)]
+    L.spand_gmres.argtypes = [_p, _i, _ip, _ip, _dp, _dp, _dp, _i, _i, _d, _i, C.POINTER(_d)]
     L.spand_nnz.restype = C.c_longlong
     L.spand_nnz.argtypes = [_p]
     L.spand_get_stop.argtypes = [_p]
@@ -265,6 +266,18 @@ class Tree:
         if it < 0:
             raise RuntimeError(self._l.spand_last_error(self._h).decode())
         self.t_cg = sec.value
+        return it, x
+
+    def gmres(self, A, b, iters=100, restart=100, tol=1e-12, verb=False, x0=None):
+        """gmres(A, rhs, x, precond, iters, restart, tol, verb), include/is.h:13 — on the GPU; (iterations, x)."""
+        N, cp, ri, v = _csc(A)
+        x = np.zeros(N) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        sec = _d(0.0)
+        it = self._l.spand_gmres(self._h, N, cp, ri, v, np.ascontiguousarray(b, dtype=np.float64), x, iters, restart,
+                                 tol, int(verb), C.byref(sec))
+        if it < 0:
+            raise RuntimeError(self._l.spand_last_error(self._h).decode())
+        self.t_gmres = sec.value
         return it, x
 
     def nnz(self): return self._l.spand_nnz(self._h)

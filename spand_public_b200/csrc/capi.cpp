@@ -111,6 +111,14 @@ int spand_cg(spand_tree* t, int N, const int* colptr, const int* rowind, const d
     int rc = guarded(t, [&] { it = t->t.cg(from_csc(N, colptr, rowind, val), rhs, x, iters, tol, verb != 0, seconds); });
     return rc == 0 ? it : -1;
 }
+int spand_gmres(spand_tree* t, int N, const int* colptr, const int* rowind, const double* val, const double* rhs,
+                double* x, int iters, int restart, double tol, int verb, double* seconds) {
+    int it = -1;
+    int rc = guarded(t, [&] {
+        it = t->t.gmres(from_csc(N, colptr, rowind, val), rhs, x, iters, restart, tol, verb != 0, seconds);
+    });
+    return rc == 0 ? it : -1;
+}
 long long spand_nnz(spand_tree* t) { return t->t.nnz(); }
 int spand_get_stop(spand_tree* t) { return t->t.get_stop(); }
 int spand_get_nlevels(spand_tree* t) { return t->t.nlevels; }

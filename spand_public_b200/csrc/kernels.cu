@@ -1185,7 +1185,17 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, int rank, int nranks, unsign
         volatile unsigned* theirs = reinterpret_cast<volatile unsigned*>(flags.p[r]) + rank;
         *theirs = epoch;
         volatile unsigned* mine = reinterpret_cast<volatile unsigned*>(flags.p[rank]) + r;
-        while ((int)(*mine - epoch) < 0) {}
+        // a peer that died (or never arrives) must not hang this GPU: give up after 60 s and fault the context,
+        // which the host sees as a CUDA error on the next synchronisation
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned spins = 0;
+        while ((int)(*mine - epoch) < 0) {
+            if ((++spins & 0xfffu) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 60000000000ull) __trap();
+            }
+        }
         __threadfence_system();
     }
 }

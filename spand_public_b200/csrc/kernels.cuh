@@ -246,4 +246,15 @@ void launch_xpay(int n, const double* x, double beta, double* y, cudaStream_t st
 void launch_gather(int n, const int* idx, const double* src, double* dst, cudaStream_t st);   // dst[i] = src[idx[i]]
 void launch_scatter(int n, const int* idx, const double* src, double* dst, cudaStream_t st);  // dst[idx[i]] = src[i]
 
+// Householder GMRES building blocks (src/is.cpp:123-300), krylov.cu. `partial` is a scratch of KR_GRID + 1 doubles;
+// tau / beta are device scalars. Two launches per call, deterministic reductions, no host synchronisation.
+constexpr int KR_GRID = 148 * 4;
+void launch_kr_house_apply(int n, double* v, const double* ess, const double* tau, double* partial, cudaStream_t st);
+void launch_kr_house_make(int n, const double* x, double* ess, double* tau, double* beta, double* partial,
+                          cudaStream_t st);
+// out[0] = a . b, reduced in a fixed order (bit-reproducible, unlike launch_dot's atomics)
+void launch_dot_det(int n, const double* a, const double* b, double* partial, double* out, cudaStream_t st);
+void launch_kr_unit(int n, int k, double* v, cudaStream_t st);            // v = e_k
+void launch_kr_residual(int n, const double* b, double* y, cudaStream_t st);  // y = b - y
+
 }  // namespace spand

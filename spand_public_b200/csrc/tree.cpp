@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1783,22 +1784,22 @@ int Tree::cg(const SpMat& A, const double* rhs, double* x, int iters, double tol
         for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) tt.push_back({j, A.rowind[k], A.val[k]});
     SpMat At = from_triplets(n, n, tt);
     int *d_rp, *d_ci;
-    double *d_v, *d_x, *d_r, *d_p, *d_z, *d_tmp, *d_b, *d_s;
+    double *d_v, *d_x, *d_r, *d_p, *d_z, *d_tmp, *d_b, *d_s, *d_part;
     CK(cudaMalloc((void**)&d_rp, sizeof(int) * (n + 1)));
     CK(cudaMalloc((void**)&d_ci, sizeof(int) * At.nnz()));
     CK(cudaMalloc((void**)&d_v, sizeof(double) * At.nnz()));
     double** vecs[] = {&d_x, &d_r, &d_p, &d_z, &d_tmp, &d_b};
     for (auto v : vecs) CK(cudaMalloc((void**)v, sizeof(double) * n));
     CK(cudaMalloc((void**)&d_s, sizeof(double) * 4));
+    CK(cudaMalloc((void**)&d_part, sizeof(double) * (KR_GRID + 1)));
     CK(cudaMemcpyAsync(d_rp, At.colptr.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_ci, At.rowind.data(), sizeof(int) * At.nnz(), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_v, At.val.data(), sizeof(double) * At.nnz(), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_b, rhs, sizeof(double) * n, cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, st_));
     auto dot = [&](const double* a, const double* b) {
-        double h;
-        CK(cudaMemsetAsync(d_s, 0, sizeof(double), st_));
-        launch_dot(n, a, b, d_s, st_);
+        double h;  // fixed-order reduction: the whole PCG is bit-reproducible
+        launch_dot_det(n, a, b, d_part, d_s, st_);
         CK(cudaMemcpyAsync(&h, d_s, sizeof(double), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
         return h;
@@ -1852,6 +1853,173 @@ int Tree::cg(const SpMat& A, const double* rhs, double* x, int iters, double tol
     cudaFree(d_v);
     for (auto v : vecs) cudaFree(*v);
     cudaFree(d_s);
+    cudaFree(d_part);
+    return result;
+}
+
+// src/is.cpp:123-300: Householder GMRES, left preconditioned, restarted. The Krylov basis is kept as the
+// essential parts of the reflectors in an N x (restart + 1) array in HBM (column i holds H_i below row i); the
+// small triangular factor, the Givens rotations and the rotated right-hand side w live on the host, which reads
+// back the k + 1 leading entries of the new column once per iteration (the only synchronisation).
+int Tree::gmres(const SpMat& A, const double* rhs, double* x, int iters, int restart, double tol_, bool verbose,
+                double* seconds) {
+    if (!factorized_) throw std::runtime_error("gmres: call factorize first");
+    const int m = A.cols;
+    if (restart < 1) throw std::runtime_error("gmres: restart must be >= 1");
+    if (restart > m) restart = m;
+    std::vector<Triplet> tt;
+    tt.reserve(A.nnz());
+    for (int j = 0; j < m; j++)
+        for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) tt.push_back({j, A.rowind[k], A.val[k]});
+    SpMat At = from_triplets(m, m, tt);  // CSR of A = CSC of A^T
+    int *d_rp, *d_ci;
+    double *d_v, *d_x, *d_b, *d_w, *d_t, *d_xn, *d_H, *d_tau, *d_beta, *d_part;
+    CK(cudaMalloc((void**)&d_rp, sizeof(int) * (m + 1)));
+    CK(cudaMalloc((void**)&d_ci, sizeof(int) * At.nnz()));
+    CK(cudaMalloc((void**)&d_v, sizeof(double) * At.nnz()));
+    double** vecs[] = {&d_x, &d_b, &d_w, &d_t, &d_xn};
+    for (auto v : vecs) CK(cudaMalloc((void**)v, sizeof(double) * m));
+    CK(cudaMalloc((void**)&d_H, sizeof(double) * (size_t)m * (restart + 1)));
+    CK(cudaMalloc((void**)&d_tau, sizeof(double) * (restart + 1)));
+    CK(cudaMalloc((void**)&d_beta, sizeof(double)));
+    CK(cudaMalloc((void**)&d_part, sizeof(double) * (KR_GRID + 1)));
+    CK(cudaMemcpyAsync(d_rp, At.colptr.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_ci, At.rowind.data(), sizeof(int) * At.nnz(), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_v, At.val.data(), sizeof(double) * At.nnz(), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_b, rhs, sizeof(double) * m, cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_x, x, sizeof(double) * m, cudaMemcpyHostToDevice, st_));
+    auto Hess = [&](int i) { return d_H + (size_t)i * m + i + 1; };  // essential part of reflector i (length m-i-1)
+    auto apply = [&](double* vec, int i) { launch_kr_house_apply(m - i, vec + i, Hess(i), d_tau + i, d_part, st_); };
+    auto norm = [&](const double* a) {
+        double h;
+        launch_dot_det(m, a, a, d_part, d_beta, st_);
+        CK(cudaMemcpyAsync(&h, d_beta, sizeof(double), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        return std::sqrt(h);
+    };
+    // r0 = M^-1 (rhs - A x) into d_w, then the first reflector; returns beta
+    auto start_cycle = [&]() {
+        launch_spmv(m, d_rp, d_ci, d_v, d_x, d_w, st_);
+        launch_kr_residual(m, d_b, d_w, st_);
+        solve_device(d_w);
+    };
+    auto first_reflector = [&]() {
+        double beta;
+        CK(cudaMemsetAsync(d_tau, 0, sizeof(double) * (restart + 1), st_));
+        launch_kr_house_make(m, d_w, Hess(0), d_tau, d_beta, d_part, st_);
+        CK(cudaMemcpyAsync(&beta, d_beta, sizeof(double), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        return beta;
+    };
+    struct Giv {
+        double c = 1, s = 0;
+        void make(double p, double q) {  // Eigen JacobiRotation::makeGivens, real scalars
+            if (q == 0) {
+                c = p < 0 ? -1 : 1;
+                s = 0;
+            } else if (p == 0) {
+                c = 0;
+                s = q < 0 ? 1 : -1;
+            } else if (std::fabs(p) > std::fabs(q)) {
+                double t = q / p, u = std::sqrt(1 + t * t);
+                if (p < 0) u = -u;
+                c = 1 / u;
+                s = -t * c;
+            } else {
+                double t = p / q, u = std::sqrt(1 + t * t);
+                if (q < 0) u = -u;
+                s = -1 / u;
+                c = -t * s;
+            }
+        }
+        void apply_adjoint(double& xp, double& xq) const {
+            double a = c * xp - s * xq, b = s * xp + c * xq;
+            xp = a;
+            xq = b;
+        }
+    };
+    CK(cudaStreamSynchronize(st_));
+    const double t0 = wtime();
+    int result = 0;
+    const int maxIters = iters;
+    iters = 0;
+    do {
+        if (norm(d_b) <= std::numeric_limits<double>::min()) {
+            CK(cudaMemsetAsync(d_x, 0, sizeof(double) * m, st_));
+            result = 1;  // the reference returns `true`
+            break;
+        }
+        start_cycle();
+        const double r0Norm = norm(d_w);
+        if (r0Norm == 0) {
+            result = 1;
+            break;
+        }
+        std::vector<double> R((size_t)(restart + 1) * (restart + 1), 0.0), w(restart + 1, 0.0), head(restart + 2, 0.0);
+        std::vector<Giv> G(restart);
+        w[0] = first_reflector();
+        bool done = false;
+        for (int k = 1; k <= restart && !done; ++k) {
+            ++iters;
+            launch_kr_unit(m, k - 1, d_w, st_);
+            for (int i = k - 1; i >= 0; --i) apply(d_w, i);
+            launch_spmv(m, d_rp, d_ci, d_v, d_w, d_t, st_);
+            solve_device(d_t);
+            for (int i = 0; i < k; ++i) apply(d_t, i);
+            if (k < m) {  // new reflector from v.tail(m - k) (an all-zero tail gives tau = 0, like the skipped branch)
+                launch_kr_house_make(m - k, d_t + k, Hess(k), d_tau + k, d_beta, d_part, st_);
+                apply(d_t, k);
+            }
+            const int nh = std::min(k + 1, m);
+            CK(cudaMemcpyAsync(head.data(), d_t, sizeof(double) * nh, cudaMemcpyDeviceToHost, st_));
+            CK(cudaStreamSynchronize(st_));
+            if (nh < k + 1) head[k] = 0.0;
+            for (int i = 0; i < k - 1; ++i) G[i].apply_adjoint(head[i], head[i + 1]);
+            if (k < m && head[k] != 0.0) {
+                G[k - 1].make(head[k - 1], head[k]);
+                G[k - 1].apply_adjoint(head[k - 1], head[k]);
+                G[k - 1].apply_adjoint(w[k - 1], w[k]);
+            }
+            for (int i = 0; i < k; i++) R[i + (size_t)(k - 1) * (restart + 1)] = head[i];
+            const double tol_error = std::fabs(w[k]) / r0Norm;
+            const bool stop = (k == m || tol_error < tol_ || iters == maxIters);
+            if (verbose) printf("%d: |Ax-b|/|b| = %3.2e <? %3.2e\n", iters, tol_error, tol_);
+            if (stop || k == restart) {
+                std::vector<double> y(w.begin(), w.begin() + k);
+                for (int i = k - 1; i >= 0; --i) {
+                    for (int j = i + 1; j < k; j++) y[i] -= R[i + (size_t)j * (restart + 1)] * y[j];
+                    y[i] /= R[i + (size_t)i * (restart + 1)];
+                }
+                // x_new = H_0 ... H_{k-1} [y; 0]  (x_new(i) += y(i) before H_i only touches rows >= i)
+                CK(cudaMemsetAsync(d_xn, 0, sizeof(double) * m, st_));
+                CK(cudaMemcpyAsync(d_xn, y.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st_));
+                for (int i = k - 1; i >= 0; --i) apply(d_xn, i);
+                launch_axpy(m, 1.0, d_xn, d_x, st_);
+                CK(cudaStreamSynchronize(st_));  // y goes out of scope
+                if (stop) {
+                    done = true;
+                    break;
+                }
+                k = 0;
+                start_cycle();
+                std::fill(R.begin(), R.end(), 0.0);
+                std::fill(w.begin(), w.end(), 0.0);
+                w[0] = first_reflector();
+            }
+        }
+        result = iters;
+    } while (false);
+    CK(cudaMemcpyAsync(x, d_x, sizeof(double) * m, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    if (seconds) *seconds = wtime() - t0;
+    cudaFree(d_rp);
+    cudaFree(d_ci);
+    cudaFree(d_v);
+    for (auto v : vecs) cudaFree(*v);
+    cudaFree(d_H);
+    cudaFree(d_tau);
+    cudaFree(d_beta);
+    cudaFree(d_part);
     return result;
 }
 

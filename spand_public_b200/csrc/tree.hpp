@@ -105,6 +105,9 @@ class Tree {
     void solve(double* x_host);       // in place, host vector of length N
     void solve_device(double* x_dev); // in place, device vector of length N (natural ordering)
     int cg(const SpMat& A, const double* rhs, double* x, int iters, double tol, bool verb, double* seconds);
+    // src/is.cpp:123-300 (Householder GMRES, left preconditioned by this tree); same return value as the reference
+    int gmres(const SpMat& A, const double* rhs, double* x, int iters, int restart, double tol, bool verb,
+              double* seconds);
     long long nnz();
     int get_stop() const;
     SpMat trailing_mat();

@@ -39,6 +39,7 @@ def _load():
     lib.orc_factorize.argtypes = [_p]
     lib.orc_solve.argtypes = [_p, _dp]
     lib.orc_cg.argtypes = [_p, _i, _ip, _ip, _dp, _dp, _dp, _i, _d, _i]
+    lib.orc_gmres.argtypes = [_p, _i, _ip, _ip, _dp, _dp, _dp, _i, _i, _d, _i]
     lib.orc_nnz.restype = C.c_longlong
     lib.orc_nnz.argtypes = [_p]
     lib.orc_get_stop.argtypes = [_p]
@@ -143,6 +144,16 @@ class OracleTree:
         N, cp, ri, v = _csc(A)
         x = np.zeros(N)
         it = self._l.orc_cg(self._h, N, cp, ri, v, np.ascontiguousarray(b, dtype=np.float64), x, iters, tol, int(verb))
+        if it < 0:
+            raise RuntimeError(self._l.orc_last_error(self._h).decode())
+        return it, x
+
+    def gmres(self, A, b, iters=100, restart=100, tol=1e-12, verb=False):
+        """src/is.cpp:123-300; x0 = 0, returns (iterations, x)."""
+        N, cp, ri, v = _csc(A)
+        x = np.zeros(N)
+        it = self._l.orc_gmres(self._h, N, cp, ri, v, np.ascontiguousarray(b, dtype=np.float64), x, iters, restart,
+                               tol, int(verb))
         if it < 0:
             raise RuntimeError(self._l.orc_last_error(self._h).decode())
         return it, x

@@ -448,3 +448,66 @@ def test_plu_singular_pivot_raises():
     g.assemble(A)
     with pytest.raises(RuntimeError, match="Singular Pivot"):
         g.factorize()
+
+
+# ---- GMRES (src/is.cpp:123-300) on the GPU vs the oracle's restatement ----
+@pytest.mark.parametrize("n,d,L,tol,restart", [(32, 2, 5, 1e-2, 100), (16, 3, 5, 1e-2, 3), (20, 2, 4, 0.0, 100)])
+def test_gmres_spd_matches_oracle(n, d, L, tol, restart):
+    """Iteration count within +-1 of the oracle and the same solution (SPD matrix, LLT preconditioner)."""
+    A, g, o = _pair(n, d, L, tol)
+    g.assemble(A)
+    o.assemble(A)
+    g.factorize()
+    o.factorize()
+    b = S.random(A.shape[0], 2019)
+    itg, xg = g.gmres(A, b, 100, restart, 1e-12)
+    ito, xo = o.gmres(A, b, 100, restart, 1e-12)
+    assert abs(itg - ito) <= 1, (itg, ito)
+    assert np.linalg.norm(A @ xg - b) / np.linalg.norm(b) <= 1e-10
+    assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) <= 1e-8
+
+
+@pytest.mark.parametrize("n,L,tol,restart", [(12, 5, 1e-2, 100), (16, 6, 1e-2, 4)])
+def test_gmres_c5_family_matches_oracle(n, L, tol, restart):
+    """Config C5's matrix family (anisotropic convection-diffusion, non-symmetric), GEN + PLU, GMRES(restart)."""
+    A = S.aniso_convdiff(n)
+    X = S.linspace_nd(n, 3)
+    g = S.Tree(L)
+    g.set_tol(tol)
+    g.set_symm_kind(S.GEN)
+    g.set_scaling_kind(S.PLU)
+    g.set_use_geo(True)
+    g.set_Xcoo(X)
+    o = O.OracleTree(L, tol=tol, symm_kind=O.GEN, scaling_kind=O.PLU)
+    o.set_coords(X)
+    G = S.symmetric_graph(A)
+    g.partition(G)
+    o.partition(G)
+    g.assemble(A)
+    o.assemble(A)
+    g.factorize()
+    o.factorize()
+    b = S.random(A.shape[0], 2019)
+    itg, xg = g.gmres(A, b, 200, restart, 1e-12)
+    ito, xo = o.gmres(A, b, 200, restart, 1e-12)
+    assert abs(itg - ito) <= 1, (itg, ito)
+    rg = np.linalg.norm(A @ xg - b) / np.linalg.norm(b)
+    ro = np.linalg.norm(A @ xo - b) / np.linalg.norm(b)
+    assert rg <= max(10 * ro, 1e-9), (rg, ro)
+
+
+def test_gmres_edge_cases():
+    """Zero right-hand side returns x = 0 (is.cpp:137-141); iteration cap is honoured (is.cpp:231)."""
+    A, g, o = _pair(16, 2, 4, 1e-1)
+    g.assemble(A)
+    o.assemble(A)
+    g.factorize()
+    o.factorize()
+    N = A.shape[0]
+    it, x = g.gmres(A, np.zeros(N), 10, 5, 1e-12, x0=np.ones(N))
+    assert it == 1 and not x.any()
+    b = S.random(N, 2019)
+    itg, xg = g.gmres(A, b, 3, 100, 1e-14)
+    ito, xo = o.gmres(A, b, 3, 100, 1e-14)
+    assert itg == ito == 3
+    assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) <= 1e-8
