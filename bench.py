@@ -364,6 +364,10 @@ def main():
                 "unit": "GB/s", "peak_source": hbm_src}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
     roof["traffic"] = None
+    try:  # DRAM bytes of the captured launches (ncu --set full, committed under profiles/); per launch, not averaged
+        roof["traffic_captured"] = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
     roof["launches"] = int(fam[dom][1])
     roof["avg_launch_ms"] = fam[dom][0] / max(1, fam[dom][1])
     roof["family_kernel_seconds"] = fam_s
@@ -377,6 +381,20 @@ def main():
     roof["gemm_family"] = {"bound": "tensor", "achieved": gemm_fl / max(fam_s["gemm"], 1e-9) / 1e12,
                            "peak": fp64_peak, "unit": "TFLOP/s",
                            "frac": (gemm_fl / max(fam_s["gemm"], 1e-9) / 1e12 / fp64_peak) if fp64_peak else None}
+    # every family against its own bound (algorithmic work of SURVEY.md 8(d) / kernel time of the family)
+    roof["families"] = {
+        "rrqr": {"bound": "hbm", "achieved_gbs": float(by["rrqr"]) / max(fam_s["rrqr"], 1e-9) / 1e9,
+                 "frac": float(by["rrqr"]) / max(fam_s["rrqr"], 1e-9) / 1e9 / hbm_peak},
+        "trsm": {"bound": "hbm", "achieved_gbs": float(by["trsm"]) / max(fam_s["trsm"], 1e-9) / 1e9,
+                 "frac": float(by["trsm"]) / max(fam_s["trsm"], 1e-9) / 1e9 / hbm_peak,
+                 "tflops": float(lg["fl_panel"].sum()) / max(fam_s["trsm"], 1e-9) / 1e12},
+        "copy": {"bound": "hbm", "achieved_gbs": float(by["copy"]) / max(fam_s["copy"], 1e-9) / 1e9,
+                 "frac": float(by["copy"]) / max(fam_s["copy"], 1e-9) / 1e9 / hbm_peak},
+        "gemm": {"bound": "tensor", "achieved_tflops": gemm_fl / max(fam_s["gemm"], 1e-9) / 1e12,
+                 "frac": (gemm_fl / max(fam_s["gemm"], 1e-9) / 1e12 / fp64_peak) if fp64_peak else None},
+        "potrf": {"bound": "tensor", "achieved_tflops": float(lg["fl_pivot"].sum()) / max(fam_s["potrf"], 1e-9) / 1e12,
+                  "frac": (float(lg["fl_pivot"].sum()) / max(fam_s["potrf"], 1e-9) / 1e12 / fp64_peak) if fp64_peak else None},
+    }
     phases = {"eliminate": lg["t_elim"].sum(), "scale": lg["t_scale"].sum(), "sparsify": lg["t_spars"].sum(),
               "merge": lg["t_merge"].sum()}
     roof["phase_seconds"] = {k: float(v) for k, v in phases.items()}

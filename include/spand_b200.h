@@ -71,6 +71,9 @@ int spand_cg(spand_tree* t, int N, const int* colptr, const int* rowind, const d
 int spand_gmres(spand_tree* t, int N, const int* colptr, const int* rowind, const double* val, const double* rhs,
                 double* x, int iters, int restart, double tol, int verb, double* seconds);
 
+/* profiling aid: per-phase clock64 cycles of the RRQR kernel, non-zero only in -DSPAND_RRQR_TIMING builds */
+void spand_debug_rrqr_phases(unsigned long long* out48, int reset);
+
 /* Tree::nnz / get_stop / get_nlevels                include/tree.h:158-160 */
 long long spand_nnz(spand_tree* t);
 int spand_get_stop(spand_tree* t);

@@ -530,6 +530,31 @@ void OTree::sparsify_cluster(OCluster* self) {
     std::vector<double> diag(mn);
     for (int i = 0; i < mn; i++) diag[i] = Asn(i, i);
     int rank = choose_rank(diag.data(), mn, tol);
+    if (getenv("SPAND_ORACLE_DEADCOLS") && rank > 0) {
+        // analysis hook (not part of the restatement): how much of the per-step panel sweep of a truncated QRCP
+        // touches columns whose residual norm is already below the stopping threshold (they can never be pivots)
+        const double margin = atof(getenv("SPAND_ORACLE_DEADCOLS"));
+        const double thr2 = margin * tol * diag[0] * margin * tol * diag[0];
+        std::vector<double> res2(cols, 0.0);  // residual norm^2 of column p below row k, built bottom-up
+        std::vector<std::vector<double>> tail(cols);
+        double all = 0, live = 0, live_blk = 0;
+        for (int p = 0; p < cols; p++) {
+            tail[p].assign(mn + 1, 0.0);
+            for (int k = std::min(mn, p + 1) - 1; k >= 0; k--) tail[p][k] = tail[p][k + 1] + Asn(k, p) * Asn(k, p);
+        }
+        for (int k = 0; k < rank; k++) {
+            const int kb = k - k % 16;  // liveness refreshed at block boundaries only
+            for (int p = k + 1; p < cols; p++) {
+                all += rows - k;
+                if (tail[p][std::min(k, mn)] >= thr2) live += rows - k;
+                if (tail[p][std::min(kb, mn)] >= thr2) live_blk += rows - k;
+            }
+        }
+        static double g_all[64], g_live[64], g_blk[64];
+        g_all[ilvl] += all; g_live[ilvl] += live; g_blk[ilvl] += live_blk;
+        fprintf(stderr, "DEADCOLS lvl %d rows %d cols %d rank %d live %.3f live_blk %.3f | level so far %.3f %.3f (%.3g)\n", ilvl, rows, cols,
+                rank, all > 0 ? live / all : 1.0, all > 0 ? live_blk / all : 1.0, g_live[ilvl] / g_all[ilvl], g_blk[ilvl] / g_all[ilvl], g_all[ilvl]);
+    }
     {
         double r = rows, cc = cols, rf = mn, rk = rank;
         lg.fl_rrqr_full += 4 * r * cc * rf - 2 * (r + cc) * rf * rf + (4.0 / 3.0) * rf * rf * rf;

@@ -12,7 +12,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libspand_b200.so")
+# SPAND_B200_BUILD selects an alternative build directory (kernel tuning experiments: scripts/rrqr_tune.py)
+LIB_PATH = os.path.join(_HERE, os.environ.get("SPAND_B200_BUILD", "_build"), "libspand_b200.so")
 
 SPD, SYM, GEN = 0, 1, 2
 LLT, PLU = 0, 3
@@ -26,7 +27,7 @@ EXPORTS = [
     "spand_create", "spand_destroy", "spand_last_error", "spand_set_tol", "spand_set_skip", "spand_set_symm_kind",
     "spand_set_scaling_kind", "spand_set_use_geo", "spand_set_verb", "spand_set_use_sparsify", "spand_set_device",
     "spand_set_coords", "spand_set_stop", "spand_partition", "spand_get_partition", "spand_get_perm", "spand_get_N",
-    "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_gmres", "spand_nnz", "spand_get_stop",
+    "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_gmres", "spand_debug_rrqr_phases", "spand_nnz", "spand_get_stop",
     "spand_get_nlevels", "spand_num_clusters", "spand_get_stats", "spand_log_fields", "spand_log_field_name",
     "spand_get_log", "spand_factorize_seconds", "spand_analyze_seconds", "spand_plan_analyze", "spand_plan_live_edges",
     "spand_plan_counts", "spand_get_cluster_layout", "spand_mg_setup", "spand_mg_get_handle", "spand_mg_set_peers",

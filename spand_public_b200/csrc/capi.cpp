@@ -119,6 +119,7 @@ int spand_gmres(spand_tree* t, int N, const int* colptr, const int* rowind, cons
     });
     return rc == 0 ? it : -1;
 }
+void spand_debug_rrqr_phases(unsigned long long* out48, int reset) { spand::rrqr_phase_cycles(out48, reset != 0); }
 long long spand_nnz(spand_tree* t) { return t->t.nnz(); }
 int spand_get_stop(spand_tree* t) { return t->t.get_stop(); }
 int spand_get_nlevels(spand_tree* t) { return t->t.nlevels; }

@@ -52,11 +52,49 @@ SpMat from_triplets(int rows, int cols, const std::vector<Triplet>& t) {
 }
 
 SpMat from_csc(int n, const int* colptr, const int* rowind, const double* val) {
+    // canonical input (rows strictly increasing inside every column, the normal case): plain copies
+    bool canonical = colptr[0] == 0;
+    for (int j = 0; j < n && canonical; j++) {
+        canonical = colptr[j + 1] >= colptr[j];
+        for (int k = colptr[j] + 1; k < colptr[j + 1] && canonical; k++) canonical = rowind[k] > rowind[k - 1];
+        if (canonical && colptr[j + 1] > colptr[j])
+            canonical = rowind[colptr[j]] >= 0 && rowind[colptr[j + 1] - 1] < n;
+    }
+    if (canonical) {
+        SpMat A;
+        A.rows = A.cols = n;
+        const size_t nnz = (size_t)colptr[n];
+        A.colptr.assign(colptr, colptr + n + 1);
+        A.rowind.assign(rowind, rowind + nnz);
+        if (val) A.val.assign(val, val + nnz);
+        else A.val.assign(nnz, 1.0);
+        return A;
+    }
     std::vector<Triplet> t;
     t.reserve(colptr[n]);
     for (int j = 0; j < n; j++)
         for (int k = colptr[j]; k < colptr[j + 1]; k++) t.push_back({rowind[k], j, val ? val[k] : 1.0});
     return from_triplets(n, n, t);
+}
+
+SpMat transpose(const SpMat& A) {
+    SpMat T;
+    T.rows = A.cols;
+    T.cols = A.rows;
+    const size_t nnz = A.rowind.size();
+    T.colptr.assign(A.rows + 1, 0);
+    for (size_t k = 0; k < nnz; k++) T.colptr[A.rowind[k] + 1]++;
+    for (int i = 0; i < A.rows; i++) T.colptr[i + 1] += T.colptr[i];
+    std::vector<int> pos(T.colptr.begin(), T.colptr.end() - 1);
+    T.rowind.resize(nnz);
+    T.val.resize(nnz);
+    for (int j = 0; j < A.cols; j++)
+        for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) {
+            const int p = pos[A.rowind[k]]++;
+            T.rowind[p] = j;
+            T.val[p] = A.val[k];
+        }
+    return T;
 }
 
 SpMat symmetric_graph(const SpMat& A) {

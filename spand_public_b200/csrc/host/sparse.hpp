@@ -45,6 +45,8 @@ SpMat from_triplets(int rows, int cols, const std::vector<Triplet>& t);
 SpMat from_csc(int n, const int* colptr, const int* rowind, const double* val);
 
 // |A| + |A^T| + I
+// A^T by one counting pass (rows of every column come out sorted)
+SpMat transpose(const SpMat& A);
 SpMat symmetric_graph(const SpMat& A);
 // A[p,p]: entry (i,j) goes to (pinv[i], pinv[j])
 SpMat symm_perm(const SpMat& A, const std::vector<int>& p);

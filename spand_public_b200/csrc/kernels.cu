@@ -627,10 +627,10 @@ constexpr int SV_B = 32;
 
 // trans == 0: x <- T^-1 x with T lower (forward) ; trans == 1: x <- T^-T x with T lower (backward)
 // trans == 2: x <- T^-1 x with T upper (backward substitution, PLU's U)
-__global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__ tasks, int trans) {
+__global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__ tasks, int trans, int skip_small) {
     TrsvTask t = tasks[blockIdx.x];
     int n = t.n;
-    if (n == 0) return;
+    if (n == 0 || (skip_small && n <= 32)) return;  // n <= 32: trsv_small_kernel
     int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double xb[SV_B];
     const double* T = t.T;
@@ -718,6 +718,153 @@ __global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__
             }
             __syncthreads();
         }
+    }
+}
+
+// Triangles of at most 32 rows (the bulk of the low levels): one warp per task, the triangle preloaded into
+// registers (lane i holds row i, or column i for the transposed solve) so that the substitution chain contains no
+// memory access. Same operation order as trsv_kernel's single-block case.
+__global__ void __launch_bounds__(128) trsv_small_kernel(const TrsvTask* __restrict__ tasks, int nt, int trans) {
+    const int ti = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ti >= nt) return;
+    const TrsvTask t = tasks[ti];
+    const int n = t.n, lane = threadIdx.x & 31;
+    if (n == 0 || n > 32) return;
+    const double* T = t.T;
+    double tr[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        double v = 0.0;
+        if (lane < n && j < n) v = (trans == 1) ? T[j + (size_t)lane * t.ld] : T[lane + (size_t)j * t.ld];
+        tr[j] = v;
+    }
+    double xi = 0.0;
+    if (lane < n) xi = (trans == 0 && t.perm != nullptr) ? t.x[t.perm[lane]] : t.x[lane];
+    double dg = 1.0;  // diagonal entry of the own row
+#pragma unroll
+    for (int j = 0; j < 32; j++)
+        if (lane == j) dg = tr[j];
+    if (trans == 2 && t.diag != nullptr && lane < n) dg = t.diag[lane];
+    __syncwarp();
+    if (trans == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (j < n) {
+                const double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                if (lane == j) xi = xj;
+                if (lane > j) xi -= tr[j] * xj;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 31; j >= 0; j--) {
+            if (j < n) {
+                const double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                if (lane == j) xi = xj;
+                if (lane < j) xi -= tr[j] * xj;
+            }
+        }
+    }
+    if (lane < n) t.x[lane] = xi;
+}
+
+// Large operands (top levels: few tasks, hundreds of rows and columns each): the rows (forward) / columns
+// (transposed) of a task are spread over blockIdx.y, and inside a CTA the inner dimension is split over the 8 warps
+// with several independent loads in flight per lane; partial sums are combined in a fixed order (deterministic).
+constexpr int GV_T = 256;
+__global__ void __launch_bounds__(GV_T) gemv_n_big_kernel(const GemvTask* __restrict__ tasks,
+                                                         const GemvContrib* __restrict__ contribs) {
+    const GemvTask t = tasks[blockIdx.x];
+    const int r0 = blockIdx.y * 64;
+    if (r0 >= t.m) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double part[GV_T / 32][64];
+    const int i0 = r0 + lane, i1 = r0 + 32 + lane;
+    const bool v0 = i0 < t.m, v1 = i1 < t.m;
+    const int j0 = v0 ? i0 : r0, j1 = v1 ? i1 : r0;  // clamped row indices: loads stay in range, results are masked
+    double s0 = 0.0, s1 = 0.0;
+    for (int ci = 0; ci < t.nc; ci++) {
+        const GemvContrib c = contribs[t.c0 + ci];
+        int p = warp;
+        for (; p + 24 < c.k; p += 32) {
+            double a0[4], a1[4], xv[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double* col = c.A + (size_t)(p + 8 * q) * c.lda;
+                a0[q] = col[j0];
+                a1[q] = col[j1];
+                xv[q] = c.x[p + 8 * q];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                s0 = fma(a0[q], xv[q], s0);
+                s1 = fma(a1[q], xv[q], s1);
+            }
+        }
+        for (; p < c.k; p += 8) {
+            const double* col = c.A + (size_t)p * c.lda;
+            const double xv = c.x[p];
+            s0 = fma(col[j0], xv, s0);
+            s1 = fma(col[j1], xv, s1);
+        }
+    }
+    part[warp][lane] = s0;
+    part[warp][lane + 32] = s1;
+    __syncthreads();
+    if (tid < 64 && r0 + tid < t.m) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < GV_T / 32; w++) s += part[w][tid];
+        t.y[r0 + tid] -= s;
+    }
+}
+
+__global__ void __launch_bounds__(GV_T) gemv_t_big_kernel(const GemvTask* __restrict__ tasks,
+                                                         const GemvContrib* __restrict__ contribs) {
+    const GemvTask t = tasks[blockIdx.x];
+    const int c0 = blockIdx.y * 32;
+    if (c0 >= t.m) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int jb = c0 + warp * 4;  // this warp's four output columns
+    if (jb >= t.m) return;
+    int jj[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) jj[q] = min(jb + q, t.m - 1);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int ci = 0; ci < t.nc; ci++) {
+        const GemvContrib c = contribs[t.c0 + ci];
+        const double* a[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) a[q] = c.A + (size_t)jj[q] * c.lda;
+        int i = lane;
+        for (; i + 32 < c.k; i += 64) {
+            const double x0 = c.x[i], x1 = c.x[i + 32];
+            double b0[4], b1[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                b0[q] = a[q][i];
+                b1[q] = a[q][i + 32];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                s[q] = fma(b0[q], x0, s[q]);
+                s[q] = fma(b1[q], x1, s[q]);
+            }
+        }
+        if (i < c.k) {
+            const double x0 = c.x[i];
+#pragma unroll
+            for (int q = 0; q < 4; q++) s[q] = fma(a[q][i], x0, s[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) s[q] = warp_sum(s[q]);
+    if (lane < 4 && jb + lane < t.m) {
+        double v = s[0];
+        if (lane == 1) v = s[1];
+        if (lane == 2) v = s[2];
+        if (lane == 3) v = s[3];
+        t.y[jb + lane] -= v;
     }
 }
 
@@ -1295,11 +1442,21 @@ void launch_copy(const CopyTask* t, int nt, cudaStream_t st) {
     if (nt > 0) copy_kernel<<<(nt + 3) / 4, 128, 0, st>>>(t, nt);
 }
 
-void launch_trsv(const TrsvTask* t, int nt, int trans, cudaStream_t st) {
-    if (nt > 0) trsv_kernel<<<nt, SV_T, 0, st>>>(t, trans);
+void launch_trsv(const TrsvTask* t, int nt, int trans, int max_n, cudaStream_t st) {
+    if (nt <= 0) return;
+    // triangles of at most 32 rows: one warp each; the CTA kernel takes the rest (and is skipped when there is none)
+    trsv_small_kernel<<<(nt + 3) / 4, 128, 0, st>>>(t, nt, trans);
+    if (max_n > 32) trsv_kernel<<<nt, SV_T, 0, st>>>(t, trans, 1);
 }
-void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, cudaStream_t st) {
-    if (nt > 0) gemv_kernel<<<nt, SV_T, 0, st>>>(t, c, trans);
+void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, int max_m, cudaStream_t st) {
+    if (nt <= 0) return;
+    if (max_m <= 64) {
+        gemv_kernel<<<nt, SV_T, 0, st>>>(t, c, trans);
+    } else if (trans == 0) {
+        gemv_n_big_kernel<<<dim3(nt, (max_m + 63) / 64), GV_T, 0, st>>>(t, c);
+    } else {
+        gemv_t_big_kernel<<<dim3(nt, (max_m + 31) / 32), GV_T, 0, st>>>(t, c);
+    }
 }
 void launch_house(const HouseTask* t, int nt, int trans, cudaStream_t st) {
     if (nt > 0) house_kernel<<<nt, SV_T, 0, st>>>(t, trans);

@@ -171,10 +171,13 @@ void launch_gemm_small(const GemmTask* t, int nt, const GemmContrib* c, cudaStre
 void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int nthreads, bool in_smem,
                  int smem, cudaStream_t st);
 int rrqr_max_smem();
+// debug builds (-DSPAND_RRQR_TIMING): accumulated clock64 cycles per kernel phase, [10] = CTAs counted
+void rrqr_phase_cycles(unsigned long long* out48, bool reset);
 size_t rrqr_smem_bytes(int rows, int maxcols, int G, int nb, int ld, bool in_smem);
 void launch_copy(const CopyTask* t, int nt, cudaStream_t st);
-void launch_trsv(const TrsvTask* t, int nt, int trans, cudaStream_t st);
-void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, cudaStream_t st);
+// max_n / max_m: upper bound of the task sizes of the launch (selects the kernel shapes and the grid)
+void launch_trsv(const TrsvTask* t, int nt, int trans, int max_n, cudaStream_t st);
+void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, int max_m, cudaStream_t st);
 void launch_house(const HouseTask* t, int nt, int trans, cudaStream_t st);
 void launch_xcopy(const XCopyTask* t, int nt, cudaStream_t st);
 void launch_fill(double* p, size_t n, double v, cudaStream_t st);

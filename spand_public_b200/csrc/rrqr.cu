@@ -27,12 +27,40 @@
 
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
 namespace cg = cooperative_groups;
 
+// CTAs per SM the streaming shape (256 threads, panel in global memory) is compiled for: 4 -> 64 registers per thread
+#ifndef SPAND_STREAM_MINB
+#define SPAND_STREAM_MINB 4
+#endif
+
 namespace spand {
+
+// Phase timers of the RRQR kernel (debug builds with -DSPAND_RRQR_TIMING only: scripts/rrqr_phases.py). Thread 0 of
+// every CTA accumulates clock64() deltas per phase and adds them to this table when the CTA retires.
+__device__ unsigned long long g_qr_phase[48];  // [shape class: smem panel / streaming 256 / global 512][16]
+#ifdef SPAND_RRQR_TIMING
+#define QT_DECL unsigned long long qt_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long qt_t = clock64();
+#define QT(i)                                \
+    if (tid == 0) {                          \
+        const long long qt_n = clock64();    \
+        qt_acc[i] += (unsigned long long)(qt_n - qt_t); \
+        qt_t = qt_n;                         \
+    }
+#define QT_FLUSH                                                         \
+    if (tid == 0) {                                                      \
+        for (int qi = 0; qi < 10; qi++) atomicAdd(&g_qr_phase[QT_CLASS * 16 + qi], qt_acc[qi]); \
+        atomicAdd(&g_qr_phase[QT_CLASS * 16 + 10], 1ull);                                \
+    }
+#else
+#define QT_DECL
+#define QT(i)
+#define QT_FLUSH
+#endif
 
 namespace {
 
@@ -94,6 +122,9 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
     const QrSrc* src = srcs + t.src0;
     const int rows = t.rows;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    QT_DECL
+    constexpr int QT_CLASS = SMEM_PANEL ? 0 : (NT == 256 ? 1 : 2);
+    (void)QT_CLASS;
 
     __shared__ double red[2][NW];
     __shared__ double alpha_s[2];
@@ -261,6 +292,7 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
         propose(lb, 0, 0);
     }
     csync();
+    QT(0)  // gather + initial norms + first proposal
 
     int rank = mn;
     int k0 = 0, nb = min(t.nb, mn);
@@ -304,6 +336,7 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
             }
         }
         __syncthreads();
+        QT(1)  // winner selection + reflector pull
         // ---- aux = V(k:, 0:j)^T v ----
         if (j > 0) {
             for (int tt = warp; tt < j; tt += NW) {
@@ -315,6 +348,7 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
             }
             __syncthreads();
         }
+        QT(2)  // aux = V^T v
         // ---- F(:, j), row k of the panel, partial norms, local candidate for step k + 1 ----
         Cand best{-1.0, INT_MAX, -1};
         const double2* v2 = reinterpret_cast<const double2*>(vj);
@@ -346,24 +380,30 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
                 if (!my_act) my_cl = 0;
                 if (__ballot_sync(FULL, my_act) == 0) continue;
                 double s[WB];
-                int coff[WB];
                 const int nhere = min(WB, ncl - first);
-#pragma unroll
-                for (int c = 0; c < WB; c++) {
-                    s[c] = 0.0;
-                    coff[c] = min(c, nhere - 1) * ld2;  // clamp: columns past the slab re-read the last one
-                }
-                const double2* cb = reinterpret_cast<const double2*>(P) + (size_t)first * ld2;
                 int i2 = (k >> 1) + lane;
-                if constexpr (MINB == 1) {
-                    for (; i2 + 32 < npair; i2 += 64) {
-                        const double2 v0 = v2[i2], v1 = v2[i2 + 32];
+                if constexpr (MINB != 4) {
+                    // 128- / 80-register shapes: one pointer per column advanced by a constant (no per-load index
+                    // arithmetic), two row chunks = 2 WB loads of 16 bytes in flight per lane.
+                    // Columns past the slab re-read the last one.
+                    const double2* pc[WB];
+#pragma unroll
+                    for (int c = 0; c < WB; c++) {
+                        s[c] = 0.0;
+                        pc[c] = reinterpret_cast<const double2*>(P) + ((size_t)(first + min(c, nhere - 1)) * ld2 + i2);
+                    }
+                    const double2* vp = v2 + i2;
+                    int rem = npair - i2;  // row pairs left for this lane (stride 32)
+                    for (; rem > 32; rem -= 64) {
+                        const double2 v0 = vp[0], v1 = vp[32];
                         double2 a0[WB], a1[WB];
 #pragma unroll
                         for (int c = 0; c < WB; c++) {
-                            a0[c] = cb[coff[c] + i2];
-                            a1[c] = cb[coff[c] + i2 + 32];
+                            a0[c] = pc[c][0];
+                            a1[c] = pc[c][32];
+                            pc[c] += 64;
                         }
+                        vp += 64;
 #pragma unroll
                         for (int c = 0; c < WB; c++) {
                             s[c] = fma(a0[c].x, v0.x, s[c]);
@@ -372,16 +412,37 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
                             s[c] = fma(a1[c].y, v1.y, s[c]);
                         }
                     }
-                }
-                for (; i2 < npair; i2 += 32) {
-                    const double2 vv = v2[i2];
-                    double2 a0[WB];
+                    if (rem > 0) {
+                        const double2 vv = vp[0];
+                        double2 a0[WB];
 #pragma unroll
-                    for (int c = 0; c < WB; c++) a0[c] = cb[coff[c] + i2];
+                        for (int c = 0; c < WB; c++) a0[c] = pc[c][0];
+#pragma unroll
+                        for (int c = 0; c < WB; c++) {
+                            s[c] = fma(a0[c].x, vv.x, s[c]);
+                            s[c] = fma(a0[c].y, vv.y, s[c]);
+                        }
+                    }
+                } else {
+                    // 64-register shape: 32-bit column offsets from one base keep the four loads of a row chunk
+                    // back to back (with per-column pointers the register allocator serialises them)
+                    int coff[WB];
 #pragma unroll
                     for (int c = 0; c < WB; c++) {
-                        s[c] = fma(a0[c].x, vv.x, s[c]);
-                        s[c] = fma(a0[c].y, vv.y, s[c]);
+                        s[c] = 0.0;
+                        coff[c] = min(c, nhere - 1) * ld2;
+                    }
+                    const double2* cb = reinterpret_cast<const double2*>(P) + (size_t)first * ld2;
+                    for (; i2 < npair; i2 += 32) {
+                        const double2 vv = v2[i2];
+                        double2 a0[WB];
+#pragma unroll
+                        for (int c = 0; c < WB; c++) a0[c] = cb[coff[c] + i2];
+#pragma unroll
+                        for (int c = 0; c < WB; c++) {
+                            s[c] = fma(a0[c].x, vv.x, s[c]);
+                            s[c] = fma(a0[c].y, vv.y, s[c]);
+                        }
                     }
                 }
                 int bit = 16;
@@ -543,11 +604,92 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
             }
         }
         if (k + 1 >= mn) break;  // factorization complete, rank = mn
+        QT(3)  // sweep (warp 0's share)
         Cand lb = block_best(best, par);  // contains a block barrier: F and row k are visible below
+        QT(4)  // block_best = waiting for the slowest warp of the sweep
         // ---- end of block: trailing rows of the own active columns  W -= V F^T ----
         int jn = j + 1;
         if (j == nb - 1) {
             const int kend = k + 1;
+            if constexpr (!SMEM_PANEL) {
+                // Panel in global memory: a warp updates TB columns at once, two rows per lane (16-byte accesses),
+                // all loads of a pass issued before the first FMA; V is read once per row pair for the TB columns.
+                // Row kend - 1 shares a pair with row kend when kend is odd: it is final and passes through
+                // unchanged (its V entries are masked).
+                constexpr int TB = (MINB == 1) ? 8 : 4;
+                const int ld2 = ld >> 1, ldv2 = ldv >> 1;
+                const int i2lo = kend >> 1;
+                const double2* Vs2 = reinterpret_cast<const double2*>(Vs);
+                for (int first = warp * TB; first < ncl; first += TB * NW) {
+                    bool act[TB];
+                    bool any = false;
+#pragma unroll
+                    for (int c = 0; c < TB; c++) {
+                        act[c] = first + c < ncl && pos[first + c] >= kend;
+                        any |= act[c];
+                    }
+                    if (!any) continue;
+                    const double* fb = Fs + (size_t)first * FLD;
+                    if constexpr (MINB != 4) {
+                        double2* pa[TB];
+#pragma unroll
+                        for (int c = 0; c < TB; c++)
+                            pa[c] = reinterpret_cast<double2*>(P) + ((size_t)(first + (act[c] ? c : 0)) * ld2 + i2lo + lane);
+                        const double2* vp = Vs2 + i2lo + lane;
+                        for (int i2 = i2lo + lane; i2 < npair; i2 += 32) {
+                            const bool keepx = 2 * i2 < kend;
+                            double2 a[TB];
+#pragma unroll
+                            for (int c = 0; c < TB; c++)
+                                if (act[c]) a[c] = pa[c][0];
+#pragma unroll
+                            for (int tt = 0; tt < QNB; tt++)
+                                if (tt < nb) {
+                                    double2 v = vp[(size_t)tt * ldv2];
+                                    if (keepx) v.x = 0.0;
+#pragma unroll
+                                    for (int c = 0; c < TB; c++)
+                                        if (act[c]) {
+                                            const double f = fb[c * FLD + tt];
+                                            a[c].x = fma(-v.x, f, a[c].x);
+                                            a[c].y = fma(-v.y, f, a[c].y);
+                                        }
+                                }
+#pragma unroll
+                            for (int c = 0; c < TB; c++) {
+                                if (act[c]) pa[c][0] = a[c];
+                                pa[c] += 32;
+                            }
+                            vp += 32;
+                        }
+                    } else {
+                        double2* cb = reinterpret_cast<double2*>(P) + (size_t)first * ld2;
+                        for (int i2 = i2lo + lane; i2 < npair; i2 += 32) {
+                            const bool keepx = 2 * i2 < kend;
+                            double2 a[TB];
+#pragma unroll
+                            for (int c = 0; c < TB; c++)
+                                if (act[c]) a[c] = cb[(size_t)c * ld2 + i2];
+#pragma unroll
+                            for (int tt = 0; tt < QNB; tt++)
+                                if (tt < nb) {
+                                    double2 v = Vs2[i2 + (size_t)tt * ldv2];
+                                    if (keepx) v.x = 0.0;
+#pragma unroll
+                                    for (int c = 0; c < TB; c++)
+                                        if (act[c]) {
+                                            const double f = fb[c * FLD + tt];
+                                            a[c].x = fma(-v.x, f, a[c].x);
+                                            a[c].y = fma(-v.y, f, a[c].y);
+                                        }
+                                }
+#pragma unroll
+                            for (int c = 0; c < TB; c++)
+                                if (act[c]) cb[(size_t)c * ld2 + i2] = a[c];
+                        }
+                    }
+                }
+            } else
             for (int base = 0; base < ncl; base += ngroups) {
                 const int cl = base + grp;
                 if (cl >= ncl || pos[cl] < kend) continue;
@@ -568,13 +710,19 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
             jn = 0;
             __syncthreads();
         }
+        QT(5)  // end-of-block trailing update
         propose(lb, k + 1, jn);
+        QT(6)  // speculative reflector + record broadcast
         csync();
+        QT(7)  // cluster barrier
     }
     // All CTAs leave the loop at the same step. One more barrier so that no CTA exits (or starts scattering over
     // its panel) while a sibling may still be pulling from its slots.
     csync();
-    if (rank >= rows) return;  // nothing to do (tree.cpp:1317-1319); csize unchanged
+    if (rank >= rows) {  // nothing to do (tree.cpp:1317-1319); csize unchanged
+        QT_FLUSH
+        return;
+    }
 
     // ---- scatter triu(R[:rank,:]) P^T back into the own columns of the edge blocks, in place ----
     {
@@ -606,6 +754,8 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
         }
     }
     if (crank == 0 && tid == 0) csize[t.cluster] = rank;
+    QT(8)  // scatter
+    QT_FLUSH
 }
 
 template <int G, int NT, bool SP, int QNB = QR_NB, int MINB = (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))>
@@ -636,6 +786,14 @@ void launch_one(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol,
 
 int rrqr_max_smem() { return 224 * 1024; }
 
+void rrqr_phase_cycles(unsigned long long* out48, bool reset) {
+    cudaMemcpyFromSymbol(out48, g_qr_phase, sizeof(unsigned long long) * 48);
+    if (reset) {
+        unsigned long long z[48] = {};
+        cudaMemcpyToSymbol(g_qr_phase, z, sizeof(z));
+    }
+}
+
 size_t rrqr_smem_bytes(int rows, int maxcols, int G, int nb, int ld, bool in_smem) {
     size_t cpcm = (size_t)(maxcols + G - 1) / G;
     size_t cpce = (cpcm + 3) & ~(size_t)3;
@@ -656,11 +814,11 @@ void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol
         }
         // streaming shape: panel in global memory, small CTAs, several per SM
         switch (G) {
-            case 1: launch_one<1, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
-            case 2: launch_one<2, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
-            case 4: launch_one<4, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
-            case 8: launch_one<8, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
-            default: launch_one<16, 256, false, QR_NBS, 4>(t, nt, s, csize, tol, smem, st); break;
+            case 1: launch_one<1, 256, false, QR_NBS, SPAND_STREAM_MINB>(t, nt, s, csize, tol, smem, st); break;
+            case 2: launch_one<2, 256, false, QR_NBS, SPAND_STREAM_MINB>(t, nt, s, csize, tol, smem, st); break;
+            case 4: launch_one<4, 256, false, QR_NBS, SPAND_STREAM_MINB>(t, nt, s, csize, tol, smem, st); break;
+            case 8: launch_one<8, 256, false, QR_NBS, SPAND_STREAM_MINB>(t, nt, s, csize, tol, smem, st); break;
+            default: launch_one<16, 256, false, QR_NBS, SPAND_STREAM_MINB>(t, nt, s, csize, tol, smem, st); break;
         }
         return;
     }

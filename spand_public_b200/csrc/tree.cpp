@@ -435,6 +435,14 @@ void Tree::assemble(const SpMat& A) {
     if (N == 0 || A.rows != N) throw std::runtime_error("assemble: call partition first with a matrix of the same size");
     ensure_device();
     CK(cudaStreamSynchronize(st_));
+    const bool timing = getenv("SPAND_TIMING") != nullptr;
+    double tm0 = wtime();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const double now = wtime();
+        fprintf(stderr, "[spand] assemble: %-28s %8.2f ms\n", what, (now - tm0) * 1e3);
+        tm0 = now;
+    };
     arena_->reset();
     scratch_->reset();
     stager_.reset();
@@ -453,9 +461,11 @@ void Tree::assemble(const SpMat& A) {
         l = fresh;
     }
     build_clusters();
+    lap("reset + build_clusters");
     const bool reuse = plan_valid_ && plan_ord_serial_ == ord_serial_ && plan_.symmetric == symmetry() &&
                        plan_.want_flag == use_want_sparsify && pat_colptr_ == A.colptr && pat_rowind_ == A.rowind;
     if (!reuse) analyze(A);
+    lap(reuse ? "pattern check (plan reused)" : "symbolic analysis");
 
     const int ncl = ord.norders;
     const size_t nedges = plan_.en1.size();
@@ -521,6 +531,7 @@ void Tree::assemble(const SpMat& A) {
         h_eptr_[e] = leaf_base[mg() ? h_owner_[plan_.en1[e]] : 0] + leaf_off_[e];
         h_eld_[e] = std::max(1, cl_[plan_.en2[e]].size);
     }
+    lap("host tables");
     stager_.upload(d_perm_, ord.perm.data(), sizeof(int) * N, st_);
     stager_.upload(d_csize_, h_csize_.data(), sizeof(int) * ncl, st_);
     stager_.upload(d_xptr_, h_xptr_.data(), sizeof(double*) * ncl, st_);
@@ -532,6 +543,7 @@ void Tree::assemble(const SpMat& A) {
     CK(cudaMemsetAsync(dblocks, 0, leaf_total_ * sizeof(double), st_));
     launch_scatter_values(d_val, d_valmap_, (size_t)A.nnz(), dblocks, st_);
     CK(cudaStreamSynchronize(st_));
+    lap("uploads + scatter kernel");
     stager_.reset();
     scratch_->reset();
     assembled_ = true;
@@ -919,6 +931,7 @@ void Tree::phase_eliminate(LevelLog& lg, SolveLevel& sl) {
         run_gemm(tasks, con, lg);
     }
     // recorded operations (tree.cpp:909-910, :885-892) as solve batches; sizes are captured now
+    sl.max_e = level_max_size();  // bounds every pivot / panel dimension of this level's recorded operations
     sl.n_e_trsv = (int)L.E.size();
     sl.e_trsv = arena_->alloc_n<TrsvTask>(L.E.size());
     launch_expand_trsv(tab_, D.E, D.e_piv, sl.n_e_trsv, sl.e_trsv, st_);
@@ -1070,6 +1083,7 @@ void Tree::phase_eliminate_plu(LevelLog& lg, SolveLevel& sl) {
     }
     // recorded operations: ScalingPLUQ, GemmOut (forward only), GemmIn (backward only)
     sl.e_trsv = to_device(trsv, arena_);
+    sl.max_e = level_max_size();
     sl.n_e_trsv = (int)trsv.size();
     sl.n_e_gemv_f = (int)L.e_gf.size();
     sl.e_gemv_f = arena_->alloc_n<GemvTask>(L.e_gf.size());
@@ -1109,6 +1123,7 @@ void Tree::phase_scale_plu(LevelLog& lg, SolveLevel& sl) {
     run_rowperm(rperm, lg);
     run_trsm(TRSM_LLN, left, lg);
     sl.s_trsv = to_device(trsv, arena_);
+    sl.max_s = level_max_size();
     sl.n_s_trsv = (int)trsv.size();
 }
 
@@ -1154,6 +1169,7 @@ void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
         run_trsm(TRSM_RLT, right, lg);
         run_trsm(TRSM_LLN, left, lg);
     }
+    sl.max_s = level_max_size();
     sl.n_s_trsv = (int)L.S.size();
     sl.s_trsv = arena_->alloc_n<TrsvTask>(L.S.size());
     launch_expand_trsv(tab_, D.S, D.s_piv, sl.n_s_trsv, sl.s_trsv, st_);
@@ -1233,9 +1249,11 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         const char* mode_env = getenv("SPAND_RRQR_MODE");  // "smem": cluster kernels with the panel in shared memory
         const bool smem_mode = mode_env != nullptr && std::string(mode_env) == "smem";
         const int stream_tmin = getenv("SPAND_RRQR_TMIN") ? atoi(getenv("SPAND_RRQR_TMIN")) : 48;
-        const int stream_ctas = getenv("SPAND_RRQR_CTAS") ? atoi(getenv("SPAND_RRQR_CTAS")) : 2368;
+        const int stream_ctas = getenv("SPAND_RRQR_CTAS") ? atoi(getenv("SPAND_RRQR_CTAS")) : 1776;
         const long smem1_max = (getenv("SPAND_RRQR_SMEM1KB") ? atol(getenv("SPAND_RRQR_SMEM1KB")) : 200) * 1024;
-        const double l2_budget = (getenv("SPAND_RRQR_L2MB") ? atof(getenv("SPAND_RRQR_L2MB")) : 128.0) * 1048576.0;
+        const double l2_budget = (getenv("SPAND_RRQR_L2MB") ? atof(getenv("SPAND_RRQR_L2MB")) : 1.0e5) * 1048576.0;
+        // panels smaller than this stay in (distributed) shared memory even in wide wavefronts
+        const double stream_min_bytes = (getenv("SPAND_RRQR_MINKB") ? atof(getenv("SPAND_RRQR_MINKB")) : 300.0) * 1024.0;
         for (size_t i = 0; i < nq; i++) {
             QrTask& t = tasks[i];
             int mn = std::max(1, std::min(t.rows, t.maxcols));
@@ -1265,6 +1283,7 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             }
             bool stream = !smem_mode && !force_global && force_g == 0 && per_color[task_color[i]] >= stream_tmin;
             if (stream && config(256, 1, true) <= smem1_max) stream = false;  // fits one CTA's shared memory
+            if (stream && 8.0 * t.rows * t.maxcols < stream_min_bytes) stream = false;
             if (stream) {
                 // Streaming shape: the panel lives in the scratch arena and is read once per Householder step by
                 // small CTAs (256 threads, 64 registers, several per SM); the cluster is as wide as needed for the
@@ -1738,10 +1757,10 @@ void Tree::solve_device(double* x_dev) {
     // (and panels) of other ranks through NVLink after a peer barrier.
     for (int l = 0; l < nlevels; l++) {
         SolveLevel& s = solve_[l];
-        launch_trsv(s.e_trsv, s.n_e_trsv, 0, st_);
+        launch_trsv(s.e_trsv, s.n_e_trsv, 0, s.max_e, st_);
         mg_barrier();
-        launch_gemv(s.e_gemv_f, s.n_e_gemv_f, s.e_gemv_fc, 0, st_);
-        launch_trsv(s.s_trsv, s.n_s_trsv, 0, st_);
+        launch_gemv(s.e_gemv_f, s.n_e_gemv_f, s.e_gemv_fc, 0, s.max_e, st_);
+        launch_trsv(s.s_trsv, s.n_s_trsv, 0, s.max_s, st_);
         launch_house(s.house, s.n_house, 1, st_);
         launch_xcopy(s.m_fwd, s.n_merge, st_);
     }
@@ -1751,10 +1770,10 @@ void Tree::solve_device(double* x_dev) {
         launch_house(s.house, s.n_house, 0, st_);
         // LLT: x <- L^-T x, x_s -= A[n,s]^T x_n ; PLU: x <- U^-1 x, x_s -= A[s,n] x_n   (operations.cpp bwd)
         const bool plu = scale_kind == PLU;
-        launch_trsv(s.s_trsv, s.n_s_trsv, plu ? 2 : 1, st_);
+        launch_trsv(s.s_trsv, s.n_s_trsv, plu ? 2 : 1, s.max_s, st_);
         mg_barrier();
-        launch_gemv(s.e_gemv_b, s.n_e_gemv_b, s.e_gemv_bc, plu ? 0 : 1, st_);
-        launch_trsv(s.e_trsv, s.n_e_trsv, plu ? 2 : 1, st_);
+        launch_gemv(s.e_gemv_b, s.n_e_gemv_b, s.e_gemv_bc, plu ? 0 : 1, s.max_e, st_);
+        launch_trsv(s.e_trsv, s.n_e_trsv, plu ? 2 : 1, s.max_e, st_);
     }
     if (!mg()) {
         launch_scatter(N, d_perm_, xleaf, x_dev, st_);  // x = P b
@@ -1777,12 +1796,7 @@ void Tree::solve(double* x_host) {
 int Tree::cg(const SpMat& A, const double* rhs, double* x, int iters, double tol_, bool verbose, double* seconds) {
     if (!factorized_) throw std::runtime_error("cg: call factorize first");
     int n = A.cols;
-    // CSR of A = CSC of A^T
-    std::vector<Triplet> tt;
-    tt.reserve(A.nnz());
-    for (int j = 0; j < n; j++)
-        for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) tt.push_back({j, A.rowind[k], A.val[k]});
-    SpMat At = from_triplets(n, n, tt);
+    SpMat At = transpose(A);  // CSR of A = CSC of A^T
     int *d_rp, *d_ci;
     double *d_v, *d_x, *d_r, *d_p, *d_z, *d_tmp, *d_b, *d_s, *d_part;
     CK(cudaMalloc((void**)&d_rp, sizeof(int) * (n + 1)));
@@ -1867,11 +1881,7 @@ int Tree::gmres(const SpMat& A, const double* rhs, double* x, int iters, int res
     const int m = A.cols;
     if (restart < 1) throw std::runtime_error("gmres: restart must be >= 1");
     if (restart > m) restart = m;
-    std::vector<Triplet> tt;
-    tt.reserve(A.nnz());
-    for (int j = 0; j < m; j++)
-        for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) tt.push_back({j, A.rowind[k], A.val[k]});
-    SpMat At = from_triplets(m, m, tt);  // CSR of A = CSC of A^T
+    SpMat At = transpose(A);  // CSR of A = CSC of A^T
     int *d_rp, *d_ci;
     double *d_v, *d_x, *d_b, *d_w, *d_t, *d_xn, *d_H, *d_tau, *d_beta, *d_part;
     CK(cudaMalloc((void**)&d_rp, sizeof(int) * (m + 1)));

@@ -152,6 +152,7 @@ class Tree {
         TrsvTask* s_trsv = nullptr; int n_s_trsv = 0;
         HouseTask* house = nullptr; int n_house = 0;
         XCopyTask* m_fwd = nullptr; XCopyTask* m_bwd = nullptr; int n_merge = 0;
+        int max_e = 0, max_s = 0;  // largest cluster at eliminate / scale time: sizes the solve launches
     };
     // device copies of the id arrays of one SymLevel (symbolic.hpp), resident in sym_arena_
     struct DevLevel {

@@ -13,15 +13,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_two_gpu_sharding_is_bit_identical_to_one_gpu():
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    nproc = int(os.environ.get("SPAND_MG_RANKS", "2"))  # 4 / 8: same test on more sub-trees
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
                         "--master-addr", "127.0.0.1", "--master-port", "29551", os.path.join(ROOT, "tests", "mg_worker.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("MG_RESULT ")][-1]
     per_rank = json.loads(line[len("MG_RESULT "):])
-    assert len(per_rank) == 2
+    assert len(per_rank) == nproc
     for recs in per_rank:
         for rec in recs:
             assert rec["same_ranks"] and rec["same_nnz"], rec
