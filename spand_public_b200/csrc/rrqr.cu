@@ -96,6 +96,14 @@ struct CandRec {  // what a CTA tells the cluster about its candidate for the ne
     int stop, pad;
 };
 
+// D = C + A B on one 8 x 8 x 4 FP64 tensor-core tile: a = A[lane / 4][lane % 4], b = B[lane % 4][lane / 4],
+// (c0, c1) = C[lane / 4][2 (lane % 4) + {0, 1}]
+__device__ __forceinline__ void dmma_f64(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ bool better(double v, int p, double bv, int bp) { return v > bv || (v == bv && p < bp); }
 
 __device__ __forceinline__ Cand warp_best(Cand b, int width) {
@@ -612,81 +620,50 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_blocked_kernel(const QrTask* __
         if (j == nb - 1) {
             const int kend = k + 1;
             if constexpr (!SMEM_PANEL) {
-                // Panel in global memory: a warp updates TB columns at once, two rows per lane (16-byte accesses),
-                // all loads of a pass issued before the first FMA; V is read once per row pair for the TB columns.
-                // Row kend - 1 shares a pair with row kend when kend is odd: it is final and passes through
-                // unchanged (its V entries are masked).
-                constexpr int TB = (MINB == 1) ? 8 : 4;
-                const int ld2 = ld >> 1, ldv2 = ldv >> 1;
-                const int i2lo = kend >> 1;
-                const double2* Vs2 = reinterpret_cast<const double2*>(Vs);
-                for (int first = warp * TB; first < ncl; first += TB * NW) {
-                    bool act[TB];
-                    bool any = false;
+                // Panel in global memory: the rank-nb update W(kend:, active) -= V F^T runs on the FP64 tensor cores
+                // (DMMA m8n8k4). A warp owns a strip of 8 columns: the B fragments (F of those columns) are loaded
+                // once, then the strip is swept in tiles of 8 rows (two tiles in flight): A = -V from shared memory,
+                // C read-modify-written in place. Rows above kend (final R entries) and columns that are already
+                // pivots are computed but never stored.
+                const int g = lane >> 2, q = lane & 3;
+                const int r_lo = kend & ~7;
+                for (int first = warp * 8; first < ncl; first += 8 * NW) {
+                    unsigned am = 0;
 #pragma unroll
-                    for (int c = 0; c < TB; c++) {
-                        act[c] = first + c < ncl && pos[first + c] >= kend;
-                        any |= act[c];
+                    for (int c = 0; c < 8; c++)
+                        if (first + c < ncl && pos[first + c] >= kend) am |= 1u << c;
+                    if (am == 0) continue;
+                    double bf[QNB / 4];
+#pragma unroll
+                    for (int kk = 0; kk < QNB / 4; kk++) {
+                        const int tt = kk * 4 + q;
+                        bf[kk] = (tt < nb && first + g < ncl) ? Fs[(size_t)(first + g) * FLD + tt] : 0.0;
                     }
-                    if (!any) continue;
-                    const double* fb = Fs + (size_t)first * FLD;
-                    if constexpr (MINB != 4) {
-                        double2* pa[TB];
+                    const bool actA = (am >> (2 * q)) & 1u, actB = (am >> (2 * q + 1)) & 1u;
+                    double* colA = P + (size_t)(first + 2 * q) * ld;
+                    double* colB = colA + ld;
+                    for (int r = r_lo; r < rows; r += 16) {
+                        const int row0 = r + g, row1 = r + 8 + g;
+                        const bool ok0 = row0 >= kend && row0 < rows, ok1 = row1 >= kend && row1 < rows;
+                        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+                        if (ok0 && actA) c00 = colA[row0];
+                        if (ok0 && actB) c01 = colB[row0];
+                        if (ok1 && actA) c10 = colA[row1];
+                        if (ok1 && actB) c11 = colB[row1];
 #pragma unroll
-                        for (int c = 0; c < TB; c++)
-                            pa[c] = reinterpret_cast<double2*>(P) + ((size_t)(first + (act[c] ? c : 0)) * ld2 + i2lo + lane);
-                        const double2* vp = Vs2 + i2lo + lane;
-                        for (int i2 = i2lo + lane; i2 < npair; i2 += 32) {
-                            const bool keepx = 2 * i2 < kend;
-                            double2 a[TB];
-#pragma unroll
-                            for (int c = 0; c < TB; c++)
-                                if (act[c]) a[c] = pa[c][0];
-#pragma unroll
-                            for (int tt = 0; tt < QNB; tt++)
-                                if (tt < nb) {
-                                    double2 v = vp[(size_t)tt * ldv2];
-                                    if (keepx) v.x = 0.0;
-#pragma unroll
-                                    for (int c = 0; c < TB; c++)
-                                        if (act[c]) {
-                                            const double f = fb[c * FLD + tt];
-                                            a[c].x = fma(-v.x, f, a[c].x);
-                                            a[c].y = fma(-v.y, f, a[c].y);
-                                        }
-                                }
-#pragma unroll
-                            for (int c = 0; c < TB; c++) {
-                                if (act[c]) pa[c][0] = a[c];
-                                pa[c] += 32;
+                        for (int kk = 0; kk < QNB / 4; kk++) {
+                            const int tt = kk * 4 + q;
+                            if (kk * 4 < nb) {  // uniform
+                                const double a0 = (tt < nb && row0 < ldv) ? -Vs[row0 + (size_t)tt * ldv] : 0.0;
+                                const double a1 = (tt < nb && row1 < ldv) ? -Vs[row1 + (size_t)tt * ldv] : 0.0;
+                                dmma_f64(c00, c01, a0, bf[kk]);
+                                dmma_f64(c10, c11, a1, bf[kk]);
                             }
-                            vp += 32;
                         }
-                    } else {
-                        double2* cb = reinterpret_cast<double2*>(P) + (size_t)first * ld2;
-                        for (int i2 = i2lo + lane; i2 < npair; i2 += 32) {
-                            const bool keepx = 2 * i2 < kend;
-                            double2 a[TB];
-#pragma unroll
-                            for (int c = 0; c < TB; c++)
-                                if (act[c]) a[c] = cb[(size_t)c * ld2 + i2];
-#pragma unroll
-                            for (int tt = 0; tt < QNB; tt++)
-                                if (tt < nb) {
-                                    double2 v = Vs2[i2 + (size_t)tt * ldv2];
-                                    if (keepx) v.x = 0.0;
-#pragma unroll
-                                    for (int c = 0; c < TB; c++)
-                                        if (act[c]) {
-                                            const double f = fb[c * FLD + tt];
-                                            a[c].x = fma(-v.x, f, a[c].x);
-                                            a[c].y = fma(-v.y, f, a[c].y);
-                                        }
-                                }
-#pragma unroll
-                            for (int c = 0; c < TB; c++)
-                                if (act[c]) cb[(size_t)c * ld2 + i2] = a[c];
-                        }
+                        if (ok0 && actA) colA[row0] = c00;
+                        if (ok0 && actB) colB[row0] = c01;
+                        if (ok1 && actA) colA[row1] = c10;
+                        if (ok1 && actB) colB[row1] = c11;
                     }
                 }
             } else

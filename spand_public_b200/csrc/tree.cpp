@@ -1198,9 +1198,16 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         // per_color counts the tasks of the whole wavefront (all ranks): the launch shapes are the single-GPU ones
         std::vector<int> per_color(std::max(1, ncolors), 0);
         for (const SymQr& q : L.q) per_color[q.color]++;
+        // ... except the cluster width G of the streaming shape, which does not change a task's arithmetic (same
+        // columns, same 32-lane reduction trees): it is sized from this rank's share of the wavefront, so a rank that
+        // holds a quarter of the tasks spreads each of them over four times as many CTAs
+        std::vector<int> per_color_own(std::max(1, ncolors), 0);
         std::vector<const SymQr*> own;
         for (const SymQr& q : L.q)
-            if (mine(q.cluster)) own.push_back(&q);
+            if (mine(q.cluster)) {
+                own.push_back(&q);
+                per_color_own[q.color]++;
+            }
         const size_t nq = own.size();
         std::vector<QrTask> tasks(nq);
         std::vector<int> task_color(nq);
@@ -1290,7 +1297,7 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 // wavefront to put about four CTAs on every SM and for the per-CTA state to stay small.
                 t.nb = std::min(QR_NBS, mn);
                 int G = 1;
-                while (G < 16 && per_color[task_color[i]] * G < stream_ctas) G *= 2;
+                while (G < 16 && per_color_own[task_color[i]] * G < stream_ctas) G *= 2;
                 // keep the panels of the CTAs resident at the same time (about 592) inside the L2
                 const double panel_bytes = 8.0 * t.rows * t.maxcols;
                 while (G < 16 && ((double)stream_ctas / G) * panel_bytes > l2_budget) G *= 2;
