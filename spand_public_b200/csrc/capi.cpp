@@ -94,7 +94,7 @@ int spand_get_perm(spand_tree* t, int* perm) {
 }
 int spand_get_N(spand_tree* t) { return t->t.N; }
 int spand_assemble(spand_tree* t, int N, const int* colptr, const int* rowind, const double* val) {
-    return guarded(t, [&] { t->t.assemble(from_csc(N, colptr, rowind, val)); });
+    return guarded(t, [&] { t->t.assemble_csc(N, colptr, rowind, val); });
 }
 int spand_factorize(spand_tree* t) {
     return guarded(t, [&] { t->t.factorize(); });

@@ -653,11 +653,21 @@ __global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__
         for (int b = 0; b < nblk; b++) {
             int j0 = b * SV_B, nb = min(SV_B, n - j0);
             if (warp == 0) {
+                // the 32 x 32 diagonal block goes to registers first (lane i holds row i): no load on the chain
+                double tr[SV_B], dg = 1.0;
+#pragma unroll
+                for (int j = 0; j < SV_B; j++) {
+                    tr[j] = (lane < nb && j < nb) ? T[(j0 + lane) + (size_t)(j0 + j) * t.ld] : 0.0;
+                    if (lane == j) dg = (j < nb) ? tr[j] : 1.0;
+                }
                 double xi = (lane < nb) ? x[j0 + lane] : 0.0;
-                for (int j = 0; j < nb; j++) {
-                    double xj = __shfl_sync(0xffffffffu, xi, j) / T[(j0 + j) + (size_t)(j0 + j) * t.ld];
-                    if (lane == j) xi = xj;
-                    if (lane > j && lane < nb) xi -= T[(j0 + lane) + (size_t)(j0 + j) * t.ld] * xj;
+#pragma unroll
+                for (int j = 0; j < SV_B; j++) {
+                    if (j < nb) {
+                        double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                        if (lane == j) xi = xj;
+                        if (lane > j && lane < nb) xi -= tr[j] * xj;
+                    }
                 }
                 if (lane < nb) {
                     x[j0 + lane] = xi;
@@ -684,11 +694,20 @@ __global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__
             }
             __syncthreads();
             if (warp == 0) {
+                double tr[SV_B], dg = 1.0;  // lane i holds column i of the diagonal block
+#pragma unroll
+                for (int j = 0; j < SV_B; j++) {
+                    tr[j] = (lane < nb && j < nb) ? T[(j0 + j) + (size_t)(j0 + lane) * t.ld] : 0.0;
+                    if (lane == j) dg = (j < nb) ? tr[j] : 1.0;
+                }
                 double xi = (lane < nb) ? xb[lane] : 0.0;
-                for (int j = nb - 1; j >= 0; j--) {
-                    double xj = __shfl_sync(0xffffffffu, xi, j) / T[(j0 + j) + (size_t)(j0 + j) * t.ld];
-                    if (lane == j) xi = xj;
-                    if (lane < j) xi -= T[(j0 + j) + (size_t)(j0 + lane) * t.ld] * xj;
+#pragma unroll
+                for (int j = SV_B - 1; j >= 0; j--) {
+                    if (j < nb) {
+                        double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                        if (lane == j) xi = xj;
+                        if (lane < j) xi -= tr[j] * xj;
+                    }
                 }
                 if (lane < nb) x[j0 + lane] = xi;
             }
@@ -698,12 +717,21 @@ __global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__
         for (int b = nblk - 1; b >= 0; b--) {
             int j0 = b * SV_B, nb = min(SV_B, n - j0);
             if (warp == 0) {
+                double tr[SV_B], dg = 1.0;  // lane i holds row i of the diagonal block
+#pragma unroll
+                for (int j = 0; j < SV_B; j++) {
+                    tr[j] = (lane < nb && j < nb) ? T[(j0 + lane) + (size_t)(j0 + j) * t.ld] : 0.0;
+                    if (lane == j) dg = (j < nb) ? tr[j] : 1.0;
+                }
+                if (t.diag && lane < nb) dg = t.diag[j0 + lane];
                 double xi = (lane < nb) ? x[j0 + lane] : 0.0;
-                for (int j = nb - 1; j >= 0; j--) {
-                    double dj = t.diag ? t.diag[j0 + j] : T[(j0 + j) + (size_t)(j0 + j) * t.ld];
-                    double xj = __shfl_sync(0xffffffffu, xi, j) / dj;
-                    if (lane == j) xi = xj;
-                    if (lane < j) xi -= T[(j0 + lane) + (size_t)(j0 + j) * t.ld] * xj;
+#pragma unroll
+                for (int j = SV_B - 1; j >= 0; j--) {
+                    if (j < nb) {
+                        double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                        if (lane == j) xi = xj;
+                        if (lane < j) xi -= tr[j] * xj;
+                    }
                 }
                 if (lane < nb) {
                     x[j0 + lane] = xi;
@@ -912,6 +940,54 @@ __global__ void __launch_bounds__(SV_T) house_kernel(const HouseTask* __restrict
         for (int i = j + 1 + tid; i < t.rows; i += SV_T) t.x[i] -= w * v[i];
         if (tid == 0) t.x[j] -= w;
         __syncthreads();
+    }
+}
+
+// Same operation with the vector held in registers (row i on thread i mod NT): a reflector costs one pass over its
+// column of V and ONE barrier (the exchange of the per-warp partial dot products, double buffered), instead of four.
+// WARP == true: tasks of at most 64 rows, one warp each, no barrier at all.
+template <int NT, int R, bool WARP>
+__global__ void __launch_bounds__(WARP ? 128 : NT) house_reg_kernel(const HouseTask* __restrict__ tasks, int nt, int trans) {
+    const int ti = WARP ? (int)(blockIdx.x * 4 + (threadIdx.x >> 5)) : (int)blockIdx.x;
+    if (ti >= nt) return;
+    const HouseTask t = tasks[ti];
+    if (t.rank >= t.rows) return;
+    const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    __shared__ double part[2][NT / 32];
+    double xr[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = tid + r * NT;
+        xr[r] = (i < t.rows) ? t.x[i] : 0.0;
+    }
+    for (int s = 0; s < t.rank; s++) {
+        const int j = trans ? s : (t.rank - 1 - s);
+        const double* v = t.V + (size_t)j * t.rows;
+        const double tau = t.tau[j];
+        double vr[R], w = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = tid + r * NT;
+            vr[r] = (i > j && i < t.rows) ? v[i] : (i == j ? 1.0 : 0.0);
+            w = fma(vr[r], xr[r], w);
+        }
+        w = warp_sum(w);
+        if (!WARP) {
+            if (lane == 0) part[s & 1][warp] = w;
+            __syncthreads();
+            w = 0.0;
+#pragma unroll
+            for (int q = 0; q < NT / 32; q++) w += part[s & 1][q];
+        }
+        w *= tau;
+#pragma unroll
+        for (int r = 0; r < R; r++) xr[r] = fma(-w, vr[r], xr[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = tid + r * NT;
+        if (i < t.rows) t.x[i] = xr[r];
     }
 }
 
@@ -1458,8 +1534,11 @@ void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, int
         gemv_t_big_kernel<<<dim3(nt, (max_m + 31) / 32), GV_T, 0, st>>>(t, c);
     }
 }
-void launch_house(const HouseTask* t, int nt, int trans, cudaStream_t st) {
-    if (nt > 0) house_kernel<<<nt, SV_T, 0, st>>>(t, trans);
+void launch_house(const HouseTask* t, int nt, int trans, int max_rows, cudaStream_t st) {
+    if (nt <= 0) return;
+    if (max_rows <= 64) house_reg_kernel<32, 2, true><<<(nt + 3) / 4, 128, 0, st>>>(t, nt, trans);
+    else if (max_rows <= 1024) house_reg_kernel<256, 4, false><<<nt, 256, 0, st>>>(t, nt, trans);
+    else house_kernel<<<nt, SV_T, 0, st>>>(t, trans);
 }
 void launch_xcopy(const XCopyTask* t, int nt, cudaStream_t st) {
     if (nt > 0) xcopy_kernel<<<(nt + 3) / 4, 128, 0, st>>>(t, nt);

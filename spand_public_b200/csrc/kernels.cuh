@@ -178,7 +178,7 @@ void launch_copy(const CopyTask* t, int nt, cudaStream_t st);
 // max_n / max_m: upper bound of the task sizes of the launch (selects the kernel shapes and the grid)
 void launch_trsv(const TrsvTask* t, int nt, int trans, int max_n, cudaStream_t st);
 void launch_gemv(const GemvTask* t, int nt, const GemvContrib* c, int trans, int max_m, cudaStream_t st);
-void launch_house(const HouseTask* t, int nt, int trans, cudaStream_t st);
+void launch_house(const HouseTask* t, int nt, int trans, int max_rows, cudaStream_t st);
 void launch_xcopy(const XCopyTask* t, int nt, cudaStream_t st);
 void launch_fill(double* p, size_t n, double v, cudaStream_t st);
 

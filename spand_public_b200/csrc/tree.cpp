@@ -431,8 +431,28 @@ void Tree::plan_counts(int level, long long out[12]) const {
 
 // src/tree.cpp:505-575 — the values go to the device as they are (CSC order) and are scattered into the dense
 // leaf blocks by one kernel
-void Tree::assemble(const SpMat& A) {
-    if (N == 0 || A.rows != N) throw std::runtime_error("assemble: call partition first with a matrix of the same size");
+void Tree::assemble(const SpMat& A) { assemble_impl(&A, A.rows, A.colptr.data(), A.rowind.data(), A.val.data()); }
+
+// Borrowed CSC arrays (the C ABI's spand_assemble): when the pattern is the one the plan was built for — the usual
+// case of repeated factorizations — nothing is copied on the host, the values go straight from the caller's buffer
+// to the device. Otherwise the matrix is canonicalised (sorted, duplicates summed) and analysed first.
+void Tree::assemble_csc(int n, const int* colptr, const int* rowind, const double* val) {
+    const bool same = plan_valid_ && n == N && pat_colptr_.size() == (size_t)n + 1 &&
+                      std::memcmp(pat_colptr_.data(), colptr, sizeof(int) * ((size_t)n + 1)) == 0 &&
+                      std::memcmp(pat_rowind_.data(), rowind, sizeof(int) * pat_rowind_.size()) == 0;
+    if (same) {
+        assemble_impl(nullptr, n, colptr, rowind, val);
+    } else {
+        SpMat A = from_csc(n, colptr, rowind, val);
+        assemble_impl(&A, n, A.colptr.data(), A.rowind.data(), A.val.data());
+    }
+}
+
+// A == nullptr: the caller has verified that (colptr, rowind) equal the planned pattern
+void Tree::assemble_impl(const SpMat* Afull, int n_in, const int* colptr, const int* rowind, const double* val) {
+    (void)rowind;
+    if (N == 0 || n_in != N) throw std::runtime_error("assemble: call partition first with a matrix of the same size");
+    const size_t nnz_in = (size_t)colptr[n_in];
     ensure_device();
     CK(cudaStreamSynchronize(st_));
     const bool timing = getenv("SPAND_TIMING") != nullptr;
@@ -463,8 +483,16 @@ void Tree::assemble(const SpMat& A) {
     build_clusters();
     lap("reset + build_clusters");
     const bool reuse = plan_valid_ && plan_ord_serial_ == ord_serial_ && plan_.symmetric == symmetry() &&
-                       plan_.want_flag == use_want_sparsify && pat_colptr_ == A.colptr && pat_rowind_ == A.rowind;
-    if (!reuse) analyze(A);
+                       plan_.want_flag == use_want_sparsify &&
+                       (Afull == nullptr || (pat_colptr_ == Afull->colptr && pat_rowind_ == Afull->rowind));
+    if (!reuse) {
+        if (Afull != nullptr) {
+            analyze(*Afull);
+        } else {  // same pattern but the plan depends on a setting that changed: analyse a copy
+            SpMat A = from_csc(n_in, colptr, rowind, val);
+            analyze(A);
+        }
+    }
     lap(reuse ? "pattern check (plan reused)" : "symbolic analysis");
 
     const int ncl = ord.norders;
@@ -538,10 +566,10 @@ void Tree::assemble(const SpMat& A) {
     stager_.upload(d_eptr_, h_eptr_.data(), sizeof(double*) * plan_.nleaf_edges, st_);
     stager_.upload(d_eld_, h_eld_.data(), sizeof(int) * plan_.nleaf_edges, st_);
     // values
-    double* d_val = scratch_->alloc_n<double>(A.nnz());
-    CK(cudaMemcpyAsync(d_val, A.val.data(), sizeof(double) * A.nnz(), cudaMemcpyHostToDevice, st_));
+    double* d_val = scratch_->alloc_n<double>(nnz_in);
+    CK(cudaMemcpyAsync(d_val, val, sizeof(double) * nnz_in, cudaMemcpyHostToDevice, st_));
     CK(cudaMemsetAsync(dblocks, 0, leaf_total_ * sizeof(double), st_));
-    launch_scatter_values(d_val, d_valmap_, (size_t)A.nnz(), dblocks, st_);
+    launch_scatter_values(d_val, d_valmap_, nnz_in, dblocks, st_);
     CK(cudaStreamSynchronize(st_));
     lap("uploads + scatter kernel");
     stager_.reset();
@@ -1768,13 +1796,13 @@ void Tree::solve_device(double* x_dev) {
         mg_barrier();
         launch_gemv(s.e_gemv_f, s.n_e_gemv_f, s.e_gemv_fc, 0, s.max_e, st_);
         launch_trsv(s.s_trsv, s.n_s_trsv, 0, s.max_s, st_);
-        launch_house(s.house, s.n_house, 1, st_);
+        launch_house(s.house, s.n_house, 1, s.max_s, st_);
         launch_xcopy(s.m_fwd, s.n_merge, st_);
     }
     for (int l = nlevels - 1; l >= 0; l--) {
         SolveLevel& s = solve_[l];
         launch_xcopy(s.m_bwd, s.n_merge, st_);
-        launch_house(s.house, s.n_house, 0, st_);
+        launch_house(s.house, s.n_house, 0, s.max_s, st_);
         // LLT: x <- L^-T x, x_s -= A[n,s]^T x_n ; PLU: x <- U^-1 x, x_s -= A[s,n] x_n   (operations.cpp bwd)
         const bool plu = scale_kind == PLU;
         launch_trsv(s.s_trsv, s.n_s_trsv, plu ? 2 : 1, s.max_s, st_);

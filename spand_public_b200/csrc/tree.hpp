@@ -101,6 +101,7 @@ class Tree {
     void set_coords(int dim, int N, const double* X);
     void partition(const SpMat& A);
     void assemble(const SpMat& A);
+    void assemble_csc(int n, const int* colptr, const int* rowind, const double* val);  // borrowed arrays, no host copy
     void factorize();                 // throws std::runtime_error("Error: Non-SPD Pivot\n") etc.
     void solve(double* x_host);       // in place, host vector of length N
     void solve_device(double* x_dev); // in place, device vector of length N (natural ordering)
@@ -182,6 +183,7 @@ class Tree {
     SymbolicPlan plan_;
     bool plan_valid_ = false;
     int ord_serial_ = 0, plan_ord_serial_ = -1;
+    void assemble_impl(const SpMat* Afull, int n, const int* colptr, const int* rowind, const double* val);
     std::vector<int> pat_colptr_, pat_rowind_;  // pattern the plan and the value map were built for
     std::vector<size_t> leaf_off_;              // element offset of every leaf block in the assembled buffer
     size_t leaf_total_ = 0;
