@@ -35,14 +35,16 @@ for spec in args or ["base"]:
     if spec != "base":
         for kv in spec.split(","):
             k, v = kv.split("=")
-            os.environ["SPAND_RRQR_" + k] = v
-            keys.append("SPAND_RRQR_" + k)
+            name = k if k.startswith("SPAND_") else "SPAND_RRQR_" + k
+            os.environ[name] = v
+            keys.append(name)
     try:
         best = None
         for rep in range(2):
             t.assemble(A); t.factorize()
             lg = t.log()
-            cur = (t.factorize_seconds(), float(lg["t_spars"].sum()), [round(float(x) * 1e3, 1) for x in lg["t_spars"]])
+            cur = (t.factorize_seconds(), float(lg["t_spars"].sum()), [round(float(x) * 1e3, 1) for x in lg["t_spars"]],
+                   [round(float(x) * 1e3, 1) for x in lg["t_scale"]], [round(float(x) * 1e3, 1) for x in lg["t_elim"]])
             best = cur if best is None or cur[0] < best[0] else best
         ranks = t.stats()[2].copy()
         if ref_ranks is None:
@@ -50,7 +52,8 @@ for spec in args or ["base"]:
         x = t.solve(b)
         res = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
         print(json.dumps({"variant": spec, "factorize_ms": round(best[0] * 1e3, 1), "sparsify_ms": round(best[1] * 1e3, 1),
-                          "ranks_differ": int((ranks != ref_ranks).sum()), "residual": res, "spars_per_level_ms": best[2]}),
+                          "ranks_differ": int((ranks != ref_ranks).sum()), "residual": res, "spars_per_level_ms": best[2],
+                          "scale_per_level_ms": best[3], "elim_per_level_ms": best[4]}),
               flush=True)
     except Exception as e:  # a variant that does not fit (shared memory, scratch) must not end the sweep
         print(json.dumps({"variant": spec, "error": str(e)[:300]}), flush=True)

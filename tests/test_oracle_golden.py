@@ -211,3 +211,58 @@ def test_readme_run_shape():
     assert t.nnz() == g["nnz"]
     it, _ = t.cg(A, S.random(1024, 2019), 100, 1e-12)
     assert it == g["cg"]
+
+
+def test_readme_gmres_run():
+    """README.md:215-230: the example run converges in 6 GMRES iterations with a residual that drops by 1.5-3
+    orders of magnitude per iteration down to ~1e-14 (algebraic partition of an older revision: indicative, so the
+    count is pinned to 6 +- 1 and the final residual to <= 1e-12 on the geometric partition of the same matrix)."""
+    A = S.neglapl(32, 2)
+    t = O.OracleTree(5, tol=1e-2)
+    t.set_coords(S.linspace_nd(32, 2)[::-1] + 1.0)
+    t.partition(S.symmetric_graph(A))
+    t.assemble(A)
+    t.factorize()
+    b = S.random(1024, 2019)
+    it, x = t.gmres(A, b, 100, 100, 1e-12)
+    assert abs(it - 6) <= 1
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 1e-12
+
+
+def test_gmres_restatement_properties():
+    """src/is.cpp:123-300 semantics: zero rhs -> x = 0 and `true`; the iteration cap is honoured; a restart does
+    not change the iterates of a preconditioner that is an exact inverse (1 iteration); restarted and full GMRES
+    reach the same solution; non-symmetric C5-family matrix with the PLU preconditioner converges."""
+    A = S.neglapl(12, 2)
+    N = A.shape[0]
+    b = S.random(N, 2019)
+    exact = O.OracleTree(3, tol=0.0)
+    exact.set_coords(S.linspace_nd(12, 2))
+    exact.partition(A)
+    exact.assemble(A)
+    exact.factorize()
+    it, x = exact.gmres(A, np.zeros(N), 10, 5, 1e-12)
+    assert it == 1 and not x.any()
+    it, x = exact.gmres(A, b, 10, 5, 1e-10)
+    assert it == 1 and np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 1e-10
+    loose = O.OracleTree(3, tol=0.3)
+    loose.set_coords(S.linspace_nd(12, 2))
+    loose.partition(A)
+    loose.assemble(A)
+    loose.factorize()
+    it_cap, _ = loose.gmres(A, b, 2, 100, 1e-14)
+    assert it_cap == 2
+    it_full, x_full = loose.gmres(A, b, 200, 200, 1e-12)
+    it_rs, x_rs = loose.gmres(A, b, 200, 3, 1e-12)
+    assert it_rs >= it_full > 2
+    assert np.linalg.norm(x_full - x_rs) / np.linalg.norm(x_full) <= 1e-9
+    G = S.aniso_convdiff(8)
+    assert abs(G - G.T).max() > 1e-3  # genuinely non-symmetric
+    t = O.OracleTree(4, tol=1e-2, symm_kind=O.GEN, scaling_kind=O.PLU)
+    t.set_coords(S.linspace_nd(8, 3))
+    t.partition(S.symmetric_graph(G))
+    t.assemble(G)
+    t.factorize()
+    bb = S.random(G.shape[0], 2019)
+    it, x = t.gmres(G, bb, 100, 100, 1e-12)
+    assert it < 20 and np.linalg.norm(G @ x - bb) / np.linalg.norm(bb) <= 1e-11

@@ -98,3 +98,38 @@ def test_plan_needs_partition_first():
     g = S.Tree(3)
     with pytest.raises(RuntimeError):
         g.plan_analyze(S.neglapl(5, 2))
+
+
+def test_csc_input_need_not_be_canonical():
+    """spand_partition / spand_plan_analyze take borrowed CSC arrays: rows sorted inside every column take the
+    copy-only path, anything else (unsorted rows, duplicates to be summed) is canonicalised first
+    (spand_public_b200/csrc/host/sparse.cpp from_csc). Both must give the same partition and the same plan."""
+    A = S.neglapl(10, 2).tocsc()
+    A.sort_indices()
+    N = A.shape[0]
+    L = S.lib()
+    X = S.linspace_nd(10, 2)
+    rng = np.random.RandomState(0)
+    indptr = A.indptr.astype(np.int32)
+    ind = A.indices.astype(np.int32).copy()
+    for j in range(N):  # shuffle the rows of every column
+        sl = slice(indptr[j], indptr[j + 1])
+        ind[sl] = ind[sl][rng.permutation(indptr[j + 1] - indptr[j])]
+    results = []
+    for rowind in (A.indices.astype(np.int32), ind):
+        h = L.spand_create(3)
+        L.spand_set_use_geo(h, 1)
+        assert L.spand_set_coords(h, 2, N, np.ascontiguousarray(X.T).ravel()) == 0
+        assert L.spand_partition(h, N, indptr, np.ascontiguousarray(rowind)) == 0
+        perm = np.zeros(N, dtype=np.int32)
+        L.spand_get_perm(h, perm)
+        assert L.spand_plan_analyze(h, N, indptr, np.ascontiguousarray(rowind)) == 0
+        counts = np.zeros(12, dtype=np.int64)
+        per_level = []
+        for lvl in range(3):
+            assert L.spand_plan_counts(h, lvl, counts) == 0
+            per_level.append(counts.copy())
+        results.append((perm, np.array(per_level)))
+        L.spand_destroy(h)
+    assert np.array_equal(results[0][0], results[1][0])
+    assert np.array_equal(results[0][1], results[1][1])
