@@ -88,7 +88,10 @@ struct QrSrc {
 };
 
 constexpr int QR_NB = 16;   // block size of the blocked QRCP (dlaqps-like)
-constexpr int QR_NBS = 8;   // block size of the streaming shape (panel in global memory, 64 registers per thread)
+#ifndef SPAND_QR_NBS
+#define SPAND_QR_NBS 8
+#endif
+constexpr int QR_NBS = SPAND_QR_NBS;   // block size of the streaming shape (panel in global memory, 64 registers per thread)
 constexpr int QR_FLD = 17;  // row stride of the F block in shared memory (odd: conflict-free)
 
 struct QrTask {
