@@ -225,6 +225,14 @@ void Tree::partition(const SpMat& A) {
 // non-zeros of A to their position inside the dense leaf blocks (util.cpp:454-486 block2dense), and the plan of
 // every level (symbolic.hpp). Everything is uploaded into sym_arena_ and reused by later assemble() calls.
 void Tree::analyze_host(const SpMat& A, std::vector<unsigned>& valmap) {
+    const bool timing = getenv("SPAND_TIMING") != nullptr;
+    double tm0 = wtime();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const double now = wtime();
+        fprintf(stderr, "[spand] analyze: %-30s %8.2f ms\n", what, (now - tm0) * 1e3);
+        tm0 = now;
+    };
     const bool symm = symmetry();
     const int ncl = ord.norders;
     std::vector<int> pinv(N), cmap(N);
@@ -275,6 +283,7 @@ void Tree::analyze_host(const SpMat& A, std::vector<unsigned>& valmap) {
     }
     if (total >= 0xffffffffull) throw std::runtime_error("assemble: leaf blocks exceed the 32-bit value map");
     leaf_total_ = total;
+    lap("leaf block structure");
     // pass 2: value map
     valmap.assign(A.nnz(), 0xffffffffu);
     for (int s : bottoms_[0]) {
@@ -292,11 +301,13 @@ void Tree::analyze_host(const SpMat& A, std::vector<unsigned>& valmap) {
             }
         }
     }
+    lap("value map");
     // plan
     std::vector<SymCluster> sc(ncl);
     for (int c = 0; c < ncl; c++)
         sc[c] = SymCluster{cl_[c].level, cl_[c].hlevel, cl_[c].parent, cl_[c].child_begin, cl_[c].child_end, cl_[c].sparsify};
     build_symbolic(sc, bottoms_, leaf_n1, leaf_n2, symm, use_want_sparsify, plan_);
+    lap("build_symbolic (all levels)");
     pat_colptr_ = A.colptr;
     pat_rowind_ = A.rowind;
     plan_ord_serial_ = ord_serial_;
