@@ -133,3 +133,40 @@ def test_csc_input_need_not_be_canonical():
         L.spand_destroy(h)
     assert np.array_equal(results[0][0], results[1][0])
     assert np.array_equal(results[0][1], results[1][1])
+
+
+def test_partition_is_independent_of_host_threads(monkeypatch):
+    """The geometric bisections of one depth run on a thread pool (host/partition.cpp) and the ordering sorts the
+    distinct ClusterIDs instead of the dofs: the ClusterID of every dof and the assembly permutation must not depend
+    on the number of threads (1 = the sequential order of the reference, src/partition.cpp:384-478)."""
+    n, d, L = 48, 3, 9  # 110 592 dofs: above the size where the pool is used
+    A = S.symmetric_graph(S.neglapl(n, d))
+    X = S.linspace_nd(n, d)
+    results = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("SPAND_HOST_THREADS", threads)
+        t = S.Tree(L)
+        t.set_use_geo(True)
+        t.set_Xcoo(X)
+        t.partition(A)
+        results.append((t.get_assembly_perm().copy(), np.stack(t.partition_ids())))
+    for perm, ids in results[1:]:
+        assert np.array_equal(perm, results[0][0])
+        assert np.array_equal(ids, results[0][1])
+    # the permutation is the one of the reference's ordering, restated literally: identity, then one stable sort per
+    # level by the progressively merged ClusterIDs (src/tree.cpp:344-352) = a lexicographic sort whose most
+    # significant key is the ClusterID merged up to the top level
+    perm, ids = results[0]
+    slv, ssp, llv, lsp, rlv, rsp = [ids[i].astype(np.int64) for i in range(6)]
+    keys = []  # most significant first
+    per_level = []
+    for lvl in range(L):
+        if lvl > 0:
+            ml, mr = llv < lvl, rlv < lvl
+            llv, lsp = np.where(ml, llv + 1, llv), np.where(ml, lsp // 2, lsp)
+            rlv, rsp = np.where(mr, rlv + 1, rlv), np.where(mr, rsp // 2, rsp)
+        per_level.append([slv, ssp, llv.copy(), lsp.copy(), rlv.copy(), rsp.copy()])
+    for lvl in reversed(range(L)):
+        keys.extend(per_level[lvl])
+    ref = np.lexsort(tuple(reversed(keys)))
+    assert np.array_equal(ref.astype(perm.dtype), perm)
