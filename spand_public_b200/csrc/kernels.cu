@@ -1014,14 +1014,6 @@ __global__ void spmv_kernel(int n, const int* __restrict__ rowptr, const int* __
     if (row < n && sub == 0) y[row] = s;
 }
 
-__global__ void dot_kernel(int n, const double* __restrict__ a, const double* __restrict__ b, double* out) {
-    __shared__ double red[8];
-    double s = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += a[i] * b[i];
-    s = block_sum<256>(s, red);
-    if (threadIdx.x == 0) atomicAdd(out, s);
-}
-
 __global__ void axpy_kernel(int n, double alpha, const double* __restrict__ x, double* __restrict__ y) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += alpha * x[i];
 }
@@ -1550,9 +1542,6 @@ void launch_fill(double* p, size_t n, double v, cudaStream_t st) {
 void launch_spmv(int n, const int* rowptr, const int* colind, const double* val, const double* x, double* y,
                  cudaStream_t st) {
     if (n > 0) spmv_kernel<<<(int)(((size_t)n * 4 + 255) / 256), 256, 0, st>>>(n, rowptr, colind, val, x, y);
-}
-void launch_dot(int n, const double* a, const double* b, double* out, cudaStream_t st) {
-    if (n > 0) dot_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(n, a, b, out);
 }
 void launch_axpy(int n, double alpha, const double* x, double* y, cudaStream_t st) {
     if (n > 0) axpy_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, alpha, x, y);

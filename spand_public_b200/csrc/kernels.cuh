@@ -246,7 +246,6 @@ void launch_scatter_values(const double* val, const unsigned* map, size_t n, dou
 // PCG building blocks (src/is.cpp:39-121)
 void launch_spmv(int n, const int* rowptr, const int* colind, const double* val, const double* x, double* y,
                  cudaStream_t st);
-void launch_dot(int n, const double* a, const double* b, double* out, cudaStream_t st);  // out must be zeroed
 void launch_axpy(int n, double alpha, const double* x, double* y, cudaStream_t st);      // y += alpha x
 void launch_xpay(int n, const double* x, double beta, double* y, cudaStream_t st);       // y = x + beta y
 void launch_gather(int n, const int* idx, const double* src, double* dst, cudaStream_t st);   // dst[i] = src[idx[i]]
