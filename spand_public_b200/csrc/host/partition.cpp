@@ -137,12 +137,14 @@ std::vector<ClusterID> partition_modifiedND(const SpMat& A, int nlevels, const D
         long sepmin, sepmax, septot;
     };
     std::vector<Work> work(max_threads);
+    std::vector<ClusterID> part_prev;
     for (int depth = 0; depth < nlevels - 1; depth++) {
         int level = nlevels - depth - 1;
         int nseps = 1 << depth;
         std::vector<std::vector<int>> newdoms(2 * nseps);
         const int nthreads = (N >= 100000) ? std::min(max_threads, nseps) : 1;
         std::atomic<int> next(0);
+        part_prev = part;
         auto run = [&](int tix) {
             Work& w = work[tix];
             if ((int)w.scratch.size() < N + 1) {
@@ -161,27 +163,33 @@ std::vector<ClusterID> partition_modifiedND(const SpMat& A, int nlevels, const D
                 if (geo) separator_geo(colptr, rowval, dofs, parttmp, *Xcoo, scratch);
                 else separator_metis(colptr, rowval, dofs, parttmp);
                 SepID idleft(level - 1, 2 * sep), idright(level - 1, 2 * sep + 1);
+                // A separator dof sits in two sub-domains (its l and r sides), i.e. two threads may hold it: each
+                // reads the ClusterID as it was when the depth started (part_prev, immutable) and writes back only the
+                // fields that carried its own separator id, which no other sub-domain of this depth can own.
+                long nnewsep = 0;
                 for (size_t i = 0; i < dofs.size(); i++) {
-                    ClusterID& p = part[dofs[i]];
+                    const int g = dofs[i];
+                    const ClusterID& p0 = part_prev[g];
+                    ClusterID q = p0;
                     int side = parttmp[i];
                     if (side == 0 || side == 1) {
                         const SepID& idside = (side == 0 ? idleft : idright);
-                        if (p.self == idself) p.self = idside;
-                        if (p.l == idself) p.l = idside;
-                        if (p.r == idself) p.r = idside;
+                        if (q.self == idself) q.self = idside;
+                        if (q.l == idself) q.l = idside;
+                        if (q.r == idself) q.r = idside;
                     } else if (side == 2) {
-                        if (p.self == idself) {
-                            p.l = idleft;
-                            p.r = idright;
+                        if (q.self == idself) {
+                            q.l = idleft;
+                            q.r = idright;
                         }
                     }
-                }
-                long nnewsep = 0;
-                for (int g : dofs) {
-                    const ClusterID& p = part[g];
-                    if (p.self == idleft || p.l == idleft || p.r == idleft) newdoms[2 * sep].push_back(g);
-                    if (p.self == idright || p.l == idright || p.r == idright) newdoms[2 * sep + 1].push_back(g);
-                    if (p.self == idself && p.l == idleft && p.r == idright) nnewsep++;
+                    ClusterID& p = part[g];
+                    if (!(q.self == p0.self)) p.self = q.self;
+                    if (!(q.l == p0.l)) p.l = q.l;
+                    if (!(q.r == p0.r)) p.r = q.r;
+                    if (q.self == idleft || q.l == idleft || q.r == idleft) newdoms[2 * sep].push_back(g);
+                    if (q.self == idright || q.l == idright || q.r == idright) newdoms[2 * sep + 1].push_back(g);
+                    if (q.self == idself && q.l == idleft && q.r == idright) nnewsep++;
                 }
                 w.sepmin = std::min(w.sepmin, nnewsep);
                 w.sepmax = std::max(w.sepmax, nnewsep);

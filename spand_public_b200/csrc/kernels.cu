@@ -1494,7 +1494,14 @@ void launch_getrf_finish(const GetrfTask* t, int nt, cudaStream_t st) {
     getrf_finish_kernel<<<nt, 256, 128 * 1024, st>>>(t);
 }
 void launch_rowperm(const RowPermTask* t, int nt, cudaStream_t st) {
-    if (nt > 0) rowperm_kernel<<<nt, 128, 6144 * sizeof(double) + 64, st>>>(t);
+    if (nt <= 0) return;
+    constexpr int smem = 6144 * sizeof(double) + 64;  // above the 48 KB default: needs the opt-in attribute
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(rowperm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    rowperm_kernel<<<nt, 128, smem, st>>>(t);
 }
 
 void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const int* tile_prefix, int total_tiles,

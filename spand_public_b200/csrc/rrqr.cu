@@ -28,6 +28,8 @@
 #include <cfloat>
 #include <climits>
 #include <cstdlib>
+#include <stdexcept>
+#include <string>
 
 #include "kernels.cuh"
 
@@ -756,7 +758,10 @@ void launch_one(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, t, s, csize, tol);
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, t, s, csize, tol);
+    if (err != cudaSuccess)  // a shape the device cannot schedule must not pass silently (the ranks would be garbage)
+        throw std::runtime_error(std::string("rrqr launch failed (G=") + std::to_string(G) + ", threads=" +
+                                 std::to_string(NT) + ", smem=" + std::to_string(smem) + "): " + cudaGetErrorString(err));
 }
 
 }  // namespace

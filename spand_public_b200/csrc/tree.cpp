@@ -11,6 +11,7 @@
 #include <map>
 #include <unordered_map>
 #include <stdexcept>
+#include <string>
 
 namespace spand {
 
@@ -603,6 +604,9 @@ int Tree::level_max_size() const {
 }
 
 void Tree::check_error() {
+    // launch-configuration errors are only reported by the launch itself / cudaGetLastError
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) throw std::runtime_error(std::string("CUDA launch error: ") + cudaGetErrorString(le));
     int err = 0;
     CK(cudaMemcpyAsync(&err, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
@@ -1369,9 +1373,13 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 nd = config(256, 1 << g, true);
                 if (nd <= kBuckets[4]) gi = g;
                 else if (nd <= MAXS) {
-                    nt = 512;
-                    nd = config(512, 1 << g, true);
-                    gi = g;
+                    // 512 threads change the lanes per column and with them the padding of ld: check again
+                    const long nd512 = config(512, 1 << g, true);
+                    if (nd512 <= MAXS) {
+                        nt = 512;
+                        nd = nd512;
+                        gi = g;
+                    }
                 }
             }
             if (gi >= 0) {

@@ -511,3 +511,38 @@ def test_gmres_edge_cases():
     ito, xo = o.gmres(A, b, 3, 100, 1e-14)
     assert itg == ito == 3
     assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) <= 1e-8
+
+
+def test_plu_row_pivoting_matters():
+    """A pivot block whose diagonal does not dominate: dgetrf really permutes rows, so ScalingPLUQ's P (row
+    permutation of the in-edges, src/tree.cpp:838-853, and of the right-hand side, operations.cpp) is exercised.
+    The diagonally dominant matrices of the other PLU tests never pivot."""
+    n, L = 16, 4
+    A = S.neglapl(n, 2).tocsc().astype(np.float64)
+    rng = np.random.RandomState(11)
+    A.data = A.data + rng.uniform(-0.3, 0.3, A.nnz)
+    A.setdiag(rng.uniform(0.3, 0.8, A.shape[0]) * rng.choice([-1.0, 1.0], A.shape[0]))  # weak, sign-mixed diagonal
+    A = A.tocsc()
+    X = S.linspace_nd(n, 2)
+    G = S.symmetric_graph(A)
+    g = S.Tree(L)
+    g.set_tol(0.0)
+    g.set_symm_kind(S.GEN)
+    g.set_scaling_kind(S.PLU)
+    g.set_use_geo(True)
+    g.set_Xcoo(X)
+    o = O.OracleTree(L, tol=0.0, symm_kind=O.GEN, scaling_kind=O.PLU)
+    o.set_coords(X)
+    g.partition(G)
+    o.partition(G)
+    g.assemble(A)
+    o.assemble(A)
+    g.factorize()
+    o.factorize()
+    b = S.random(A.shape[0], 2019)
+    xg, xo = g.solve(b), o.solve(b)
+    ro = np.linalg.norm(A @ xo - b) / np.linalg.norm(b)
+    rg = np.linalg.norm(A @ xg - b) / np.linalg.norm(b)
+    assert ro <= 1e-8, ro  # the oracle solves it: the test matrix is usable
+    assert rg <= max(100 * ro, 1e-9), (rg, ro)
+    assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) <= 1e-6
