@@ -196,3 +196,54 @@ def test_csc_duplicates_and_empty_columns():
     assert L.spand_get_N(h) == n
     L.spand_destroy(h)
     assert C.has_canonical_format and C.nnz <= 300
+
+
+def test_threaded_geometric_partition_matches_literal_restatement():
+    """Modified nested dissection with geometric bisection (src/partition.cpp:139-210, :384-478) restated with numpy,
+    sub-domain by sub-domain in the reference's sequential order, against the threaded C++ front end on a problem
+    large enough for the thread pool (110 592 dofs, 9 levels, up to 128 sub-domains per depth)."""
+    n, d, L = 48, 3, 9
+    A = S.symmetric_graph(S.neglapl(n, d)).tocsr()
+    X = S.linspace_nd(n, d)
+    N = A.shape[0]
+    t = S.Tree(L)
+    t.set_use_geo(True)
+    t.set_Xcoo(X)
+    t.partition(A)
+    got = np.stack(t.partition_ids()).astype(np.int64)  # self_lvl, self_sep, l_lvl, l_sep, r_lvl, r_sep
+    ids = np.zeros((6, N), dtype=np.int64)
+    ids[0::2] = L - 1  # (lvl, sep) = (L - 1, 0) for self, l, r
+    doms = [np.arange(N)]
+    for depth in range(L - 1):
+        level = L - depth - 1
+        new = []
+        for sep, dofs in enumerate(doms):
+            if len(dofs) == 0:
+                new += [dofs, dofs]
+                continue
+            Xd = X[:, dofs]
+            rng_ = Xd.max(axis=1) - Xd.min(axis=1)
+            best = int(np.argmax(rng_))  # first maximal range, like the strict '>' of the reference
+            xs = Xd[best]
+            midv = np.partition(xs, len(dofs) // 2)[len(dofs) // 2]
+            parts = (xs >= midv).astype(np.int64)
+            sub = A[dofs][:, dofs]
+            touches_left = (sub @ (parts == 0).astype(np.float64)) > 0
+            parts[(parts == 1) & touches_left] = 2
+            idself, idl, idr = (level, sep), (level - 1, 2 * sep), (level - 1, 2 * sep + 1)
+            q = ids[:, dofs].copy()
+            for f in (0, 2, 4):  # self, l, r move to the side the dof fell on
+                m = (q[f] == idself[0]) & (q[f + 1] == idself[1])
+                for side, idside in ((0, idl), (1, idr)):
+                    mm = m & (parts == side)
+                    q[f, mm], q[f + 1, mm] = idside
+            on_sep = (parts == 2) & (ids[0, dofs] == idself[0]) & (ids[1, dofs] == idself[1])
+            q[2, on_sep], q[3, on_sep] = idl
+            q[4, on_sep], q[5, on_sep] = idr
+            ids[:, dofs] = q
+            def member(idx):
+                return ((q[0] == idx[0]) & (q[1] == idx[1])) | ((q[2] == idx[0]) & (q[3] == idx[1])) | \
+                       ((q[4] == idx[0]) & (q[5] == idx[1]))
+            new += [dofs[member(idl)], dofs[member(idr)]]
+        doms = new
+    assert np.array_equal(got, ids)
