@@ -2,6 +2,9 @@
 #include "symbolic.hpp"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <stdexcept>
 
 #include "kernels.cuh"
@@ -59,6 +62,18 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
 
     std::vector<int> task_of_edge;
     std::vector<int> slot(ncl, -1), tlist, color;
+    double tsec[6] = {0, 0, 0, 0, 0, 0};
+    auto nowf = [] {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    };
+    double tlast = nowf();
+    auto lap = [&](int i) {
+        double n = nowf();
+        tsec[i] += n - tlast;
+        tlast = n;
+    };
     for (int l = 0; l < nlevels; l++) {
         SymLevel& L = plan.lv[l];
         const std::vector<int>& bottom = bottoms[l];
@@ -73,6 +88,7 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
             for (int e : in[s]) L.e_in.push_back({e, piv, en1[e], s});
             for (size_t k = 1; k < out[s].size(); k++) L.e_out.push_back({out[s][k], piv, en2[out[s][k]], s});
         }
+        lap(0);
         // Schur complement targets in the reference's loop order (tree.cpp:862-869 / :943-947, gemm_edges :761-772)
         L.fill0 = (int)en1.size();
         {
@@ -136,6 +152,7 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
             for (int e : targets) task_of_edge[e] = -1;
         }
         L.fill1 = (int)en1.size();
+        lap(1);
         // recorded operations (tree.cpp:909-910, :885-892 / GEN :950-956)
         {
             struct F { int target, edge, src; };
@@ -170,6 +187,7 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
                 i = j;
             }
         }
+        lap(2);
         // set_eliminated (cluster.cpp:32-45)
         {
             std::vector<char> dead_mark;
@@ -204,6 +222,7 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
                 }
             }
         }
+        lap(3);
         // ---------------- scale ----------------
         for (int c : bottom) {
             if (eliminated[c] || cl[c].level <= l) continue;
@@ -248,6 +267,7 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
                 L.q.push_back(t);
             }
         }
+        lap(4);
         // ---------------- merge (tree.cpp:1106-1184) ----------------
         L.medge0 = L.medge1 = (int)en1.size();
         if (l < nlevels - 1) {
@@ -296,7 +316,12 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
                     in[c].clear();
                 }
         }
+        lap(5);
     }
+    if (getenv("SPAND_TIMING"))
+        fprintf(stderr, "[spand] build_symbolic: elim lists %.0f ms, schur %.0f ms, solve lists %.0f ms, set_eliminated %.0f ms, "
+                        "scale+sparsify %.0f ms, merge %.0f ms\n", tsec[0] * 1e3, tsec[1] * 1e3, tsec[2] * 1e3, tsec[3] * 1e3,
+                tsec[4] * 1e3, tsec[5] * 1e3);
 }
 
 }  // namespace spand
