@@ -530,6 +530,11 @@ void OTree::sparsify_cluster(OCluster* self) {
     std::vector<double> diag(mn);
     for (int i = 0; i < mn; i++) diag[i] = Asn(i, i);
     int rank = choose_rank(diag.data(), mn, tol);
+    if (const char* qlog = getenv("SPAND_ORACLE_QRLOG")) {
+        // analysis hook (not part of the restatement): one line per RRQR "level rows cols rank" for traffic models
+        static FILE* qf = fopen(qlog, "w");
+        if (qf) { fprintf(qf, "%d %d %d %d\n", ilvl, rows, cols, rank); fflush(qf); }
+    }
     if (getenv("SPAND_ORACLE_DEADCOLS") && rank > 0) {
         // analysis hook (not part of the restatement): how much of the per-step panel sweep of a truncated QRCP
         // touches columns whose residual norm is already below the stopping threshold (they can never be pivots)
@@ -549,6 +554,25 @@ void OTree::sparsify_cluster(OCluster* self) {
                 if (tail[p][std::min(k, mn)] >= thr2) live += rows - k;
                 if (tail[p][std::min(kb, mn)] >= thr2) live_blk += rows - k;
             }
+        }
+        if (getenv("SPAND_ORACLE_HOTCOLS")) {
+            // hot/cold model: at a block boundary kb a column is "hot" when its residual norm is at least theta times
+            // the pivot level |R(kb,kb)|; only hot columns are swept during the block
+            const int nbh = atoi(getenv("SPAND_ORACLE_HOTCOLS"));
+            static double h_all[64], h_hot[3][64];
+            const double th[3] = {0.25, 0.5, 0.75};
+            for (int k = 0; k < rank; k++) {
+                const int kb = k - k % nbh;
+                const double lev2 = Asn(kb, kb) * Asn(kb, kb);
+                for (int p = k + 1; p < cols; p++) {
+                    h_all[ilvl] += rows - k;
+                    for (int q = 0; q < 3; q++)
+                        if (tail[p][std::min(kb, mn)] >= th[q] * th[q] * lev2) h_hot[q][ilvl] += rows - k;
+                }
+            }
+            fprintf(stderr, "HOTCOLS lvl %d rows %d cols %d rank %d | level so far hot(.25) %.3f hot(.5) %.3f hot(.75) %.3f (%.3g)\n",
+                    ilvl, rows, cols, rank, h_hot[0][ilvl] / h_all[ilvl], h_hot[1][ilvl] / h_all[ilvl],
+                    h_hot[2][ilvl] / h_all[ilvl], h_all[ilvl]);
         }
         static double g_all[64], g_live[64], g_blk[64];
         g_all[ilvl] += all; g_live[ilvl] += live; g_blk[ilvl] += live_blk;
