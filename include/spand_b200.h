@@ -71,6 +71,17 @@ int spand_cg(spand_tree* t, int N, const int* colptr, const int* rowind, const d
 int spand_gmres(spand_tree* t, int N, const int* colptr, const int* rowind, const double* val, const double* rhs,
                 double* x, int iters, int restart, double tol, int verb, double* seconds);
 
+/* geqp3(A, jpvt, tau) + choose_rank(diag(R), tol) + triu(R[:rank, :]) P^T on ONE dense matrix through the batched
+ * sparsification kernel                              src/util.cpp:383-394, :434-452, src/tree.cpp:1334-1335
+ * A: rows x cols column-major, given as nsrc column blocks of equal width (transposed != 0: every block is stored
+ * transposed, as the out-edges of a cluster are, src/tree.cpp:1211-1217). On return *rank is the truncated rank and, when
+ * *rank < rows, the first *rank rows of every block of R (same layout as A) hold triu(R[:rank, :]) P^T; V (rows x
+ * min(rows, cols), unit diagonal implicit) and tau hold the Householder reflectors. G / nthreads / in_smem / nb select
+ * the launch shape (cluster width, CTA size, panel in shared or global memory, block size); theta > 0 selects the
+ * hot / cold variant for global panels. Kernel-level parity tests drive every shape through this entry. */
+int spand_geqp3_truncated(int rows, int cols, const double* A, int nsrc, int transposed, double tol, int G,
+                          int nthreads, int in_smem, int nb, double theta, int* rank, double* R, double* V, double* tau);
+
 /* profiling aid: per-phase clock64 cycles of the RRQR kernel, non-zero only in -DSPAND_RRQR_TIMING builds */
 void spand_debug_rrqr_phases(unsigned long long* out48, int reset);
 

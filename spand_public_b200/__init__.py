@@ -27,7 +27,7 @@ EXPORTS = [
     "spand_create", "spand_destroy", "spand_last_error", "spand_set_tol", "spand_set_skip", "spand_set_symm_kind",
     "spand_set_scaling_kind", "spand_set_use_geo", "spand_set_verb", "spand_set_use_sparsify", "spand_set_device",
     "spand_set_coords", "spand_set_stop", "spand_partition", "spand_get_partition", "spand_get_perm", "spand_get_N",
-    "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_gmres", "spand_debug_rrqr_phases", "spand_nnz", "spand_get_stop",
+    "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_gmres", "spand_debug_rrqr_phases", "spand_geqp3_truncated", "spand_nnz", "spand_get_stop",
     "spand_get_nlevels", "spand_num_clusters", "spand_get_stats", "spand_log_fields", "spand_log_field_name",
     "spand_get_log", "spand_factorize_seconds", "spand_analyze_seconds", "spand_plan_analyze", "spand_plan_live_edges",
     "spand_plan_counts", "spand_get_cluster_layout", "spand_mg_setup", "spand_mg_get_handle", "spand_mg_set_peers",
@@ -121,6 +121,38 @@ def _csc(A):
     A.sort_indices()
     return (A.shape[0], np.ascontiguousarray(A.indptr, dtype=np.int32), np.ascontiguousarray(A.indices, dtype=np.int32),
             np.ascontiguousarray(A.data, dtype=np.float64))
+
+
+def geqp3_truncated(A, tol, nsrc=1, transposed=False, G=1, nthreads=256, in_smem=False, nb=8, theta=0.5):
+    """geqp3 + choose_rank + triu(R[:rank]) P^T of one dense matrix through the batched sparsification kernel
+    (reference src/util.cpp:383-452, src/tree.cpp:1334-1335). Returns (rank, AsnP or None when rank >= rows, V, tau)."""
+    A = np.asarray(A, dtype=np.float64)
+    rows, cols = A.shape
+    w = cols // nsrc
+    blocks = [A[:, i * w:(i + 1) * w] for i in range(nsrc)]
+    # device layout: block i column-major rows x w, or its transpose w x rows (column-major) for out-edges
+    flat = np.concatenate([(b.T if transposed else b).ravel(order="F") for b in blocks])
+    R = np.zeros_like(flat)
+    mn = min(rows, cols)
+    V = np.zeros(rows * mn)
+    tau = np.zeros(mn)
+    rank = C.c_int(0)
+    fn = lib().spand_geqp3_truncated
+    fn.argtypes = [_i, _i, _dp, _i, _i, _d, _i, _i, _i, _i, _d, C.POINTER(C.c_int), _dp, _dp, _dp]
+    rc = fn(rows, cols, np.ascontiguousarray(flat), nsrc, int(transposed), float(tol), G, nthreads, int(in_smem), nb,
+            float(theta), C.byref(rank), R, V, tau)
+    if rc != 0:
+        raise RuntimeError("spand_geqp3_truncated failed (see stderr)")
+    r = rank.value
+    out = None
+    if r < rows:
+        cols_out = []
+        for i in range(nsrc):
+            blk = R[i * w * rows:(i + 1) * w * rows]
+            blk = blk.reshape((w, rows), order="F").T if transposed else blk.reshape((rows, w), order="F")
+            cols_out.append(blk[:r, :])
+        out = np.concatenate(cols_out, axis=1)
+    return r, out, V.reshape((rows, mn), order="F"), tau
 
 
 # ---- host utilities (src/util.cpp, include/mmio.hpp counterparts) ----

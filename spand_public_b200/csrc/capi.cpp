@@ -1,4 +1,5 @@
 // C ABI of the B200 path (include/spand_b200.h). Thin: argument marshalling + error mapping only.
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -118,6 +119,14 @@ int spand_gmres(spand_tree* t, int N, const int* colptr, const int* rowind, cons
         it = t->t.gmres(from_csc(N, colptr, rowind, val), rhs, x, iters, restart, tol, verb != 0, seconds);
     });
     return rc == 0 ? it : -1;
+}
+int spand_geqp3_truncated(int rows, int cols, const double* A, int nsrc, int transposed, double tol, int G,
+                          int nthreads, int in_smem, int nb, double theta, int* rank, double* R, double* V, double* tau) {
+    static thread_local std::string err;
+    const int rc = spand::rrqr_single(rows, cols, A, nsrc, transposed, tol, G, nthreads, in_smem, nb, theta, rank, R, V,
+                                      tau, err);
+    if (rc != 0) fprintf(stderr, "spand_geqp3_truncated: %s\n", err.c_str());
+    return rc;
 }
 void spand_debug_rrqr_phases(unsigned long long* out48, int reset) { spand::rrqr_phase_cycles(out48, reset != 0); }
 long long spand_nnz(spand_tree* t) { return t->t.nnz(); }

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <string>
 
 #include "symbolic.hpp"
 
@@ -171,9 +172,15 @@ void launch_gemm_small(const GemmTask* t, int nt, const GemmContrib* c, cudaStre
 // One thread-block cluster of G CTAs per task. Launch shapes: (128 threads, G = 1, panel in shared memory),
 // (256 threads, G = 1..16, panel in distributed shared memory), (512 threads, G = 8, panel in global scratch).
 // smem = dynamic shared memory per CTA >= rrqr_smem_bytes(...) of every task of the launch.
+// theta > 0 (global panels only): hot / cold kernel, columns below theta x the pivot's norm at the start of a block
+// are refreshed once per block on the tensor cores instead of being swept every step; theta = 0: every column swept.
 void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int nthreads, bool in_smem,
-                 int smem, cudaStream_t st);
+                 int smem, cudaStream_t st, double theta = 0.0);
 int rrqr_max_smem();
+// one dense matrix through the batch kernels (kernel-level tests); see rrqr.cu
+int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transposed, double tol, int G, int nthreads,
+                int in_smem, int nb, double theta, int* rank_out, double* R_host, double* V_host, double* tau_host,
+                std::string& err);
 // debug builds (-DSPAND_RRQR_TIMING): accumulated clock64 cycles per kernel phase, [10] = CTAs counted
 void rrqr_phase_cycles(unsigned long long* out48, bool reset);
 size_t rrqr_smem_bytes(int rows, int maxcols, int G, int nb, int ld, bool in_smem);

@@ -1298,6 +1298,8 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         const int force_g = getenv("SPAND_RRQR_FORCE_G") ? atoi(getenv("SPAND_RRQR_FORCE_G")) : 0;
         const char* mode_env = getenv("SPAND_RRQR_MODE");  // "smem": cluster kernels with the panel in shared memory
         const bool smem_mode = mode_env != nullptr && std::string(mode_env) == "smem";
+        // hot / cold threshold of the global-panel kernel (rrqr.cu); 0 = sweep every column every step
+        const double qr_theta = getenv("SPAND_RRQR_THETA") ? atof(getenv("SPAND_RRQR_THETA")) : 0.5;
         const int stream_tmin = getenv("SPAND_RRQR_TMIN") ? atoi(getenv("SPAND_RRQR_TMIN")) : 48;
         const int stream_ctas = getenv("SPAND_RRQR_CTAS") ? atoi(getenv("SPAND_RRQR_CTAS")) : 1776;
         const long smem1_max = (getenv("SPAND_RRQR_SMEM1KB") ? atol(getenv("SPAND_RRQR_SMEM1KB")) : 200) * 1024;
@@ -1434,7 +1436,8 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                     cudaStream_t s = side_[nside % kSide];
                     CK(cudaStreamWaitEvent(s, ev_fork_, 0));
                     launch_rrqr(dt + b, (int)(e - b), ds, d_csize_, tol, G,
-                                mode == 0 ? 128 : ((mode == 1 || mode == 4) ? 256 : 512), mode != 2 && mode != 4, smem, s);
+                                mode == 0 ? 128 : ((mode == 1 || mode == 4) ? 256 : 512), mode != 2 && mode != 4, smem, s,
+                                qr_theta);
                     nside++;
                     lg.launches++;
                     family_launches[F_RRQR]++;

@@ -19,7 +19,7 @@ def run(n, d, L, tol, sharded, local_rank):
     t = S.Tree(L)
     t.set_device(local_rank)
     if sharded:
-        t.mg_init(dist, device=local_rank, arena_gb=float(os.environ.get("SPAND_MG_ARENA_GB", "4")))
+        t.mg_init(dist, device=local_rank, arena_gb=float(os.environ.get("SPAND_MG_ARENA_GB", "8")))
     t.set_tol(tol)
     t.set_use_geo(True)
     t.set_Xcoo(S.linspace_nd(n, d))
@@ -40,7 +40,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
     out = []
-    for (n, d, L, tol) in [(16, 3, 6, 1e-2), (32, 2, 6, 0.0), (24, 3, 8, 1e-2)]:
+    # the last one (64^3, 13 levels) is large enough for the streaming RRQR shapes (wavefronts of >= 48 panels > 300 KB)
+    for (n, d, L, tol) in [(16, 3, 6, 1e-2), (32, 2, 6, 0.0), (24, 3, 8, 1e-2), (64, 3, 13, 1e-2)]:
         sh = run(n, d, L, tol, True, local_rank)
         one = run(n, d, L, tol, False, local_rank)
         res = float(np.linalg.norm(sh["A"] @ sh["x"] - sh["b"]) / np.linalg.norm(sh["b"]))

@@ -1,0 +1,33 @@
+"""Rank parity rule shared by the GPU tests (north_star: "the same sparsified ranks, or ranks within +-1 at RRQR pivot
+ties, which are reported").
+
+Inputs are the write_stats triples (order id, original size, final rank) of both sides, same cluster order.
+A cluster's *original size* at a hierarchy level > 0 is the sum of its children's ranks, so a +-1 decision at a tie
+below changes the input of the clusters above it. The rule therefore is, for every cluster:
+    |rank_gpu - rank_ref| <= 1 + |size_gpu - size_ref|
+(leaf clusters have identical sizes, so there it is the plain +-1 rule), and at most `max_frac` of the clusters may
+differ at all. Every differing cluster is listed in the report."""
+import numpy as np
+
+
+def rank_parity(ids_g, size_g, rank_g, ids_o, size_o, rank_o, max_frac=0.03, label=""):
+    ids_g, ids_o = np.asarray(ids_g), np.asarray(ids_o)
+    assert np.array_equal(ids_g, ids_o), "cluster order ids differ: ordering / hierarchy parity is broken"
+    size_g, size_o = np.asarray(size_g, dtype=np.int64), np.asarray(size_o, dtype=np.int64)
+    rank_g, rank_o = np.asarray(rank_g, dtype=np.int64), np.asarray(rank_o, dtype=np.int64)
+    dr, ds = rank_g - rank_o, size_g - size_o
+    differ = np.nonzero(dr)[0]
+    bad = differ[np.abs(dr[differ]) > 1 + np.abs(ds[differ])]
+    lines = [f"[rank report{' ' + label if label else ''}] {len(differ)}/{len(dr)} clusters differ from the oracle "
+             f"(max |d rank| = {int(np.abs(dr).max()) if len(dr) else 0}, sum d rank = {int(dr.sum())}, "
+             f"clusters breaking the +-1 rule: {len(bad)})"]
+    for i in differ[:200]:
+        lines.append(f"   cluster {int(ids_g[i])}: size {int(size_g[i])} vs {int(size_o[i])}, "
+                     f"rank {int(rank_g[i])} vs {int(rank_o[i])}")
+    if len(differ) > 200:
+        lines.append(f"   ... {len(differ) - 200} more")
+    report = "\n".join(lines)
+    print("\n" + report)
+    assert len(bad) == 0, report
+    assert len(differ) <= max(2, max_frac * len(dr)), report
+    return len(differ)

@@ -11,6 +11,7 @@ import pytest
 
 import oracle_lib as O
 import spand_public_b200 as S
+from rank_parity import rank_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -118,10 +119,12 @@ def test_approx_residual_thresholds(n, d):
                 assert err <= (5e-12 if tol == 0.0 else tol * 2e2), (L, skip, tol, err)
 
 
-def _rank_report(g, o):
-    rg, ro = g.stats()[2], o.stats()[2]
-    diff = rg.astype(int) - ro.astype(int)
-    return diff, int((diff != 0).sum())
+def _rank_report(g, o, label=""):
+    """north_star rank rule (tests/rank_parity.py): equal, or +-1 at ties, every differing cluster listed."""
+    ig, sg, rg = g.stats()
+    io, so, ro = o.stats()
+    ndiff = rank_parity(ig, sg, rg, io, so, ro, label=label)
+    return rg.astype(int) - ro.astype(int), ndiff
 
 
 @pytest.mark.parametrize("n,d,L,tol,coords", [(32, 2, 5, 1e-2, "c1"), (30, 3, 8, 1e-2, "c2"), (64, 2, 8, 1e-3, "lin"),
@@ -146,10 +149,6 @@ def test_full_factorization_vs_oracle(n, d, L, tol, coords):
     g.factorize()
     o.factorize()
     diff, ndiff = _rank_report(g, o)
-    print(f"\n[rank report] n={n} d={d}: {ndiff}/{len(diff)} clusters differ from the oracle; "
-          f"max |diff| = {abs(diff).max()}, sum diff = {diff.sum()}")
-    # RRQR pivot ties: a few clusters may differ by a little; the bulk must be identical
-    assert ndiff <= max(2, 0.03 * len(diff))
     lg, lo = g.log(), o.log()
     assert np.allclose(lg["dofs_left_elim"], lo["dofs_left_elim"], rtol=0.02, atol=4)
     assert np.allclose(lg["dofs_left_spars"], lo["dofs_left_spars"], rtol=0.02, atol=4)
@@ -184,7 +183,6 @@ def test_every_rrqr_kernel_shape_matches_oracle(env, monkeypatch):
     g.factorize()
     o.factorize()
     diff, ndiff = _rank_report(g, o)
-    assert ndiff <= max(2, 0.03 * len(diff)), (env, ndiff, abs(diff).max())
     assert abs(g.nnz() - o.nnz()) <= 0.005 * o.nnz()
     b = S.random(A.shape[0], 2019)
     xg, xo = g.solve(b), o.solve(b)
@@ -404,7 +402,6 @@ def test_plu_full_factorization_vs_oracle(n, d, L, tol):
     g.factorize()
     o.factorize()
     diff, ndiff = _rank_report(g, o)
-    assert ndiff <= max(2, 0.03 * len(diff)), (ndiff, abs(diff).max())
     assert abs(g.nnz() - o.nnz()) <= 0.005 * o.nnz()
     lg, lo = g.log(), o.log()
     assert np.allclose(lg["dofs_left_spars"], lo["dofs_left_spars"], rtol=0.02, atol=4)
