@@ -77,13 +77,18 @@ int spand_gmres(spand_tree* t, int N, const int* colptr, const int* rowind, cons
  * transposed, as the out-edges of a cluster are, src/tree.cpp:1211-1217). On return *rank is the truncated rank and, when
  * *rank < rows, the first *rank rows of every block of R (same layout as A) hold triu(R[:rank, :]) P^T; V (rows x
  * min(rows, cols), unit diagonal implicit) and tau hold the Householder reflectors. G / nthreads / in_smem / nb select
- * the launch shape (cluster width, CTA size, panel in shared or global memory, block size); theta > 0 selects the
- * hot / cold variant for global panels. Kernel-level parity tests drive every shape through this entry. */
+ * the launch shape (cluster width, CTA size, panel in shared (1) or global (0) memory, block size); theta > 0 selects the
+ * hot / cold variant for global panels; in_smem = 2 selects the hot-set kernel (nb = capacity of its shared-memory hot
+ * set, in columns). Kernel-level parity tests drive every shape through this entry. */
 int spand_geqp3_truncated(int rows, int cols, const double* A, int nsrc, int transposed, double tol, int G,
                           int nthreads, int in_smem, int nb, double theta, int* rank, double* R, double* V, double* tau);
 
 /* profiling aid: per-phase clock64 cycles of the RRQR kernel, non-zero only in -DSPAND_RRQR_TIMING builds */
 void spand_debug_rrqr_phases(unsigned long long* out48, int reset);
+/* same for the hot-set kernel: [0] steps [1] blocks [2] blocks closed early [3] hot columns [4] unpivoted columns
+ * (both summed over the block starts) [5] threshold retries [6..9] clock64 cycles of the first CTA of every task:
+ * block boundary / hot loop / block end / gather + scatter */
+void spand_debug_hc2_stats(unsigned long long* out16, int reset);
 
 /* Tree::nnz / get_stop / get_nlevels                include/tree.h:158-160 */
 long long spand_nnz(spand_tree* t);

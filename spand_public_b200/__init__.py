@@ -27,7 +27,7 @@ EXPORTS = [
     "spand_create", "spand_destroy", "spand_last_error", "spand_set_tol", "spand_set_skip", "spand_set_symm_kind",
     "spand_set_scaling_kind", "spand_set_use_geo", "spand_set_verb", "spand_set_use_sparsify", "spand_set_device",
     "spand_set_coords", "spand_set_stop", "spand_partition", "spand_get_partition", "spand_get_perm", "spand_get_N",
-    "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_gmres", "spand_debug_rrqr_phases", "spand_geqp3_truncated", "spand_nnz", "spand_get_stop",
+    "spand_assemble", "spand_factorize", "spand_solve", "spand_solve_device", "spand_cg", "spand_gmres", "spand_debug_rrqr_phases", "spand_debug_hc2_stats", "spand_geqp3_truncated", "spand_nnz", "spand_get_stop",
     "spand_get_nlevels", "spand_num_clusters", "spand_get_stats", "spand_log_fields", "spand_log_field_name",
     "spand_get_log", "spand_factorize_seconds", "spand_analyze_seconds", "spand_plan_analyze", "spand_plan_live_edges",
     "spand_plan_counts", "spand_get_cluster_layout", "spand_mg_setup", "spand_mg_get_handle", "spand_mg_set_peers",
@@ -123,7 +123,7 @@ def _csc(A):
             np.ascontiguousarray(A.data, dtype=np.float64))
 
 
-def geqp3_truncated(A, tol, nsrc=1, transposed=False, G=1, nthreads=256, in_smem=False, nb=8, theta=0.5):
+def geqp3_truncated(A, tol, nsrc=1, transposed=False, G=1, nthreads=256, in_smem=False, nb=8, theta=0.5, hot=0):
     """geqp3 + choose_rank + triu(R[:rank]) P^T of one dense matrix through the batched sparsification kernel
     (reference src/util.cpp:383-452, src/tree.cpp:1334-1335). Returns (rank, AsnP or None when rank >= rows, V, tau)."""
     A = np.asarray(A, dtype=np.float64)
@@ -139,6 +139,8 @@ def geqp3_truncated(A, tol, nsrc=1, transposed=False, G=1, nthreads=256, in_smem
     rank = C.c_int(0)
     fn = lib().spand_geqp3_truncated
     fn.argtypes = [_i, _i, _dp, _i, _i, _d, _i, _i, _i, _i, _d, C.POINTER(C.c_int), _dp, _dp, _dp]
+    if hot > 0:  # hot-set kernel (rrqr_hc2.cu): in_smem = 2, nb carries the capacity of the hot set
+        in_smem, nb = 2, hot
     rc = fn(rows, cols, np.ascontiguousarray(flat), nsrc, int(transposed), float(tol), G, nthreads, int(in_smem), nb,
             float(theta), C.byref(rank), R, V, tau)
     if rc != 0:

@@ -128,6 +128,7 @@ int spand_geqp3_truncated(int rows, int cols, const double* A, int nsrc, int tra
     if (rc != 0) fprintf(stderr, "spand_geqp3_truncated: %s\n", err.c_str());
     return rc;
 }
+void spand_debug_hc2_stats(unsigned long long* out16, int reset) { spand::hc2_stats(out16, reset != 0); }
 void spand_debug_rrqr_phases(unsigned long long* out48, int reset) { spand::rrqr_phase_cycles(out48, reset != 0); }
 long long spand_nnz(spand_tree* t) { return t->t.nnz(); }
 int spand_get_stop(spand_tree* t) { return t->t.get_stop(); }

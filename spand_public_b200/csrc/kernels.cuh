@@ -107,6 +107,8 @@ struct QrTask {
     int L;        // lanes per column (power of two <= 32)
     int nb;       // block size <= QR_NB
     int in_smem;  // panel resident in (distributed) shared memory
+    int hcap;     // hot-set kernel (rrqr_hc2.cu): capacity of the shared-memory hot set, in columns
+    double* X;    // hot-set kernel, G > 1: exchange area of hc2_exchange_doubles(maxcols, G) doubles
 };
 
 struct CopyTask {
@@ -176,6 +178,16 @@ void launch_gemm_small(const GemmTask* t, int nt, const GemmContrib* c, cudaStre
 // are refreshed once per block on the tensor cores instead of being swept every step; theta = 0: every column swept.
 void launch_rrqr(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int nthreads, bool in_smem,
                  int smem, cudaStream_t st, double theta = 0.0);
+// Hot-set kernel (rrqr_hc2.cu): pivot search on a shared-memory copy of the columns that can win it, cold columns
+// refreshed once per block on the tensor cores. Panel in global memory (t.W), rows <= 640.
+constexpr int HC2_NB = 16;                 // largest block (reflectors between two refreshes)
+int hc2_row_pairs(int rows);               // template selector, 0: too tall for this kernel
+int hc2_threads(int rows);
+size_t hc2_smem_bytes(int rows, int maxcols, int G, int hcap, int nsrc);
+size_t hc2_exchange_doubles(int maxcols, int G);
+void launch_rrqr_hc2(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int row_pairs, int smem,
+                     double theta, cudaStream_t st);
+void hc2_stats(unsigned long long* out16, bool reset);  // -DSPAND_RRQR_TIMING builds
 int rrqr_max_smem();
 // one dense matrix through the batch kernels (kernel-level tests); see rrqr.cu
 int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transposed, double tol, int G, int nthreads,

@@ -27,6 +27,7 @@
 
 #include <cfloat>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -60,10 +61,15 @@ __device__ unsigned long long g_qr_phase[48];  // [shape class: smem panel / str
         for (int qi = 0; qi < 10; qi++) atomicAdd(&g_qr_phase[QT_CLASS * 16 + qi], qt_acc[qi]); \
         atomicAdd(&g_qr_phase[QT_CLASS * 16 + 10], 1ull);                                \
     }
+// hot / cold statistics: [11] steps, [12] blocks closed full, [13] blocks closed early, [14] hot columns at the
+// classifications, [15] unpivoted columns at the classifications
+#define QC(i, v) \
+    if (tid == 0) atomicAdd(&g_qr_phase[QT_CLASS * 16 + (i)], (unsigned long long)(v));
 #else
 #define QT_DECL
 #define QT(i)
 #define QT_FLUSH
+#define QC(i, v)
 #endif
 
 namespace {
@@ -1110,6 +1116,7 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc_kernel(const QrTask* __restr
             // a column that was not kept current in this block may beat the best hot candidate: close the block,
             // after which every column is current, and choose again among all of them
             close_block(j, k0);
+            QC(13, 1)
             k0 = k;
             j = 0;
             coldmax_l = -1.0;
@@ -1171,6 +1178,8 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc_kernel(const QrTask* __restr
             for (int w = 1; w < NW; w++) cm = fmax(cm, cmax_s[w]);
             coldmax_l = cm;
             nhot = nhot_s;
+            QC(14, nhot)
+            QC(15, min(ncl, cols - k))
         }
         // ---- pull the winner's reflector into column j of the block (zero outside [k, rows)) ----
         double* vj = Vs + (size_t)j * ldv;
@@ -1304,12 +1313,14 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc_kernel(const QrTask* __restr
         }
         if (k + 1 >= mn) break;  // factorization complete, rank = mn (every column is a pivot, or rank == rows)
         QT(3)  // sweep (warp 0's share)
+        QC(11, 1)
         j++;
         Cand lb;
         if (j == nbmax) {  // the block is full
             __syncthreads();
             QT(4)
             close_block(j, k0);
+            QC(12, 1)
             k0 = k + 1;
             j = 0;
             coldmax_l = -1.0;
@@ -1541,13 +1552,26 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
         while (ld % 16 != (2 * Ln) % 16) ld += 2;
     t.L = Ln;
     t.ld = ld;
-    const size_t smem = rrqr_smem_bytes(rows, cols, G, t.nb, ld, in_smem != 0);
+    const bool hc2 = in_smem == 2;  // hot-set kernel: panel in global memory, `nb` = capacity of the hot set
+    size_t smem = rrqr_smem_bytes(rows, cols, G, t.nb, ld, in_smem != 0);
+    if (hc2) {
+        if (hc2_row_pairs(rows) == 0) {
+            err = "rrqr_single: too many rows for the hot-set kernel";
+            return -1;
+        }
+        t.in_smem = 0;
+        t.hcap = std::max(1, std::min(nb, cols));
+        t.nb = HC2_NB;
+        t.L = 32;
+        t.ld = ld = (rows + 1) & ~1;
+        smem = hc2_smem_bytes(rows, cols, G, t.hcap, nsrc);
+    }
     if (smem > (size_t)rrqr_max_smem()) {
         err = "rrqr_single: shape does not fit the shared memory of one CTA";
         return -1;
     }
     const int mn = std::min(rows, cols);
-    double *dA = nullptr, *dW = nullptr, *dV = nullptr, *dtau = nullptr;
+    double *dA = nullptr, *dW = nullptr, *dV = nullptr, *dtau = nullptr, *dX = nullptr;
     int* dcs = nullptr;
     QrTask* dt = nullptr;
     QrSrc* ds = nullptr;
@@ -1575,13 +1599,88 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
         srcs[i].transposed = transposed;
     }
     cudaMemcpy(ds, srcs.data(), sizeof(QrSrc) * nsrc, cudaMemcpyHostToDevice);
+    if (hc2 && G > 1) {
+        cudaMalloc(&dX, sizeof(double) * hc2_exchange_doubles(cols, G));
+        cudaMemset(dX, 0, sizeof(double) * hc2_exchange_doubles(cols, G));
+    }
+    t.X = dX;
     t.W = dW;
     t.V = dV;
     t.tau = dtau;
     cudaMemcpy(dt, &t, sizeof(QrTask), cudaMemcpyHostToDevice);
+    if (const char* cps = getenv("SPAND_QR_COPIES")) {
+        // micro-benchmark hook (scripts/qr_bench.py): `copies` independent replicas of the task in ONE launch, as a
+        // wavefront of that many clusters would be; a warm-up launch on a first set of replicas, then the timed one
+        const int copies = std::max(1, atoi(cps));
+        const size_t wd = (size_t)ld * cols, vd = (size_t)rows * mn, xd = hc2 ? hc2_exchange_doubles(cols, G) : 0;
+        double *bA, *bW, *bV, *bT, *bX = nullptr;
+        int* bcs;
+        QrTask* bt;
+        QrSrc* bs;
+        const int tot = 2 * copies;
+        cudaMalloc(&bA, abytes * tot);
+        cudaMalloc(&bW, sizeof(double) * wd * tot);
+        cudaMalloc(&bV, sizeof(double) * vd * tot);
+        cudaMalloc(&bT, sizeof(double) * mn * tot);
+        if (xd) cudaMalloc(&bX, sizeof(double) * xd * tot);
+        cudaMalloc(&bcs, sizeof(int) * (nsrc + 1) * tot);
+        cudaMalloc(&bt, sizeof(QrTask) * tot);
+        cudaMalloc(&bs, sizeof(QrSrc) * nsrc * tot);
+        std::vector<QrTask> ht(tot, t);
+        std::vector<QrSrc> hs((size_t)nsrc * tot);
+        std::vector<int> hcs((size_t)(nsrc + 1) * tot);
+        for (int c = 0; c < tot; c++) {
+            cudaMemcpy(bA + (size_t)c * rows * cols, dA, abytes, cudaMemcpyDeviceToDevice);
+            ht[c].cluster = c * (nsrc + 1);
+            ht[c].src0 = c * nsrc;
+            ht[c].W = bW + wd * c;
+            ht[c].V = bV + vd * c;
+            ht[c].tau = bT + (size_t)mn * c;
+            ht[c].X = xd ? bX + xd * c : nullptr;
+            hcs[(size_t)c * (nsrc + 1)] = rows;
+            for (int i = 0; i < nsrc; i++) {
+                hs[(size_t)c * nsrc + i] = srcs[i];
+                hs[(size_t)c * nsrc + i].blk = bA + (size_t)c * rows * cols + (size_t)i * w * rows;
+                hs[(size_t)c * nsrc + i].nbr = c * (nsrc + 1) + 1 + i;
+                hcs[(size_t)c * (nsrc + 1) + 1 + i] = w;
+            }
+        }
+        cudaMemcpy(bt, ht.data(), sizeof(QrTask) * tot, cudaMemcpyHostToDevice);
+        cudaMemcpy(bs, hs.data(), sizeof(QrSrc) * nsrc * tot, cudaMemcpyHostToDevice);
+        cudaMemcpy(bcs, hcs.data(), sizeof(int) * (nsrc + 1) * tot, cudaMemcpyHostToDevice);
+        if (xd) cudaMemset(bX, 0, sizeof(double) * xd * tot);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        const int sm = (int)((smem + 1023) & ~(size_t)1023);
+        float ms = -1.f;
+        try {
+            for (int rep = 0; rep < 2; rep++) {
+                if (rep == 1) cudaEventRecord(e0, 0);
+                if (hc2) launch_rrqr_hc2(bt + rep * copies, copies, bs, bcs, tol, G, hc2_row_pairs(rows), sm, theta, 0);
+                else launch_rrqr(bt + rep * copies, copies, bs, bcs, tol, G, nthreads, in_smem != 0, sm, 0, theta);
+            }
+            cudaEventRecord(e1, 0);
+            const cudaError_t ee = cudaDeviceSynchronize();
+            if (ee != cudaSuccess) fprintf(stderr, "QRBENCH kernel error: %s\n", cudaGetErrorString(ee));
+            cudaEventElapsedTime(&ms, e0, e1);
+        } catch (std::exception& ex) {
+            fprintf(stderr, "QRBENCH launch error: %s\n", ex.what());
+        }
+        int r0 = -1;
+        cudaMemcpy(&r0, bcs + (size_t)copies * (nsrc + 1), sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "QRBENCH rows %d cols %d nsrc %d G %d copies %d mode %d nb/hot %d theta %.3f smem %d rank %d: %.3f ms\n",
+                rows, cols, nsrc, G, copies, in_smem, nb, theta, sm, r0, ms);
+        cudaFree(bA); cudaFree(bW); cudaFree(bV); cudaFree(bT); cudaFree(bX); cudaFree(bcs); cudaFree(bt); cudaFree(bs);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
     int rc = 0;
     try {
-        launch_rrqr(dt, 1, ds, dcs, tol, G, nthreads, in_smem != 0, (int)((smem + 1023) & ~(size_t)1023), 0, theta);
+        if (hc2)
+            launch_rrqr_hc2(dt, 1, ds, dcs, tol, G, hc2_row_pairs(rows), (int)((smem + 1023) & ~(size_t)1023), theta, 0);
+        else
+            launch_rrqr(dt, 1, ds, dcs, tol, G, nthreads, in_smem != 0, (int)((smem + 1023) & ~(size_t)1023), 0, theta);
     } catch (std::exception& ex) {
         err = ex.what();
         rc = -1;
@@ -1596,6 +1695,7 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
     }
     cudaFree(dA);
     cudaFree(dW);
+    cudaFree(dX);
     cudaFree(dV);
     cudaFree(dtau);
     cudaFree(dcs);

@@ -1300,6 +1300,16 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         const bool smem_mode = mode_env != nullptr && std::string(mode_env) == "smem";
         // hot / cold threshold of the global-panel kernel (rrqr.cu); 0 = sweep every column every step
         const double qr_theta = getenv("SPAND_RRQR_THETA") ? atof(getenv("SPAND_RRQR_THETA")) : 0.5;
+        // hot-set kernel (rrqr_hc2.cu) for panels in global memory: on unless SPAND_RRQR_HC2=0; per-CTA shared memory
+        // budget (two 256-thread CTAs per SM by default), CTAs wanted per wavefront, smallest panel it takes
+        const bool hc2_on = !getenv("SPAND_RRQR_HC2") || atoi(getenv("SPAND_RRQR_HC2")) != 0;
+        const long hc2_budget = (getenv("SPAND_HC2_KB") ? atol(getenv("SPAND_HC2_KB")) : 105) * 1024;
+        const long hc2_budget_big = (getenv("SPAND_HC2_BIGKB") ? atol(getenv("SPAND_HC2_BIGKB")) : 215) * 1024;
+        const int hc2_ctas = getenv("SPAND_HC2_CTAS") ? atoi(getenv("SPAND_HC2_CTAS")) : 296;  // twice the CTAs wanted
+        // hot set = columns within this factor of the largest norm (as far as the capacity goes)
+        const double hc2_theta = getenv("SPAND_HC2_THETA") ? atof(getenv("SPAND_HC2_THETA")) : 0.25;
+        const int hc2_hmax = getenv("SPAND_HC2_HMAX") ? atoi(getenv("SPAND_HC2_HMAX")) : 128;
+        const double hc2_min_bytes = (getenv("SPAND_HC2_MINKB") ? atof(getenv("SPAND_HC2_MINKB")) : 300.0) * 1024.0;
         const int stream_tmin = getenv("SPAND_RRQR_TMIN") ? atoi(getenv("SPAND_RRQR_TMIN")) : 48;
         const int stream_ctas = getenv("SPAND_RRQR_CTAS") ? atoi(getenv("SPAND_RRQR_CTAS")) : 1776;
         const long smem1_max = (getenv("SPAND_RRQR_SMEM1KB") ? atol(getenv("SPAND_RRQR_SMEM1KB")) : 200) * 1024;
@@ -1332,6 +1342,46 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 klass[i] = bucket_of(nd);
                 smem_need[i] = (int)nd;
                 continue;
+            }
+            // Hot-set kernel: the pivot search runs on a shared-memory copy of the few columns that can win it, the
+            // rest of the panel (global scratch) is refreshed once per block on the tensor cores. The capacity of the
+            // hot set and the smallest cluster width depend on the task alone (not on the wavefront or on how many GPUs
+            // share it), so the arithmetic of a task is the same however the launch is shaped.
+            const int rp = hc2_row_pairs(t.rows);
+            if (hc2_on && !smem_mode && !force_global && force_g == 0 && rp > 0 &&
+                8.0 * t.rows * t.maxcols >= hc2_min_bytes) {
+                const bool big = true;  // 512 threads, one CTA per SM
+                const long budget = big ? hc2_budget_big : hc2_budget;
+                const long ldv = (t.rows + 1) & ~1;
+                auto hcap_for = [&](int G) {  // largest hot set that fits the budget with this cluster width
+                    int h = (int)std::min<long>(hc2_hmax, std::max<long>(0, budget / (8 * ldv)));
+                    while (h > 0 && (long)hc2_smem_bytes(t.rows, t.maxcols, G, h, t.nsrc) > budget) h--;
+                    return h;
+                };
+                int gmin = 1;
+                while (gmin < 16 && hcap_for(gmin) < 32) gmin *= 2;
+                int hcap = std::min(std::min(hcap_for(gmin), hc2_hmax), t.maxcols);
+                if (hcap >= 8 || hcap == t.maxcols) {
+                    // cluster width: the wavefront should cover the SMs without exceeding them (one CTA per SM; a
+                    // 16-CTA cluster needs a whole GPC, of which there are 8: keep 16 for wavefronts of up to 6 tasks)
+                    int G = gmin;
+                    const int nown = std::max(1, per_color_own[task_color[i]]);
+                    while (G < 16 && nown * (2 * G) <= hc2_ctas / 2) G *= 2;
+                    if (G == 16 && nown > 6 && gmin <= 8) G = 8;
+                    int g = 0;
+                    while ((1 << g) < G) g++;
+                    t.hcap = hcap;
+                    t.nb = HC2_NB;
+                    t.L = 32;
+                    t.ld = (int)ldv;
+                    t.in_smem = 0;
+                    t.W = scratch_->alloc_n<double>((size_t)t.ld * t.maxcols);
+                    t.X = G > 1 ? scratch_->alloc_n<double>(hc2_exchange_doubles(t.maxcols, G)) : nullptr;
+                    nd = (long)hc2_smem_bytes(t.rows, t.maxcols, G, hcap, t.nsrc);
+                    klass[i] = (5 << 8) | (g << 4) | (rp <= 2 ? 0 : (rp <= 4 ? 1 : (rp <= 6 ? 2 : 3)));
+                    smem_need[i] = (int)nd;
+                    continue;
+                }
             }
             bool stream = !smem_mode && !force_global && force_g == 0 && per_color[task_color[i]] >= stream_tmin;
             if (stream && config(256, 1, true) <= smem1_max) stream = false;  // fits one CTA's shared memory
@@ -1435,9 +1485,41 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                     smem = (smem + 1023) & ~1023;
                     cudaStream_t s = side_[nside % kSide];
                     CK(cudaStreamWaitEvent(s, ev_fork_, 0));
+                    const bool trace = getenv("SPAND_QR_TRACE") != nullptr;  // debug: one line per launch, serialised
+                    cudaEvent_t tr0 = nullptr, tr1 = nullptr;
+                    if (trace) {
+                        CK(cudaDeviceSynchronize());
+                        CK(cudaEventCreate(&tr0));
+                        CK(cudaEventCreate(&tr1));
+                        CK(cudaEventRecord(tr0, s));
+                    }
+                    if (mode == 5) {
+                        static const int kRowPairs[4] = {2, 4, 6, 10};
+                        launch_rrqr_hc2(dt + b, (int)(e - b), ds, d_csize_, tol, G, kRowPairs[k & 15], smem, hc2_theta, s);
+                    } else
                     launch_rrqr(dt + b, (int)(e - b), ds, d_csize_, tol, G,
                                 mode == 0 ? 128 : ((mode == 1 || mode == 4) ? 256 : 512), mode != 2 && mode != 4, smem, s,
                                 qr_theta);
+                    if (trace) {
+                        CK(cudaEventRecord(tr1, s));
+                        CK(cudaEventSynchronize(tr1));
+                        float ms = 0;
+                        CK(cudaEventElapsedTime(&ms, tr0, tr1));
+                        int mr = 0, mc = 0, mh = 0;
+                        long sr = 0, sc = 0;
+                        for (size_t q = b; q < e; q++) {
+                            const QrTask& tq = sorted[q];
+                            mr = std::max(mr, tq.rows);
+                            mc = std::max(mc, tq.maxcols);
+                            mh = std::max(mh, tq.hcap);
+                            sr += tq.rows;
+                            sc += tq.maxcols;
+                        }
+                        fprintf(stderr, "QRTRACE lvl %d color %d mode %d G %d tasks %d smem %d rows max %d avg %ld cols max %d avg %ld hcap %d: %.3f ms\n",
+                                ilvl_, color, mode, G, (int)(e - b), smem, mr, sr / (long)(e - b), mc, sc / (long)(e - b), mh, ms);
+                        cudaEventDestroy(tr0);
+                        cudaEventDestroy(tr1);
+                    }
                     nside++;
                     lg.launches++;
                     family_launches[F_RRQR]++;

@@ -17,9 +17,10 @@ pytestmark = pytest.mark.gpu
 
 def _matrix(rows, cols, decay, seed):
     rng = np.random.default_rng(seed)
-    U, _ = np.linalg.qr(rng.standard_normal((rows, rows)))
-    Vt, _ = np.linalg.qr(rng.standard_normal((cols, rows)))
-    s = decay ** np.arange(rows)
+    r = min(rows, cols)
+    U, _ = np.linalg.qr(rng.standard_normal((rows, r)))
+    Vt, _ = np.linalg.qr(rng.standard_normal((cols, r)))
+    s = decay ** np.arange(r)
     A = (U * s) @ Vt.T
     # uneven column scaling: a realistic spread of column norms (near and far neighbours)
     return A * (0.05 + rng.random(cols))
@@ -54,6 +55,29 @@ SHAPES = [
     (400, 2400, 0.975, 1e-2, dict(G=16, nthreads=512, in_smem=False, nb=16, theta=0.5, nsrc=2)),
     (400, 2400, 0.975, 1e-2, dict(G=16, nthreads=512, in_smem=False, nb=16, theta=0.0)),
     (629, 2600, 0.985, 1e-2, dict(G=16, nthreads=512, in_smem=False, nb=16, theta=0.5)),
+    # hot-set kernel (rrqr_hc2.cu): capacities from "everything hot" down to 1, all cluster widths, all row classes
+    (60, 480, 0.85, 1e-2, dict(G=1, hot=64)),
+    (60, 480, 0.85, 1e-2, dict(G=1, hot=300)),
+    (61, 483, 0.85, 1e-2, dict(G=2, hot=24, nsrc=3, transposed=True)),
+    (61, 483, 0.85, 1e-2, dict(G=1, hot=1)),
+    (61, 483, 0.85, 1e-2, dict(G=4, hot=2)),
+    (150, 1200, 0.93, 1e-2, dict(G=1, hot=48)),
+    (150, 1200, 0.93, 1e-2, dict(G=4, hot=48, nsrc=4)),
+    (150, 1200, 0.93, 1e-2, dict(G=8, hot=16, theta=0.25)),
+    (150, 1200, 0.93, 1e-2, dict(G=2, hot=96, theta=0.9)),
+    (245, 1760, 0.96, 1e-2, dict(G=4, hot=40, nsrc=5, transposed=True)),
+    (245, 1760, 0.96, 1e-2, dict(G=16, hot=64)),
+    (256, 1000, 0.96, 1e-2, dict(G=2, hot=64)),
+    (257, 1000, 0.96, 1e-2, dict(G=2, hot=64)),
+    (383, 2400, 0.975, 1e-2, dict(G=8, hot=48)),
+    (400, 2400, 0.975, 1e-2, dict(G=16, hot=40, nsrc=2)),
+    (629, 2600, 0.985, 1e-2, dict(G=16, hot=24)),
+    (640, 1300, 0.985, 1e-2, dict(G=8, hot=20)),
+    (120, 90, 0.9, 1e-3, dict(G=1, hot=32)),      # cols < rows
+    (120, 90, 0.9, 0.0, dict(G=2, hot=32)),       # cols < rows, tol = 0: every column becomes a pivot
+    (64, 700, 0.999, 1e-2, dict(G=2, hot=32)),    # full rank: nothing happens
+    (100, 800, 0.9, 0.0, dict(G=2, hot=32)),      # tol = 0: full factorization
+    (100, 800, 0.5, 1e-6, dict(G=2, hot=32)),     # fast decay, small rank
     (120, 90, 0.9, 1e-3, dict(G=1, nthreads=256, in_smem=False, nb=8, theta=0.5)),     # cols < rows
     (64, 700, 0.999, 1e-2, dict(G=2, nthreads=256, in_smem=False, nb=8, theta=0.5)),   # full rank: nothing happens
     (100, 800, 0.9, 0.0, dict(G=2, nthreads=256, in_smem=False, nb=8, theta=0.5)),     # tol = 0: full factorization
@@ -90,6 +114,22 @@ def test_hot_cold_equals_full_sweep_on_tied_columns():
     A = np.concatenate([A, A], axis=1)
     r0, R0, _, _ = S.geqp3_truncated(A, 1e-2, G=2, nthreads=256, in_smem=False, nb=8, theta=0.0)
     r1, R1, _, _ = S.geqp3_truncated(A, 1e-2, G=2, nthreads=256, in_smem=False, nb=8, theta=0.5)
+    r2, R2, _, _ = S.geqp3_truncated(A, 1e-2, G=2, hot=16)
+    r3, R3, _, _ = S.geqp3_truncated(A, 1e-2, G=1, hot=200)
     rank_ref, R_ref, _ = _reference(A, 1e-2)
-    assert r0 == r1 == rank_ref
+    assert r0 == r1 == r2 == r3 == rank_ref
     assert np.abs(R1 - R0).max() <= 1e-11 * np.abs(R0).max()
+    assert np.abs(R2 - R0).max() <= 1e-11 * np.abs(R0).max()
+    assert np.abs(R3 - R0).max() <= 1e-11 * np.abs(R0).max()
+
+
+def test_hot_set_kernel_cluster_widths_agree():
+    """Sub-tree sharding changes the cluster width of a task and with it which columns are hot (applied reflector by
+    reflector) or cold (refreshed in compact-WY form): same pivots, results equal to rounding."""
+    A = _matrix(150, 1200, 0.93, 11)
+    ref = S.geqp3_truncated(A, 1e-2, G=1, hot=40)
+    for G in (2, 4, 8, 16):
+        out = S.geqp3_truncated(A, 1e-2, G=G, hot=40)
+        assert out[0] == ref[0]
+        assert np.abs(out[1] - ref[1]).max() <= 1e-12 * np.abs(ref[1]).max()
+        assert np.abs(out[2] - ref[2]).max() <= 1e-11
