@@ -40,7 +40,9 @@ for rows, cols, decay, nsrc, variants in CASES:
     if only and str(rows) not in only:
         continue
     A = matrix(rows, cols, decay, rows)
-    for copies, kw in variants:
+    for vi, (copies, kw) in enumerate(variants):
+        if os.environ.get("QRB_VARIANT") and int(os.environ["QRB_VARIANT"]) != vi:
+            continue
         os.environ["SPAND_QR_COPIES"] = str(copies)
         kw = dict(kw)
         kw.setdefault("theta", 0.25 if "hot" in kw else 0.5)

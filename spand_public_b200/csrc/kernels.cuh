@@ -108,7 +108,7 @@ struct QrTask {
     int nb;       // block size <= QR_NB
     int in_smem;  // panel resident in (distributed) shared memory
     int hcap;     // hot-set kernel (rrqr_hc2.cu): capacity of the shared-memory hot set, in columns
-    double* X;    // hot-set kernel, G > 1: exchange area of hc2_exchange_doubles(maxcols, G) doubles
+    double* X;    // hot-set kernel, G >= 8: exchange area of hc2_exchange_doubles(rows, G) doubles
 };
 
 struct CopyTask {
@@ -184,7 +184,7 @@ constexpr int HC2_NB = 16;                 // largest block (reflectors between 
 int hc2_row_pairs(int rows);               // template selector, 0: too tall for this kernel
 int hc2_threads(int rows);
 size_t hc2_smem_bytes(int rows, int maxcols, int G, int hcap, int nsrc);
-size_t hc2_exchange_doubles(int maxcols, int G);
+size_t hc2_exchange_doubles(int rows, int G);
 void launch_rrqr_hc2(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int row_pairs, int smem,
                      double theta, cudaStream_t st);
 void hc2_stats(unsigned long long* out16, bool reset);  // -DSPAND_RRQR_TIMING builds

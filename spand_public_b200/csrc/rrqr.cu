@@ -1599,9 +1599,9 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
         srcs[i].transposed = transposed;
     }
     cudaMemcpy(ds, srcs.data(), sizeof(QrSrc) * nsrc, cudaMemcpyHostToDevice);
-    if (hc2 && G > 1) {
-        cudaMalloc(&dX, sizeof(double) * hc2_exchange_doubles(cols, G));
-        cudaMemset(dX, 0, sizeof(double) * hc2_exchange_doubles(cols, G));
+    if (hc2 && G >= 8) {
+        cudaMalloc(&dX, sizeof(double) * hc2_exchange_doubles(rows, G));
+        cudaMemset(dX, 0, sizeof(double) * hc2_exchange_doubles(rows, G));
     }
     t.X = dX;
     t.W = dW;
@@ -1612,7 +1612,7 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
         // micro-benchmark hook (scripts/qr_bench.py): `copies` independent replicas of the task in ONE launch, as a
         // wavefront of that many clusters would be; a warm-up launch on a first set of replicas, then the timed one
         const int copies = std::max(1, atoi(cps));
-        const size_t wd = (size_t)ld * cols, vd = (size_t)rows * mn, xd = hc2 ? hc2_exchange_doubles(cols, G) : 0;
+        const size_t wd = (size_t)ld * cols, vd = (size_t)rows * mn, xd = hc2 ? hc2_exchange_doubles(rows, G) : 0;
         double *bA, *bW, *bV, *bT, *bX = nullptr;
         int* bcs;
         QrTask* bt;

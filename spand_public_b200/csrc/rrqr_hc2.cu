@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -99,6 +100,15 @@ __device__ __forceinline__ Cand warp_best(Cand b) {
 //   hdr[0] best squared norm, hdr[1] = (pos, col) of it, hdr[2] = (count, -) , hdr[3] = local coldmax,
 //   hdr[8 .. 8 + HC2_BINS / 2) histogram (two bins per double); then entry e: [n1, (col, pos)]
 constexpr int HC2_BINS = 64;
+// Doubles of the hot-column area of a CTA: the hot set itself, or (block end) the scratch of the cold refresh
+// followed by at least two TMA stages of one strip (8 columns) each.
+__host__ __device__ inline size_t hc2_scratch_doubles(int nw) {
+    return ((size_t)nw * (8 * (HC2_NB + 1) + HC2_NB * 8) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t hc2_hot_doubles(size_t ldv, int hcap, int nw) {
+    const size_t a = ldv * (size_t)hcap, b = hc2_scratch_doubles(nw) + 16 * ldv;
+    return a > b ? a : b;
+}
 __host__ __device__ inline size_t hc2_xstride(int cpce) { return 8 + HC2_BINS / 2 + 2 * (size_t)cpce; }
 
 __device__ __forceinline__ double pack2(int a, int b) {
@@ -107,6 +117,40 @@ __device__ __forceinline__ double pack2(int a, int b) {
 __device__ __forceinline__ void unpack2(double d, int& a, int& b) {
     a = __double2loint(d);
     b = __double2hiint(d);
+}
+
+// ---- TMA (1-D bulk copy) + mbarrier, raw PTX ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_global, unsigned bytes,
+                                            unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_global), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void team_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Warp-cooperative copy of an nf x ns tile with lanes along the fast index f: element (f, s) is produced by load(f, s)
@@ -150,7 +194,7 @@ struct HcRec {      // what a CTA tells the cluster about its candidate for the 
 template <int G, int NT, int NB, int RP, int MINB>
 __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __restrict__ tasks,
                                                             const QrSrc* __restrict__ srcs, int* csize, double tol,
-                                                            double theta2) {
+                                                            double theta2, int staged_refresh) {
     constexpr int NW = NT / 32;
     constexpr int FLD = NB + 1;
     constexpr int MT = NB / 8;
@@ -171,7 +215,11 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
     __shared__ HcRec rec[2][G];         // proposals of the cluster, double buffered on the proposal parity
     __shared__ int hist[HC2_BINS];      // own unpivoted columns by log2(level / norm^2), quarter-octave bins
     __shared__ int nh_s;
-    extern __shared__ __align__(16) double dsm[];
+    __shared__ __align__(8) unsigned long long mbar[16];  // "stage full" barriers of the cold refresh: [team][buffer]
+    extern __shared__ __align__(128) double dsm[];
+    if (threadIdx.x < 16) mbar_init(&mbar[threadIdx.x], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned tma_uses = 0;  // strips this warp's team has consumed so far (buffer and phase parity of the pipeline)
 
     // column offset of every source block inside the panel: widths read in parallel, prefix sum by the first warp
     // (an interface cluster of the upper levels has hundreds of neighbours: no serial chain of global loads)
@@ -179,7 +227,7 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
     {
         const int cpcm0 = (t.maxcols + G - 1) / G, cpce0 = (cpcm0 + 3) & ~3, hce0 = (t.hcap + 3) & ~3;
         const size_t ldv0 = (size_t)((rows + 1) & ~1);
-        const size_t hot0 = max(ldv0 * (size_t)t.hcap, (size_t)NW * (8 * FLD + NB * 8));
+        const size_t hot0 = hc2_hot_doubles(ldv0, t.hcap, NW);
         soff = (int*)(dsm + ldv0 * NB + hot0 + 2 * (size_t)hce0 + cpce0) + 2 * cpce0 + 2 * hce0;
     }
     for (int s = tid; s < t.nsrc; s += NT) soff[s + 1] = csize[src[s].nbr];
@@ -221,7 +269,7 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
 
     // H is dead between the write-back of the hot columns and the next block start: the per-warp scratch of the
     // cold refresh (F rows and Y = V^T W of one strip of 8 columns) lives in the same bytes
-    const size_t hbytes_d = max((size_t)ldv * HCAP, (size_t)NW * (8 * FLD + NB * 8));
+    const size_t hbytes_d = hc2_hot_doubles((size_t)ldv, HCAP, NW);
     double* Vs = dsm;                              // ldv x NB  reflectors of the open block (zero above the diagonal)
     double* H = Vs + (size_t)ldv * NB;             // ldv x HCAP  own hot columns, always current
     double* ftmp = H;                              // per warp: F rows of one strip of 8 cold columns
@@ -234,6 +282,9 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
     int* hcol = state + cpce;                      // local column index of every hot slot
     int* hpos = hcol + HCAPE;                      // its virtual position (kept live inside the block)
     double* slots = (double*)(soff + ((t.nsrc + 2) & ~1));  // 2 x ldv: own candidate reflectors (double buffered)
+    // Wide clusters: 16 CTAs pulling one reflector out of the winner's shared memory are serialised by its port
+    // (about 20 bytes per cycle); they exchange the candidates through L2 instead (t.X: G x 2 x ldv doubles)
+    constexpr bool XG = G >= 8;
     double* P = t.W + (size_t)c_lo * ld;           // local slab, column cl at P[cl * ld]
 
     cg::cluster_group cluster = cg::this_cluster();
@@ -273,7 +324,7 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
         const int buf = (seq++) & 1;
         my_slot = from_hot ? lb.col : -1;
         if (warp == 0) {
-            double* mine = slots + (size_t)buf * ldv;
+            double* mine = XG ? t.X + ((size_t)crank * 2 + buf) * ldv : slots + (size_t)buf * ldv;
             HcRec r;
             r.val = -1.0;
             r.beta = r.tau = 0.0;
@@ -373,7 +424,196 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
             if (col >= c_lo && col < c_hi) P[k0 + jj + (size_t)(col - c_lo) * ld] = beta_s[jj];
         }
         // ---- cold columns of the own slab: F = W^T V T, W -= V F^T, exact norms (FP64 tensor cores) ----
-        {
+        // Staged path: a strip of 8 columns is ONE contiguous piece of the slab; a TMA bulk copy brings it into a
+        // stage of the (now dead) hot-column area while the team works on the previous strip. A team of TW warps
+        // splits the rows of a strip: partial Y = V^T W per warp, summed in a fixed order, F = Y^T T, then every warp
+        // updates its rows from shared memory and stores them; the strip is read from L2 / HBM once.
+        const size_t strip_d = (size_t)8 * ld;         // doubles per stage
+        const size_t scr_d = hc2_scratch_doubles(NW);  // scratch in front of the stages
+        const int nst = hbytes_d > scr_d ? (int)((hbytes_d - scr_d) / strip_d) : 0;
+        if (nst >= 2 && staged_refresh) {
+            // teams of warps with a private ring of D stages each: D - 1 strips are in flight ahead of the one being
+            // worked on (the bytes in flight are what hides the L2 / HBM latency)
+            const int T = nst >= 12 ? 4 : (nst >= 6 ? 2 : 1);
+            const int D = min(4, nst / T);
+            const int TW = NW / T;
+            const int team = warp / TW, tw = warp % TW;
+            const int kend = k0 + jc;
+            const int g = lane >> 2, q = lane & 3;
+            double* stage = H + scr_d + (size_t)team * D * strip_d;
+            double* ypart = H + (size_t)team * TW * (NB * 8);          // [TW][NB * 8] partial Y tiles of the team
+            double* ysum = H + (size_t)NW * (NB * 8) + team * (NB * 8);  // [NB * 8] their sum
+            double* npart = H + (size_t)(NW + 4) * (NB * 8) + team * TW * 8;  // [TW][8] partial squared norms
+            unsigned long long* full = &mbar[team * 4];
+            const bool leader = tw == 0 && lane == 0;
+            fence_proxy_async();  // generic writes (hot columns, panel) before the async-proxy copies
+            __syncthreads();
+            auto cold_mask = [&](int first) {
+                unsigned m = 0;
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    if (first + c < ncl && pos[first + c] >= kend && !state[first + c]) m |= 1u << c;
+                return m;
+            };
+            auto next_cold = [&](int first, unsigned& m) {
+                m = 0;
+                for (; first < ncl; first += 8 * T) {
+                    m = cold_mask(first);
+                    if (m) return first;
+                }
+                return -1;
+            };
+            auto issue = [&](int first, int buf) {
+                const unsigned bytes = (unsigned)(min(8, ncl - first) * ld) * 8u;
+                mbar_expect_tx(&full[buf], bytes);
+                tma_load_1d(stage + (size_t)buf * strip_d, P + (size_t)first * ld, bytes, &full[buf]);
+            };
+            auto finish_norms = [&](int first, unsigned m) {  // one warp: partial norms of a strip in warp order
+                if (lane < 8 && ((m >> lane) & 1u)) {
+                    double acc = npart[lane];
+                    for (int w = 1; w < TW; w++) acc += npart[w * 8 + lane];
+                    nq1[first + lane] = acc;
+                }
+            };
+            unsigned cm = 0, cmp = 0;
+            int prev = -1, cur = -1;
+            int issued = 0, consumed = 0, scan = team * 8;
+            int fq[4];
+            unsigned mq[4];
+            const unsigned tma_base = tma_uses;
+            auto pump = [&]() {  // keep the ring full: strips consumed .. issued - 1 own a stage each
+                while (issued - consumed < D && scan < ncl) {
+                    unsigned m;
+                    const int f = next_cold(scan, m);
+                    if (f < 0) {
+                        scan = ncl;
+                        break;
+                    }
+                    scan = f + 8 * T;
+                    fq[issued & 3] = f;
+                    mq[issued & 3] = m;
+                    if (leader) issue(f, (int)((tma_base + issued) % D));
+                    issued++;
+                }
+            };
+            pump();
+            const int rstart = k0 & ~7;
+            while (consumed < issued) {
+                cur = fq[consumed & 3];
+                cm = mq[consumed & 3];
+                const unsigned use = tma_base + consumed;
+                const int buf = (int)(use % D);
+                mbar_wait(&full[buf], (use / D) & 1);
+                const double* sg = stage + (size_t)buf * strip_d;
+                // ---- partial Y = V^T W over the 8-row groups of this warp ----
+                double y0[MT][2], y1[MT][2];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) y0[mt][0] = y0[mt][1] = y1[mt][0] = y1[mt][1] = 0.0;
+                for (int r = rstart + 8 * tw; r < ldv; r += 8 * TW) {
+                    const int rr = r + 2 * q;
+                    const bool rok = rr < ldv;  // loads are predicated per lane, the mma is issued by the whole warp
+                    double2 b2 = make_double2(0.0, 0.0);
+                    if (rok) b2 = *reinterpret_cast<const double2*>(sg + (size_t)g * ld + rr);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        if (mt * 8 < jc) {  // uniform
+                            const int tt = mt * 8 + g;
+                            double2 a2 = make_double2(0.0, 0.0);
+                            if (tt < jc && rok) a2 = *reinterpret_cast<const double2*>(Vs + rr + (size_t)tt * ldv);
+                            dmma_f64(y0[mt][0], y0[mt][1], a2.x, b2.x);
+                            dmma_f64(y1[mt][0], y1[mt][1], a2.y, b2.y);
+                        }
+                    }
+                }
+                {
+                    double* yw = ypart + (size_t)tw * NB * 8;
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        yw[(mt * 8 + g) * 8 + 2 * q] = y0[mt][0] + y1[mt][0];
+                        yw[(mt * 8 + g) * 8 + 2 * q + 1] = y0[mt][1] + y1[mt][1];
+                    }
+                }
+                team_barrier(1 + team, TW * 32);  // B1: partial tiles complete; the stage of the previous strip is free
+                pump();
+                if (tw == TW - 1 && prev >= 0) finish_norms(prev, cmp);
+                // the team sums the partial tiles (each warp a slice, partials added in warp order)
+                for (int o = tw * 32 + lane; o < NB * 8; o += TW * 32) {
+                    double acc = ypart[o];
+                    for (int w = 1; w < TW; w++) acc += ypart[(size_t)w * NB * 8 + o];
+                    ysum[o] = acc;
+                }
+                team_barrier(1 + team, TW * 32);  // B2
+                // B fragments of the update: F(col g, tt) = sum_{t <= tt} Y(t, g) T(t, tt), tt = 4 kk + q
+                double bf[NB / 4];
+#pragma unroll
+                for (int kk = 0; kk < NB / 4; kk++) bf[kk] = 0.0;
+                for (int tr = 0; tr < jc; tr++) {
+                    const double yv = ysum[tr * 8 + g];
+#pragma unroll
+                    for (int kk = 0; kk < NB / 4; kk++) {
+                        const int tt = kk * 4 + q;
+                        if (tt >= tr && tt < jc) bf[kk] = fma(yv, Ts[tr * NB + tt], bf[kk]);
+                    }
+                }
+                // ---- W -= V F^T on the 8-row groups of this warp, from the stage, stored to the panel ----
+                const bool actA = (cm >> (2 * q)) & 1u, actB = (cm >> (2 * q + 1)) & 1u;
+                const double* sA = sg + (size_t)(2 * q) * ld;
+                const double* sB = sA + ld;
+                double* colA = P + (size_t)(cur + 2 * q) * ld;
+                double* colB = colA + ld;
+                double nA = 0.0, nB = 0.0;
+                for (int r = rstart + 8 * tw; r < rows; r += 16 * TW) {  // two groups in flight
+                    double cA[2], cB[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int row = r + 8 * TW * h + g;
+                        const bool in = row >= k0 && row < rows;
+                        cA[h] = in ? sA[row] : 0.0;
+                        cB[h] = in ? sB[row] : 0.0;
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < NB / 4; kk++) {
+                        const int tt = kk * 4 + q;
+                        if (kk * 4 < jc) {  // uniform
+#pragma unroll
+                            for (int h = 0; h < 2; h++) {
+                                const int row = r + 8 * TW * h + g;
+                                const double av = (tt < jc && row < ldv) ? -Vs[row + (size_t)tt * ldv] : 0.0;
+                                dmma_f64(cA[h], cB[h], av, bf[kk]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int row = r + 8 * TW * h + g;
+                        const bool in = row >= k0 && row < rows;
+                        if (actA && in) {
+                            colA[row] = cA[h];
+                            if (row >= kend) nA = fma(cA[h], cA[h], nA);
+                        }
+                        if (actB && in) {
+                            colB[row] = cB[h];
+                            if (row >= kend) nB = fma(cB[h], cB[h], nB);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 4; o <= 16; o <<= 1) {
+                    nA += __shfl_xor_sync(FULL, nA, o);
+                    nB += __shfl_xor_sync(FULL, nB, o);
+                }
+                if (g == 0) {
+                    npart[tw * 8 + 2 * q] = nA;
+                    npart[tw * 8 + 2 * q + 1] = nB;
+                }
+                prev = cur;
+                cmp = cm;
+                consumed++;
+            }
+            tma_uses += consumed;
+            team_barrier(1 + team, TW * 32);
+            if (tw == TW - 1 && prev >= 0) finish_norms(prev, cmp);
+        } else {
             const int kend = k0 + jc;
             const int g = lane >> 2, q = lane & 3;
             double* yw = ysm + (size_t)warp * NB * 8;
@@ -658,9 +898,14 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
         // ---- the winner's reflector becomes column j of the block (zero outside [k, rows)) ----
         double* vj = Vs + (size_t)j * ldv;
         {
-            const double* wv = slots + (size_t)par * ldv;
-            if constexpr (G > 1) wv = cluster.map_shared_rank(wv, wi);
-            for (int i = tid; i < ldv; i += NT) vj[i] = (i >= k && i < rows) ? wv[i] : 0.0;
+            if constexpr (XG) {
+                const double* wv = t.X + ((size_t)wi * 2 + par) * ldv;
+                for (int i = tid; i < ldv; i += NT) vj[i] = (i >= k && i < rows) ? __ldcg(wv + i) : 0.0;
+            } else {
+                const double* wv = slots + (size_t)par * ldv;
+                if constexpr (G > 1) wv = cluster.map_shared_rank(wv, wi);
+                for (int i = tid; i < ldv; i += NT) vj[i] = (i >= k && i < rows) ? wv[i] : 0.0;
+            }
             if (tid == 0) {
                 tau_s[j] = tau;
                 beta_s[j] = beta;
@@ -675,60 +920,86 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
         {
             const int kpair = k >> 1;
             const double2* v2 = reinterpret_cast<const double2*>(vj);
-            for (int s = warp; s < nh; s += NW) {
-                int p = hpos[s];
-                if (s == ps) {
-                    if (lane == 0) hpos[s] = k;
-                    continue;
+            constexpr int NU = RP <= 6 ? 2 : 1;  // hot columns a warp works on at once (independent shuffle chains)
+            for (int s0 = warp; s0 < nh; s0 += NU * NW) {
+                int sl[NU], p[NU];
+                bool act[NU];
+                double2* cp[NU];
+                double ck[NU], w[NU], q[NU];
+                double2 c[NU][RP];
+#pragma unroll
+                for (int u = 0; u < NU; u++) {
+                    sl[u] = s0 + u * NW;
+                    act[u] = sl[u] < nh;
+                    p[u] = act[u] ? hpos[sl[u]] : -1;
+                    if (act[u] && sl[u] == ps) {
+                        if (lane == 0) hpos[sl[u]] = k;
+                        act[u] = false;
+                    }
+                    if (act[u] && p[u] == k) {  // virtual swap: the column at position k takes the pivot's old place
+                        p[u] = win.pos;
+                        if (lane == 0) hpos[sl[u]] = p[u];
+                    }
+                    if (p[u] < k) act[u] = false;  // pivoted earlier in this block
+                    cp[u] = reinterpret_cast<double2*>(H + (size_t)(act[u] ? sl[u] : 0) * ldv);
+                    ck[u] = act[u] ? H[(size_t)sl[u] * ldv + k] : 0.0;
+                    w[u] = 0.0;
                 }
-                if (p == k) {  // virtual swap: the column at position k takes the pivot's old place
-                    p = win.pos;
-                    if (lane == 0) hpos[s] = p;
-                }
-                if (p < k) continue;  // pivoted earlier in this block
-                double2* cp = reinterpret_cast<double2*>(H + (size_t)s * ldv);
-                const double ck = H[(size_t)s * ldv + k];
-                double2 c[RP];
-                double w = 0.0;
+                if (!act[0] && !act[NU - 1]) continue;
 #pragma unroll
                 for (int m = 0; m < RP; m++) {
                     const int pi = lane + 32 * m;
-                    c[m] = make_double2(0.0, 0.0);
-                    if (pi >= kpair && pi < npair) {
-                        c[m] = cp[pi];
-                        const double2 vv = v2[pi];
-                        w = fma(c[m].x, vv.x, w);
-                        w = fma(c[m].y, vv.y, w);
+                    const bool in = pi >= kpair && pi < npair;
+                    const double2 vv = in ? v2[pi] : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int u = 0; u < NU; u++) {
+                        c[u][m] = (in && act[u]) ? cp[u][pi] : make_double2(0.0, 0.0);
+                        w[u] = fma(c[u][m].x, vv.x, w[u]);
+                        w[u] = fma(c[u][m].y, vv.y, w[u]);
                     }
                 }
-                w = warp_sum(w);
-                const double f = tau * w;
-                double q = 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int u = 0; u < NU; u++) w[u] += __shfl_xor_sync(FULL, w[u], o);
+                }
+                double f[NU];
+#pragma unroll
+                for (int u = 0; u < NU; u++) {
+                    f[u] = tau * w[u];
+                    q[u] = 0.0;
+                }
 #pragma unroll
                 for (int m = 0; m < RP; m++) {
                     const int pi = lane + 32 * m;
-                    if (pi >= kpair && pi < npair) {
-                        const double2 vv = v2[pi];
-                        c[m].x = fma(-f, vv.x, c[m].x);
-                        c[m].y = fma(-f, vv.y, c[m].y);
-                        cp[pi] = c[m];
-                        const int r0 = 2 * pi;
-                        if (r0 > k) q = fma(c[m].x, c[m].x, q);
-                        if (r0 + 1 > k) q = fma(c[m].y, c[m].y, q);
+                    const bool in = pi >= kpair && pi < npair;
+                    const double2 vv = in ? v2[pi] : make_double2(0.0, 0.0);
+                    const int r0 = 2 * pi;
+#pragma unroll
+                    for (int u = 0; u < NU; u++) {
+                        c[u][m].x = fma(-f[u], vv.x, c[u][m].x);
+                        c[u][m].y = fma(-f[u], vv.y, c[u][m].y);
+                        if (in && act[u]) cp[u][pi] = c[u][m];
+                        if (r0 > k) q[u] = fma(c[u][m].x, c[u][m].x, q[u]);
+                        if (r0 + 1 > k) q[u] = fma(c[u][m].y, c[u][m].y, q[u]);
                     }
                 }
-                const double ak = ck - f;  // row k of the updated column (v_k = 1)
-                const double n1 = hn1[s];
-                double newn = 0.0;
-                if (n1 != 0.0) {
-                    newn = fmax(0.0, n1 - ak * ak);
-                    if (newn <= tol3z * hn2[s]) {  // dlaqps / dlaqp2 safeguard: exact norm of the updated column
-                        newn = warp_sum(q);
-                        if (lane == 0) hn2[s] = newn;
+#pragma unroll
+                for (int u = 0; u < NU; u++) {
+                    if (!act[u]) continue;  // warp-uniform
+                    const double ak = ck[u] - f[u];  // row k of the updated column (v_k = 1)
+                    const double n1 = hn1[sl[u]];
+                    double newn = 0.0;
+                    if (n1 != 0.0) {
+                        newn = fmax(0.0, n1 - ak * ak);
+                        if (newn <= tol3z * hn2[sl[u]]) {  // dlaqps / dlaqp2 safeguard: exact norm of the updated column
+                            newn = warp_sum(q[u]);
+                            if (lane == 0) hn2[sl[u]] = newn;
+                        }
                     }
+                    if (lane == 0) hn1[sl[u]] = newn;
+                    if (better(newn, p[u], best.val, best.pos)) best = Cand{newn, p[u], sl[u]};
                 }
-                if (lane == 0) hn1[s] = newn;
-                if (better(newn, p, best.val, best.pos)) best = Cand{newn, p, s};
             }
         }
         j++;
@@ -812,7 +1083,10 @@ void launch_one_hc2(const QrTask* t, int nt, const QrSrc* s, int* csize, double 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, t, s, csize, tol, theta2);
+    // SPAND_HC2_TMA=1: cold refresh through TMA-staged strips shared by teams of warps (slower than the direct
+    // per-warp path on the shapes measured so far, kept selectable: profiles/r2_rrqr.md)
+    static const int staged = getenv("SPAND_HC2_TMA") ? atoi(getenv("SPAND_HC2_TMA")) : 0;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, t, s, csize, tol, theta2, staged);
     if (err != cudaSuccess)
         throw std::runtime_error(std::string("rrqr (hot set) launch failed (G=") + std::to_string(G) + ", threads=" +
                                  std::to_string(NT) + ", smem=" + std::to_string(smem) + "): " + cudaGetErrorString(err));
@@ -848,17 +1122,16 @@ size_t hc2_smem_bytes(int rows, int maxcols, int G, int hcap, int nsrc) {
     const size_t hcape = ((size_t)hcap + 3) & ~(size_t)3;
     const size_t nw = hc2_threads(rows) / 32;
     // the scratch of the cold refresh (per warp: F rows + Y tile of one strip) aliases the hot columns
-    const size_t hot = std::max(ldv * (size_t)hcap, nw * (8 * (HC2_NB + 1) + HC2_NB * 8));
+    const size_t hot = hc2_hot_doubles(ldv, hcap, (int)nw);
     const size_t doubles = ldv * HC2_NB + hot + 2 * hcape + cpce;
     // + source offsets (ints) + two candidate reflector slots
     return doubles * sizeof(double) + (2 * cpce + 2 * hcape + (((size_t)nsrc + 2) & ~(size_t)1)) * sizeof(int) +
            2 * ldv * sizeof(double);
 }
 
-size_t hc2_exchange_doubles(int maxcols, int G) {  // the CTAs of a cluster talk through distributed shared memory only
-    (void)maxcols;
-    (void)G;
-    return 0;
+size_t hc2_exchange_doubles(int rows, int G) {  // candidate reflectors of wide clusters travel through L2
+    const size_t ldv = ((size_t)rows + 1) & ~(size_t)1;
+    return G >= 8 ? (size_t)G * 2 * ldv : 0;
 }
 
 void hc2_stats(unsigned long long* out16, bool reset) {

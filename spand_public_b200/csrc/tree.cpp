@@ -1303,11 +1303,14 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         // hot-set kernel (rrqr_hc2.cu) for panels in global memory: on unless SPAND_RRQR_HC2=0; per-CTA shared memory
         // budget (two 256-thread CTAs per SM by default), CTAs wanted per wavefront, smallest panel it takes
         const bool hc2_on = !getenv("SPAND_RRQR_HC2") || atoi(getenv("SPAND_RRQR_HC2")) != 0;
+        const bool force_hc2 = getenv("SPAND_RRQR_HC2") && atoi(getenv("SPAND_RRQR_HC2")) == 2;  // every eligible panel
+        const int hc2_tmin = getenv("SPAND_HC2_TMIN") ? atoi(getenv("SPAND_HC2_TMIN")) : 48;
+        const int hc2_maxrows = getenv("SPAND_HC2_MAXROWS") ? atoi(getenv("SPAND_HC2_MAXROWS")) : 256;
         const long hc2_budget = (getenv("SPAND_HC2_KB") ? atol(getenv("SPAND_HC2_KB")) : 105) * 1024;
         const long hc2_budget_big = (getenv("SPAND_HC2_BIGKB") ? atol(getenv("SPAND_HC2_BIGKB")) : 215) * 1024;
         const int hc2_ctas = getenv("SPAND_HC2_CTAS") ? atoi(getenv("SPAND_HC2_CTAS")) : 296;  // twice the CTAs wanted
         // hot set = columns within this factor of the largest norm (as far as the capacity goes)
-        const double hc2_theta = getenv("SPAND_HC2_THETA") ? atof(getenv("SPAND_HC2_THETA")) : 0.25;
+        const double hc2_theta = getenv("SPAND_HC2_THETA") ? atof(getenv("SPAND_HC2_THETA")) : 0.5;
         const int hc2_hmax = getenv("SPAND_HC2_HMAX") ? atoi(getenv("SPAND_HC2_HMAX")) : 128;
         const double hc2_min_bytes = (getenv("SPAND_HC2_MINKB") ? atof(getenv("SPAND_HC2_MINKB")) : 300.0) * 1024.0;
         const int stream_tmin = getenv("SPAND_RRQR_TMIN") ? atoi(getenv("SPAND_RRQR_TMIN")) : 48;
@@ -1316,6 +1319,8 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         const double l2_budget = (getenv("SPAND_RRQR_L2MB") ? atof(getenv("SPAND_RRQR_L2MB")) : 1.0e5) * 1048576.0;
         // panels smaller than this stay in (distributed) shared memory even in wide wavefronts
         const double stream_min_bytes = (getenv("SPAND_RRQR_MINKB") ? atof(getenv("SPAND_RRQR_MINKB")) : 300.0) * 1024.0;
+        std::vector<double> color_work(std::max(1, ncolors), 0.0);  // rows x columns of this rank's tasks, per wavefront
+        for (size_t i = 0; i < nq; i++) color_work[task_color[i]] += (double)tasks[i].rows * tasks[i].maxcols;
         for (size_t i = 0; i < nq; i++) {
             QrTask& t = tasks[i];
             int mn = std::max(1, std::min(t.rows, t.maxcols));
@@ -1348,7 +1353,11 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             // hot set and the smallest cluster width depend on the task alone (not on the wavefront or on how many GPUs
             // share it), so the arithmetic of a task is the same however the launch is shaped.
             const int rp = hc2_row_pairs(t.rows);
-            if (hc2_on && !smem_mode && !force_global && force_g == 0 && rp > 0 &&
+            // Measured on C4 (profiles/r2_rrqr.md): it wins on the wide wavefronts of the middle levels (hundreds of
+            // panels of up to 256 rows, one CTA each); the few tall panels of the upper levels are still served faster
+            // by the cluster kernel that keeps all columns current.
+            const bool hc2_fits = force_hc2 || (per_color_own[task_color[i]] >= hc2_tmin && t.rows <= hc2_maxrows);
+            if (hc2_on && hc2_fits && !smem_mode && !force_global && force_g == 0 && rp > 0 &&
                 8.0 * t.rows * t.maxcols >= hc2_min_bytes) {
                 const bool big = true;  // 512 threads, one CTA per SM
                 const long budget = big ? hc2_budget_big : hc2_budget;
@@ -1364,9 +1373,12 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 if (hcap >= 8 || hcap == t.maxcols) {
                     // cluster width: the wavefront should cover the SMs without exceeding them (one CTA per SM; a
                     // 16-CTA cluster needs a whole GPC, of which there are 8: keep 16 for wavefronts of up to 6 tasks)
+                    // its share of the SMs is its share of the work of the wavefront (rows x columns: the big panels
+                    // of a wavefront are its critical path), rounded down to a power of two
                     int G = gmin;
                     const int nown = std::max(1, per_color_own[task_color[i]]);
-                    while (G < 16 && nown * (2 * G) <= hc2_ctas / 2) G *= 2;
+                    const double share = (double)t.rows * t.maxcols / std::max(1.0, color_work[task_color[i]]);
+                    while (G < 16 && 2 * G <= share * (hc2_ctas / 2)) G *= 2;
                     if (G == 16 && nown > 6 && gmin <= 8) G = 8;
                     int g = 0;
                     while ((1 << g) < G) g++;
@@ -1376,7 +1388,7 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                     t.ld = (int)ldv;
                     t.in_smem = 0;
                     t.W = scratch_->alloc_n<double>((size_t)t.ld * t.maxcols);
-                    t.X = G > 1 ? scratch_->alloc_n<double>(hc2_exchange_doubles(t.maxcols, G)) : nullptr;
+                    t.X = G >= 8 ? scratch_->alloc_n<double>(hc2_exchange_doubles(t.rows, G)) : nullptr;
                     nd = (long)hc2_smem_bytes(t.rows, t.maxcols, G, hcap, t.nsrc);
                     klass[i] = (5 << 8) | (g << 4) | (rp <= 2 ? 0 : (rp <= 4 ? 1 : (rp <= 6 ? 2 : 3)));
                     smem_need[i] = (int)nd;
