@@ -33,6 +33,8 @@ CONFIGS = {
     "c2": (30, 3, 8, 1e-2, "3D Laplacian 30^3 (mats/neglapl_3_30.mm), tol 1e-2, 8 levels"),
     "c3": (1024, 2, 14, 1e-3, "2D Laplacian 1024^2, tol 1e-3, 14 levels"),
     "c4": (128, 3, 16, 1e-2, "3D Laplacian 128^3, tol 1e-2, 16 levels"),
+    "s96": (96, 3, 15, 1e-2, "3D Laplacian 96^3, tol 1e-2, 15 levels"),
+    "s80": (80, 3, 14, 1e-2, "3D Laplacian 80^3, tol 1e-2, 14 levels"),
     "s64": (64, 3, 13, 1e-2, "3D Laplacian 64^3, tol 1e-2, 13 levels"),
     "s48": (48, 3, 12, 1e-2, "3D Laplacian 48^3, tol 1e-2, 12 levels"),
     # config C5: non-symmetric, GEN + PLU, GMRES(100); 16 = round(log2(N / 64)) (tests/spaND.cpp:137-140)
@@ -44,6 +46,105 @@ CONFIGS = {
                              "tol 1e-2, 11 levels"),
 }
 ANISO = ("c5", "c5s", "a48")  # matrix family of these configurations: S.aniso_convdiff, GEN / PLU / GMRES
+
+
+# ---- inputs of the CPU (reference) arm, generated with numpy / scipy only: that process maps oracle/_build/liboracle.so
+# and nothing of the product (the generators are checked against spand_util_* in tests/test_bench_inputs.py) ----
+def np_neglapl(n, d):
+    """mats/neglapl_d_n.mm: Dirichlet stencil Laplacian, diagonal 2 d, dof index x + n y (+ n^2 z)."""
+    import scipy.sparse as sp
+    T = sp.diags([-np.ones(n - 1), np.zeros(n), -np.ones(n - 1)], [-1, 0, 1], format="csc")
+    I = sp.identity(n, format="csc")
+    A = None
+    for k in range(d):
+        term = None
+        for j in range(d):
+            M = T if (d - 1 - j) == k else I
+            term = M if term is None else sp.kron(term, M, format="csc")
+        A = term if A is None else A + term
+    A = (A + 2 * d * sp.identity(n**d, format="csc")).tocsc()
+    A.sort_indices()
+    return A
+
+
+def np_linspace_nd(n, d):
+    """src/util.cpp:488-517: first coordinate slowest."""
+    X = np.zeros((d, n**d))
+    r = np.arange(n**d)
+    for k in range(d - 1, -1, -1):
+        X[k] = r % n
+        r = r // n
+    return X
+
+
+def np_random(size, seed):
+    """src/util.cpp:549-558: std::mt19937(seed) + uniform_real_distribution<double>(-1, 1) (two 32-bit draws each)."""
+    raw = np.random.RandomState(seed).randint(0, 2**32, size=2 * size, dtype=np.uint64)
+    u = (raw[0::2].astype(np.float64) + raw[1::2].astype(np.float64) * 4294967296.0) / 18446744073709551616.0
+    return -1.0 + 2.0 * u
+
+
+def np_symmetric_graph(A):
+    """src/util.cpp:47-63: |A| + |A^T| + I."""
+    import scipy.sparse as sp
+    G = (abs(A) + abs(A).T + sp.identity(A.shape[0], format="csc")).tocsc()
+    G.sort_indices()
+    return G
+
+
+def np_aniso_convdiff(n):
+    """Config C5: 7-point finite volumes of -div(kappa diag(1, .1, .01) grad u) + (1,1,1).grad u,
+    kappa = 10^(sin 2 pi x sin 2 pi y sin 2 pi z) at cell centres, harmonic face averages, first-order upwind."""
+    import scipy.sparse as sp
+    h = 1.0 / n
+    c = (np.arange(n) + 0.5) * h
+    sx = np.sin(2 * np.pi * c)
+    kap = 10.0 ** (sx[None, None, :] * sx[None, :, None] * sx[:, None, None])  # [k, j, i]
+    eps = (1.0, 1e-1, 1e-2)
+    N = n**3
+    idx = np.arange(N).reshape(n, n, n)  # row = i + n j + n^2 k
+    diag = np.zeros((n, n, n))
+    rows, cols, vals = [], [], []
+    for d, ax in ((0, 2), (1, 1), (2, 0)):  # direction d of the grid = axis `ax` of the [k, j, i] arrays
+        for sgn in (-1, 1):
+            sl_c = [slice(None)] * 3
+            sl_n = [slice(None)] * 3
+            sl_c[ax] = slice(1, None) if sgn < 0 else slice(None, -1)
+            sl_n[ax] = slice(None, -1) if sgn < 0 else slice(1, None)
+            sl_c, sl_n = tuple(sl_c), tuple(sl_n)
+            ka, kb = kap[sl_c], kap[sl_n]
+            kf = eps[d] * 2.0 * ka * kb / (ka + kb)
+            diag[sl_c] += kf
+            off = -kf - (1.0 if sgn < 0 else 0.0)
+            rows.append(idx[sl_c].ravel())
+            cols.append(idx[sl_n].ravel())
+            vals.append(off.ravel())
+            bd = [slice(None)] * 3
+            bd[ax] = slice(0, 1) if sgn < 0 else slice(n - 1, n)
+            bd = tuple(bd)
+            diag[bd] += eps[d] * kap[bd]  # Dirichlet ghost cell
+        diag += 1.0  # upwind convection, one per direction
+    rows.append(idx.ravel())
+    cols.append(idx.ravel())
+    vals.append(diag.ravel())
+    A = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N))
+    A.sort_indices()
+    return A
+
+
+def np_matrix_of(cfg):
+    return np_aniso_convdiff(cfg[0]) if is_aniso(cfg) else np_neglapl(cfg[0], cfg[1])
+
+
+def golden_of(name):
+    """One full run of the CPU oracle on a BASELINE-size configuration, committed with its generating script."""
+    import gzip
+    fn = os.path.join(ROOT, "tests", "golden", f"{name}_oracle.json.gz")
+    if not os.path.exists(fn):
+        return None
+    with gzip.open(fn, "rt") as f:
+        g = json.load(f)
+    return {k: g[k] for k in ("config", "N", "iterations", "solver", "residual_one_solve", "nnz", "gflop", "host")}
 
 
 def is_aniso(cfg):
@@ -146,12 +247,11 @@ def run_oracle(cfg, steps, warmup, threads):
     """CPU arm: the oracle's factorize() timed exactly where the reference driver times it
     (tests/spaND.cpp:274-292 -> <<<<tfact)."""
     import oracle_lib as O
-    import spand_public_b200 as S
     n, d, L, tol, desc = cfg
     O.lib().orc_set_threads(threads)
-    A = matrix_of(S, cfg)
-    X = S.linspace_nd(n, d)
-    G = S.symmetric_graph(A)
+    A = np_matrix_of(cfg)
+    X = np_linspace_nd(n, d)
+    G = np_symmetric_graph(A)
     gen = is_aniso(cfg)
     times = []
     info = {}
@@ -166,7 +266,7 @@ def run_oracle(cfg, steps, warmup, threads):
         if it >= warmup:
             times.append(dt)
         if it == warmup + steps - 1:
-            b = S.random(A.shape[0], 2019)
+            b = np_random(A.shape[0], 2019)
             ts = time.perf_counter()
             x = t.solve(b)
             info["tsolve_s"] = time.perf_counter() - ts
@@ -202,12 +302,6 @@ def main():
         # The reference's own CPU path = the oracle port (the reference cannot be compiled here).
         if rank != 0:
             return 0
-        sample_name = "s64" if args.steps + args.warmup <= 8 else "s48"
-        if args.config in ("c1", "c2"):
-            sample_name = args.config
-        if args.config in ANISO:
-            sample_name = "a48"
-        scfg = CONFIGS[sample_name]
         ncpu = os.cpu_count() or 1
         # The reference is sequential C++ over BLAS/LAPACK (tests/Makefile links mkl_sequential); extra BLAS threads
         # can only help inside the few large blocks and hurt on the thousands of tiny ones. Probe both settings on
@@ -217,6 +311,29 @@ def main():
             _, tt, _ = run_oracle(CONFIGS["c2"], 1, 0, th)
             probe[th] = tt[0]
         cores = min(probe, key=probe.get)
+        # Like for like: the workload itself whenever (steps + warmup) repetitions of it fit the time budget of this
+        # arm (SPAND_REF_BUDGET_S, default 1200 s), otherwise the largest member of the same family that does. Cost
+        # of one factorize() relative to C2, measured with the oracle on two hosts (tests/golden/*_oracle.json.gz:
+        # 64^3 14.9 s, 128^3 176 s where C2 takes 0.6 s; the GPU boxes run the same ratios 2.3x faster).
+        rel = {"c1": 0.02, "c2": 1.0, "c3": 8.0, "s48": 8.0, "s64": 25.0, "s80": 55.0, "s96": 105.0, "c4": 300.0,
+               "a48": 14.0, "c5s": 230.0, "c5": 1500.0}
+        budget = float(os.environ.get("SPAND_REF_BUDGET_S", "1200"))
+        reps = max(1, args.steps + args.warmup)
+        family = ["c5", "c5s", "a48"] if args.config in ANISO else (
+            [args.config] if args.config in ("c1", "c2", "c3") else ["c4", "s96", "s80", "s64", "s48"])
+        if args.config in family:
+            family = family[family.index(args.config):]
+        elif args.config not in CONFIGS:
+            family = [None] + family  # ad-hoc configuration: itself first
+        sample_name = family[-1]
+        for name in family:
+            cost = rel.get(name, 300.0) * probe[cores] * reps
+            if name is None:
+                cost = 300.0 * probe[cores] * reps * (cfg[0] ** cfg[1] / 128.0**3) ** 1.35
+            if cost <= budget:
+                sample_name = name
+                break
+        scfg = cfg if sample_name is None or sample_name == args.config else CONFIGS[sample_name]
         N, times, info = run_oracle(scfg, args.steps, args.warmup, cores)
         info["thread_probe_c2_seconds"] = {str(k): v for k, v in probe.items()}
         info["host_cpus"] = ncpu
@@ -225,10 +342,15 @@ def main():
         out = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmean * 1e3, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": desc, "sample": scfg[4]},
+               "config": {"workload": desc, "sample": scfg[4], "same_as_workload": scfg[4] == desc},
                "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port",
-                                "sample": f"full factorize() of {scfg[4]} (same family/tolerance as the workload), "
-                                          f"OpenBLAS threads={cores} (the faster of 1 and {ncpu} on a probe); throughput in dofs/s is size-normalised"},
+                                "sample": f"full factorize() of {scfg[4]}"
+                                          + (" (the workload itself)" if scfg[4] == desc else
+                                             " (largest member of the workload's family whose repetitions fit the time "
+                                             "budget of this arm; throughput in dofs/s is size-normalised and falls "
+                                             "with size on the CPU)")
+                                          + f", OpenBLAS threads={cores} (the faster of 1 and {ncpu} on a probe)",
+                                "full_workload_golden": golden_of(args.config)},
                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "factorize_time_s": tmean, **info}
         print(json.dumps(out))
@@ -283,6 +405,8 @@ def main():
     h2d = A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + b.nbytes
     d2h = b.nbytes
 
+    tcold0 = time.perf_counter()
+
     def step():
         t0 = time.perf_counter()
         t.assemble(A)
@@ -293,7 +417,11 @@ def main():
         t3 = time.perf_counter()
         return t.factorize_seconds(), t3 - t0, t1 - t0, t3 - t2, x
 
-    for _ in range(args.warmup):
+    # cold end-to-end time: partition + symbolic analysis (inside the first assemble) + assemble + factorize + solve
+    step()
+    torch.cuda.synchronize()
+    e2e_cold = tpart + (time.perf_counter() - tcold0)
+    for _ in range(max(0, args.warmup - 1)):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -324,6 +452,17 @@ def main():
     t.factorize()
     fam = t.family_stats()
     t.set_profile(False)
+    arena_b = float(t.arena_bytes())
+    if dist is not None:
+        # sharded: a family's time is the slowest rank's (every rank works on its share of the same batches); the
+        # bytes / flops of the roofline are those of the whole matrix
+        names = sorted(fam)
+        ft = torch.tensor([fam[k][0] for k in names] + [-arena_b], dtype=torch.float64, device=dev)
+        dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+        fam = {k: (float(ft[i]), fam[k][1]) for i, k in enumerate(names)}
+        ab = torch.tensor([arena_b], dtype=torch.float64, device=dev)
+        dist.all_reduce(ab, op=dist.ReduceOp.SUM)
+        arena_b = float(ab[0])
     cg_it, t_cg = None, None
     if not args.no_cg:  # collective when sharded: every rank runs the same PCG around the distributed solve
         if gen:  # tests/spaND.cpp:312-322: GMRES for non-symmetric problems
@@ -338,6 +477,15 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # the bench line carries its own correctness check (at every GPU count): one-solve residual within the reference's
+    # ApproxTest bound (tests/tests.cpp:799-856) and the Krylov iteration count against the committed oracle golden
+    gold = golden_of(args.config)
+    check = {"residual_one_solve": res, "residual_bound": 200 * tol, "iterations": cg_it,
+             "oracle_iterations": gold["iterations"] if gold else None,
+             "oracle_residual_one_solve": gold["residual_one_solve"] if gold else None}
+    check["ok"] = bool(res <= 200 * tol and (gold is None or cg_it is None or abs(cg_it - gold["iterations"]) <= 1))
+    if not check["ok"]:
+        raise SystemExit("bench.py: correctness check failed: " + json.dumps(check))
     units = N * args.steps  # sharded: the ranks factorize ONE matrix together (strong scaling)
     value = units / tdev / 1e6
     e2e_val = units / te2e / 1e6
@@ -350,7 +498,7 @@ def main():
     fam_s = {k: v[0] * 1e-3 for k, v in fam.items()}
     dom = max(fam_s, key=fam_s.get)
     by = {"rrqr": lg["by_rrqr"].sum(), "trsm": lg["by_scale"].sum(), "copy": lg["by_merge"].sum()}
-    kern = {"rrqr": "rrqr_blocked_kernel (gather + truncated QRCP + scatter)",
+    kern = {"rrqr": "rrqr_blocked_kernel / rrqr_hc_kernel / rrqr_hc2_kernel (gather + truncated QRCP + scatter)",
             "trsm": "scale_sym/trsm_strip kernels (two-sided scaling + panels)", "copy": "copy_sym_kernel + memset",
             "gemm": "gemm_tiled/gemm_sym kernels (Schur updates)", "potrf": "potrf kernels"}
     if dom in ("gemm", "potrf"):
@@ -364,8 +512,15 @@ def main():
                 "unit": "GB/s", "peak_source": hbm_src}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
     roof["traffic"] = None
-    try:  # DRAM bytes of the captured launches (ncu --set full, committed under profiles/); per launch, not averaged
-        roof["traffic_captured"] = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    try:
+        # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel family, from the
+        # ncu capture of this same command committed under profiles/ (scripts/ncu_traffic.py); averaged over the
+        # launches of the family like `achieved`
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        if dom in tr.get("families", {}):
+            roof["traffic"] = tr["families"][dom]["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr.get("source")
+            roof["algorithmic_bytes_per_launch"] = float(by.get(dom, 0.0)) / max(1, fam[dom][1])
     except Exception:
         pass
     roof["launches"] = int(fam[dom][1])
@@ -401,13 +556,16 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        scfg = CONFIGS["s64"] if args.config in ("c4", "c3") else (CONFIGS["a48"] if args.config in ANISO else cfg)
+        # bounded live sample on this box's host cores (10-30 s of CPU work); the one-off run of the oracle on the
+        # full workload is the committed golden (tests/golden/, measured on the build container's host)
+        scfg = CONFIGS["s80"] if args.config == "c4" else (CONFIGS["a48"] if args.config in ANISO else cfg)
         Nc, times, info = run_oracle(scfg, 1, 0, 1)
         cpu = {"value": Nc / times[0] / 1e6, "unit": unit, "cores": 1, "kind": "port",
                "sample": f"one full factorize() of {scfg[4]} by the oracle port (OpenBLAS 1 thread, as the reference's "
-                         f"mkl_sequential build); {times[0]:.2f} s",
+                         f"mkl_sequential build); {times[0]:.2f} s on this box",
                "factorize_time_s": times[0], "residual": info["residual"],
-               **{k: info[k] for k in ("cg_iterations", "gmres_iterations") if k in info}}
+               **{k: info[k] for k in ("cg_iterations", "gmres_iterations") if k in info},
+               "full_workload_golden": golden_of(args.config)}
 
     out = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -416,7 +574,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "N": N, "parallelism": "single GPU" if world == 1 else
                    f"one factorization sharded by ND sub-trees over {world} GPUs, peer memory over NVLink",
-                   "l2": "inputs (assembled blocks, ~%.1f GB) are larger than L2" % (t.arena_bytes() / 1e9),
+                   "l2": "inputs (assembled blocks and factors, ~%.1f GB over all ranks) are larger than L2" % (arena_b / 1e9),
                    "partition": "geometric modified ND on linspace_nd coordinates (host, untimed: %.2f s)" % tpart,
                    "symbolic": "block structure of all levels analysed once per pattern in the first assemble() "
                                "(untimed: %.2f s) and reused by every later assemble()/factorize()" % t.analyze_seconds()},
@@ -425,10 +583,13 @@ def main():
         "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "seconds_per_step": te2e / args.steps, "assemble_s": float(np.mean(tassm)),
                 "solve_s": float(np.mean(tsolve))},
+        "e2e_cold": {"seconds": e2e_cold, "value": N / e2e_cold / 1e6, "unit": unit,
+                     "what": "first call on a new matrix: partition + symbolic analysis + assemble + factorize + one solve"},
+        "correctness": check,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "residual_one_solve": res, ("gmres_iterations" if gen else "cg_iterations"): cg_it,
         ("gmres_seconds" if gen else "cg_seconds"): t_cg, "nnz_fact": int(t.nnz()),
-        "arena_gb": t.arena_bytes() / 1e9,
+        "arena_gb": arena_b / 1e9,
         "per_level": {k: [float(v) for v in lg[k]] for k in ("t_elim", "t_scale", "t_spars", "t_merge", "t_host",
                                                                "launches", "wavefronts", "dofs_left_spars")},
     }

@@ -2,6 +2,7 @@
 // (reference include/tree.h:130-198, include/is.h:12) so that tests/spaND.cpp-style drivers switch by changing
 // the namespace. Works without Eigen (std::vector based CSC); Eigen overloads appear when <Eigen/SparseCore> exists.
 #pragma once
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -76,6 +77,68 @@ class Tree {
     }
     double factorize_seconds() const { return spand_factorize_seconds(h_); }
     spand_tree* handle() const { return h_; }
+
+    // Tree::get_trailing_mat (include/tree.h:153): permuted ordering, CSC
+    struct Csc {
+        int n = 0;
+        std::vector<int> colptr, rowind;
+        std::vector<double> val;
+    };
+    Csc get_trailing_mat() const {
+        Csc T;
+        T.n = get_N();
+        const int nnz = spand_trailing(h_, nullptr, nullptr, nullptr);
+        if (nnz < 0) throw std::runtime_error(spand_last_error(h_));
+        T.colptr.assign(T.n + 1, 0);
+        T.rowind.assign(nnz, 0);
+        T.val.assign(nnz, 0.0);
+        if (spand_trailing(h_, T.colptr.data(), T.rowind.data(), T.val.data()) < 0)
+            throw std::runtime_error(spand_last_error(h_));
+        return T;
+    }
+    // Tree::log (include/tree.h:163, include/util.h:366-401): one row of spand_log_fields() doubles per level
+    std::vector<std::vector<double>> log() const {
+        const int nf = spand_log_fields(), nl = get_nlevels();
+        std::vector<double> flat((size_t)nf * nl);
+        spand_get_log(h_, flat.data());
+        std::vector<std::vector<double>> out(nl, std::vector<double>(nf));
+        for (int l = 0; l < nl; l++)
+            for (int f = 0; f < nf; f++) out[l][f] = flat[(size_t)l * nf + f];
+        return out;
+    }
+    static std::vector<std::string> log_field_names() {
+        std::vector<std::string> n;
+        for (int f = 0; f < spand_log_fields(); f++) n.push_back(spand_log_field_name(f));
+        return n;
+    }
+    // Tree::print_log (include/tree.h:164): the per-level table of the reference's verbose mode
+    void print_log(FILE* out = stdout) const {
+        const auto names = log_field_names();
+        const auto lg = log();
+        std::fprintf(out, "lvl");
+        for (const auto& n : names) std::fprintf(out, " %s", n.c_str());
+        std::fprintf(out, "\n");
+        for (size_t l = 0; l < lg.size(); l++) {
+            std::fprintf(out, "%zu", l);
+            for (double v : lg[l]) std::fprintf(out, " %.6g", v);
+            std::fprintf(out, "\n");
+        }
+    }
+    // set_monitor_flops + write_log_flops (include/tree.h:147, src/tree.cpp:60-77): lvl;kind;rows;cols;inner;time
+    void set_monitor_flops(bool on) { spand_set_monitor_flops(h_, on); }
+    void write_log_flops(const std::string& fn) const {
+        const long long n = spand_get_flops_log(h_, nullptr);
+        if (n < 0) throw std::runtime_error(spand_last_error(h_));
+        std::vector<long long> t((size_t)5 * n);
+        if (n) spand_get_flops_log(h_, t.data());
+        static const char* kind[4] = {"pivot", "panel", "gemm", "rrqr"};
+        FILE* f = std::fopen(fn.c_str(), "w");
+        if (!f) throw std::runtime_error("write_log_flops: cannot open " + fn);
+        for (long long i = 0; i < n; i++)
+            std::fprintf(f, "%lld;%s;%lld;%lld;%lld;0\n", t[5 * i], kind[t[5 * i + 1] & 3], t[5 * i + 2], t[5 * i + 3],
+                         t[5 * i + 4]);
+        std::fclose(f);
+    }
 
 #ifdef SPAND_B200_HAVE_EIGEN
     using SpMat = Eigen::SparseMatrix<double, 0, int>;

@@ -138,6 +138,15 @@ int spand_plan_counts(spand_tree* t, int level, long long* out);
 long long spand_kernel_launches(spand_tree* t);
 long long spand_arena_bytes(spand_tree* t);
 
+/* Tree::set_monitor_flops + write_log_flops       include/tree.h:147, src/tree.cpp:60-77, pushes at :592,648,662,792,1312
+ * With monitoring on, spand_get_flops_log returns one tuple (level, kind, rows, cols, inner) per BLAS call the
+ * reference would have made: kind 0 pivot (rows), 1 panel (free dimension, triangle dimension), 2 gemm (target rows,
+ * target cols, inner), 3 rrqr (rows, cols). The reference's sixth column (seconds of that call) has no counterpart:
+ * the calls of a level run as batches; per-family device time is spand_get_family_stats. Two-call protocol: out = NULL
+ * returns the number of tuples, else 5 long long per tuple are written. Call after spand_factorize. */
+int spand_set_monitor_flops(spand_tree* t, int on);
+long long spand_get_flops_log(spand_tree* t, long long* out);
+
 /* Per-kernel-family device time of the last factorize(): CUDA events recorded around every launch of the
  * family on the factorization stream (the role of the reference's per-routine Profile counters potf/trsm/
  * gemm/geqp3/merge_copy, include/util.h:262-309). Enable with spand_set_profile(t, 1) before factorize(). */

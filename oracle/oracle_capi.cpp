@@ -126,6 +126,15 @@ void orc_get_stats(void* h_, int* id, int* size, int* rank) {
 // ignored, nbrs, t_elim, t_scale, t_spars, t_merge, fl_pivot, fl_panel, fl_schur, fl_rrqr_rank, fl_rrqr_full,
 // by_scale, by_rrqr, by_merge  (22 doubles)
 int orc_log_fields() { return 22; }
+void orc_set_monitor_flops(void* h_, int on) { ((Handle*)h_)->t.monitor_flops = on != 0; }
+// two-call protocol: out == nullptr returns the number of tuples; else fills 5 long long per tuple
+long long orc_get_flops_log(void* h_, long long* out) {
+    OTree& t = ((Handle*)h_)->t;
+    if (out)
+        for (size_t i = 0; i < t.flop_log.size(); i++)
+            for (int k = 0; k < 5; k++) out[5 * i + k] = t.flop_log[i][k];
+    return (long long)t.flop_log.size();
+}
 void orc_get_log(void* h_, double* out) {
     OTree& t = ((Handle*)h_)->t;
     for (int l = 0; l < t.nlevels; l++) {

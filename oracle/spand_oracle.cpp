@@ -305,9 +305,11 @@ void OTree::schur_update(OEdge* e1, OEdge* e2, bool t1, bool t2) {
     if (n1 == n2 && symmetry()) {
         syrk(e1->A, target->A, t1 ? Trans : NoTrans, -1.0, 1.0);
         lg.fl_schur += (double)n1->size * (n1->size + 1) * s->size;
+        flop(2, n1->size, n2->size, s->size);
     } else {
         gemm(e1->A, e2->A, target->A, t1 ? Trans : NoTrans, t2 ? Trans : NoTrans, -1.0, 1.0);
         lg.fl_schur += 2.0 * n1->size * n2->size * s->size;
+        flop(2, n1->size, n2->size, s->size);
     }
 }
 
@@ -319,15 +321,18 @@ void OTree::eliminate_cluster(OCluster* self) {
         DenseMat& Ass = self->pivot()->A;
         if (potf(Ass) != 0) throw std::runtime_error("Error: Non-SPD Pivot\n");  // tree.cpp:587-590
         lg.fl_pivot += n * n * n / 3.0;
+        flop(0, (long)n, 0, 0);
         for (auto* e : self->in) {  // tree.cpp:717-724
             trsm_left(Ass, e->A, Lower, NoTrans);
             lg.fl_panel += (double)e->A.cols * n * n;
+            flop(1, e->A.cols, (long)n, 0);
         }
         bool first = true;
         for (auto& e : self->out) {
             if (first) { first = false; continue; }
             trsm_right(Ass, e->A, Lower, Trans);
             lg.fl_panel += (double)e->A.rows * n * n;
+            flop(1, e->A.rows, (long)n, 0);
         }
         // tree.cpp:862-883
         std::vector<OEdge*> outs;
@@ -380,6 +385,7 @@ void OTree::eliminate_cluster(OCluster* self) {
         for (int i = 0; i < self->size; i++) op.q[i] = i;
         split_LU(Ass, op.A, op.U);
         lg.fl_pivot += 2.0 * n * n * n / 3.0;
+        flop(0, (long)n, 0, 0);
         std::vector<OEdge*> outs;
         for (auto& e : self->out)
             if (e->n1 != e->n2) outs.push_back(e.get());
@@ -390,10 +396,12 @@ void OTree::eliminate_cluster(OCluster* self) {
                 for (int i = 0; i < tmp.rows; i++) e->A(i, j) = tmp(op.p[i], j);
             trsm_left(op.A, e->A, Lower, NoTrans);
             lg.fl_panel += (double)e->A.cols * n * n;
+            flop(1, e->A.cols, (long)n, 0);
         }
         for (auto* e : outs) {  // tree.cpp:681-689 : Ans Q^T U^-1 (Q = I for PLU)
             trsm_right(op.U, e->A, Upper, NoTrans);
             lg.fl_panel += (double)e->A.rows * n * n;
+            flop(1, e->A.rows, (long)n, 0);
         }
         for (auto* e1 : outs)
             for (auto* e2 : ins) schur_update(e1, e2, false, false);  // tree.cpp:943-947
@@ -431,9 +439,11 @@ void OTree::scale_cluster(OCluster* self) {
         DenseMat& Ass = self->pivot()->A;
         if (potf(Ass) != 0) throw std::runtime_error("Error: Non-SPD Pivot\n");
         lg.fl_pivot += n * n * n / 3.0;
+        flop(0, (long)n, 0, 0);
         for (auto* e : self->in) {
             trsm_left(Ass, e->A, Lower, NoTrans);
             lg.fl_panel += (double)e->A.cols * n * n;
+            flop(1, e->A.cols, (long)n, 0);
             lg.by_scale += 8.0 * e->A.rows * e->A.cols;  // each block is visited from both ends: 2 x 8 = 16 B/elem
         }
         bool first = true;
@@ -441,6 +451,7 @@ void OTree::scale_cluster(OCluster* self) {
             if (first) { first = false; continue; }
             trsm_right(Ass, e->A, Lower, Trans);
             lg.fl_panel += (double)e->A.rows * n * n;
+            flop(1, e->A.rows, (long)n, 0);
             lg.by_scale += 8.0 * e->A.rows * e->A.cols;
         }
         OOp op;
@@ -460,12 +471,14 @@ void OTree::scale_cluster(OCluster* self) {
         for (int i = 0; i < self->size; i++) op.q[i] = i;
         split_LU(Ass, op.A, op.U);
         lg.fl_pivot += 2.0 * n * n * n / 3.0;
+        flop(0, (long)n, 0, 0);
         for (auto* e : self->in) {
             DenseMat tmp = e->A;
             for (int j = 0; j < tmp.cols; j++)
                 for (int i = 0; i < tmp.rows; i++) e->A(i, j) = tmp(op.p[i], j);
             trsm_left(op.A, e->A, Lower, NoTrans);
             lg.fl_panel += (double)e->A.cols * n * n;
+            flop(1, e->A.cols, (long)n, 0);
             lg.by_scale += 8.0 * e->A.rows * e->A.cols;
         }
         bool first = true;
@@ -473,6 +486,7 @@ void OTree::scale_cluster(OCluster* self) {
             if (first) { first = false; continue; }
             trsm_right(op.U, e->A, Upper, NoTrans);
             lg.fl_panel += (double)e->A.rows * n * n;
+            flop(1, e->A.rows, (long)n, 0);
             lg.by_scale += 8.0 * e->A.rows * e->A.cols;
         }
         ops.push_back(std::move(op));
@@ -581,6 +595,7 @@ void OTree::sparsify_cluster(OCluster* self) {
     }
     {
         double r = rows, cc = cols, rf = mn, rk = rank;
+        flop(3, rows, cols, 0);
         lg.fl_rrqr_full += 4 * r * cc * rf - 2 * (r + cc) * rf * rf + (4.0 / 3.0) * rf * rf * rf;
         lg.fl_rrqr_rank += 4 * r * cc * rk - 2 * (r + cc) * rk * rk + (4.0 / 3.0) * rk * rk * rk;
         lg.by_rrqr += 8 * r * cc + 8 * rk * cc + 8 * r * rk;
@@ -716,6 +731,7 @@ void OTree::merge_all() {
 
 // src/tree.cpp:1447-1551
 void OTree::factorize() {
+    flop_log.clear();
     if (symm_kind == SPD && scale_kind != LLT) throw std::runtime_error("SPD requires LLT");
     if (symm_kind == GEN && scale_kind != PLU) throw std::runtime_error("GEN requires PLU");
     if (symm_kind == SYM) throw std::runtime_error("SYM/LDLT is out of scope (SURVEY.md section 2)");

@@ -20,6 +20,7 @@
 // The integer front end (modified ND, ordering, hierarchy) is shared with the product
 // (spand_public_b200/csrc/host/partition.cpp) because north_star requires it bit-exact on both sides.
 #pragma once
+#include <array>
 #include <list>
 #include <memory>
 #include <string>
@@ -115,6 +116,14 @@ class OTree {
     std::vector<std::list<std::unique_ptr<OCluster>>> bottoms;
     std::vector<std::unique_ptr<OCluster>> others;
     std::list<OOp> ops;
+    // per-call flop tuples (level, kind 0 pivot / 1 panel / 2 gemm / 3 rrqr, rows, cols, inner) exactly where the
+    // reference pushes them when set_monitor_flops is on (tree.cpp:592,648,662,792,1312; written by write_log_flops
+    // tree.cpp:60-77)
+    bool monitor_flops = false;
+    std::vector<std::array<long, 5>> flop_log;
+    void flop(int kind, long rows, long cols, long inner) {
+        if (monitor_flops) flop_log.push_back({(long)ilvl, (long)kind, rows, cols, inner});
+    }
     // (order, original size, final size) for every hierarchy cluster — the write_stats triple (tree.h:242-251)
     void stats(std::vector<int>& id, std::vector<int>& size, std::vector<int>& rank) const;
 

@@ -33,7 +33,7 @@ EXPORTS = [
     "spand_plan_counts", "spand_get_cluster_layout", "spand_mg_setup", "spand_mg_get_handle", "spand_mg_set_peers",
     "spand_mg_owner_map", "spand_kernel_launches", "spand_arena_bytes", "spand_trailing",
     "spand_util_random", "spand_util_linspace_nd", "spand_util_neglapl", "spand_util_aniso", "spand_util_mm_read",
-    "spand_util_mm_read_dense", "spand_set_profile", "spand_num_families", "spand_family_name", "spand_get_family_stats",
+    "spand_util_mm_read_dense", "spand_set_profile", "spand_set_monitor_flops", "spand_get_flops_log", "spand_num_families", "spand_family_name", "spand_get_family_stats",
 ]
 
 
@@ -378,6 +378,21 @@ class Tree:
     def arena_bytes(self): return self._l.spand_arena_bytes(self._h)
 
     def set_profile(self, on): self._l.spand_set_profile(self._h, int(on))
+
+    def set_monitor_flops(self, on): self._l.spand_set_monitor_flops(self._h, int(on))
+
+    def flops_log(self):
+        """(n, 5) int64 array of (level, kind, rows, cols, inner): reference write_log_flops, src/tree.cpp:60-77."""
+        fn = self._l.spand_get_flops_log
+        fn.restype = C.c_longlong
+        fn.argtypes = [_p, C.c_void_p]
+        n = fn(self._h, None)
+        if n < 0:
+            raise RuntimeError(self._l.spand_last_error(self._h).decode())
+        out = np.zeros((n, 5), dtype=np.int64)
+        if n:
+            fn(self._h, out.ctypes.data)
+        return out
 
     def family_stats(self):
         """{family: (device ms, launches)} of the last factorize(); ms is 0 unless set_profile(True)."""

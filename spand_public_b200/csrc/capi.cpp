@@ -55,7 +55,30 @@ int spand_set_scaling_kind(spand_tree* t, int kind) { t->t.scale_kind = kind; re
 int spand_set_use_geo(spand_tree* t, int geo) { t->t.use_geo = geo != 0; return 0; }
 int spand_set_verb(spand_tree* t, int verb) { t->t.verb = verb != 0; return 0; }
 int spand_set_use_sparsify(spand_tree* t, int use) { t->t.use_want_sparsify = use != 0; return 0; }
-int spand_set_device(spand_tree* t, int device) { t->t.device = device; return 0; }
+int spand_set_device(spand_tree* t, int device) {
+    return guarded(t, [&] {
+        if (t->t.device_in_use() && device != t->t.device)
+            throw std::runtime_error("set_device: the tree already holds memory on another device");
+        t->t.device = device;
+    });
+}
+int spand_set_monitor_flops(spand_tree* t, int on) { t->t.monitor_flops = on != 0; return 0; }
+long long spand_get_flops_log(spand_tree* t, long long* out) {
+    long long n = -1;
+    guarded(t, [&] {
+        const auto& fl = t->t.flop_log();
+        if (out)
+            for (size_t i = 0; i < fl.size(); i++) {
+                out[5 * i] = fl[i].lvl;
+                out[5 * i + 1] = fl[i].kind;
+                out[5 * i + 2] = fl[i].rows;
+                out[5 * i + 3] = fl[i].cols;
+                out[5 * i + 4] = fl[i].inner;
+            }
+        n = (long long)fl.size();
+    });
+    return n;
+}
 int spand_set_profile(spand_tree* t, int on) { t->t.profile_families = on != 0; return 0; }
 int spand_num_families(void) { return Tree::F_COUNT; }
 const char* spand_family_name(int f) { return Tree::family_name(f); }

@@ -70,10 +70,17 @@ SpMat from_csc(int n, const int* colptr, const int* rowind, const double* val) {
         else A.val.assign(nnz, 1.0);
         return A;
     }
+    // general input (unsorted rows, duplicates, empty columns): validate, then go through triplets
+    if (colptr[0] != 0) throw std::runtime_error("from_csc: colptr[0] must be 0");
+    for (int j = 0; j < n; j++)
+        if (colptr[j + 1] < colptr[j]) throw std::runtime_error("from_csc: colptr must be non-decreasing");
     std::vector<Triplet> t;
     t.reserve(colptr[n]);
     for (int j = 0; j < n; j++)
-        for (int k = colptr[j]; k < colptr[j + 1]; k++) t.push_back({rowind[k], j, val ? val[k] : 1.0});
+        for (int k = colptr[j]; k < colptr[j + 1]; k++) {
+            if (rowind[k] < 0 || rowind[k] >= n) throw std::runtime_error("from_csc: row index out of range");
+            t.push_back({rowind[k], j, val ? val[k] : 1.0});
+        }
     return from_triplets(n, n, t);
 }
 

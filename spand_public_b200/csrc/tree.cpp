@@ -102,6 +102,23 @@ Tree::Tree(int nlevels_) : nlevels(nlevels_) {
 
 Tree::~Tree() { free_device(); }
 
+// Every public entry point that touches the device runs with the tree's device current and restores the caller's
+// device afterwards (the host application may switch devices between calls, e.g. a second Tree on another GPU).
+struct Tree::DeviceGuard {
+    int prev = -1;
+    bool active = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            if (cudaSetDevice(dev) == cudaSuccess) active = true;
+        } else {
+            cudaGetLastError();  // no device at all: the entry point reports it itself
+        }
+    }
+    ~DeviceGuard() {
+        if (active) cudaSetDevice(prev);
+    }
+};
+
 void Tree::ensure_device() {
     if (st_) return;
     int ndev = 0;
@@ -124,6 +141,7 @@ void Tree::ensure_device() {
 }
 
 void Tree::free_device() {
+    DeviceGuard dev_guard(device);
     if (!st_) return;
     cudaStreamSynchronize(st_);
     for (int r = 0; r < mg_nranks; r++) {
@@ -217,6 +235,11 @@ void Tree::partition(const SpMat& A) {
     ord = build_ordering(A, nlevels, use_geo ? &Xcoo_ : nullptr, verb);
     ord_serial_++;
     N = A.rows;
+    // a new partition invalidates everything built on the previous one (plan, blocks, factors, solve batches)
+    assembled_ = false;
+    factorized_ = false;
+    plan_valid_ = false;
+    state_level_ = -1;
     log.assign(nlevels, LevelLog());
     for (auto& p : ord.part) log[p.self.lvl].dofs_nd += 1;
     for (int l = nlevels - 2; l >= 0; l--) log[l].dofs_left_nd = log[l + 1].dofs_nd + log[l + 1].dofs_left_nd;
@@ -316,6 +339,7 @@ void Tree::analyze_host(const SpMat& A, std::vector<unsigned>& valmap) {
 }
 
 void Tree::analyze(const SpMat& A) {
+    DeviceGuard dev_guard(device);
     const double t0 = wtime();
     const int ncl = ord.norders;
     std::vector<unsigned> valmap;
@@ -462,6 +486,7 @@ void Tree::assemble_csc(int n, const int* colptr, const int* rowind, const doubl
 
 // A == nullptr: the caller has verified that (colptr, rowind) equal the planned pattern
 void Tree::assemble_impl(const SpMat* Afull, int n_in, const int* colptr, const int* rowind, const double* val) {
+    DeviceGuard dev_guard(device);
     (void)rowind;
     if (N == 0 || n_in != N) throw std::runtime_error("assemble: call partition first with a matrix of the same size");
     const size_t nnz_in = (size_t)colptr[n_in];
@@ -682,6 +707,7 @@ void Tree::alloc_edges(int e0, int e1, bool zero, LevelLog& lg) {
 // multi-GPU setup (one process per GPU; the handles travel through the caller's process group)
 // ------------------------------------------------------------------------------------------------
 void Tree::mg_setup(int rank, int nranks, size_t arena_bytes) {
+    DeviceGuard dev_guard(device);
     if (nranks < 1 || nranks > MG_MAX_RANKS || (nranks & (nranks - 1)) != 0)
         throw std::runtime_error("mg_setup: the number of ranks must be a power of two <= 16");
     if (nranks > 1 && nranks > (1 << (nlevels - 1))) throw std::runtime_error("mg_setup: more ranks than sub-trees");
@@ -705,6 +731,7 @@ void Tree::mg_get_handle(void* out64) const {
 }
 
 void Tree::mg_set_peers(const void* handles) {
+    DeviceGuard dev_guard(device);
     for (int r = 0; r < mg_nranks; r++) {
         if (r == mg_rank) continue;
         cudaIpcMemHandle_t h;
@@ -1659,6 +1686,7 @@ void Tree::phase_merge(LevelLog& lg, SolveLevel& sl) {
 // FACTORIZE — src/tree.cpp:1447-1551
 // ------------------------------------------------------------------------------------------------
 void Tree::factorize() {
+    DeviceGuard dev_guard(device);
     if (symm_kind == SPD && scale_kind != LLT) throw std::runtime_error("SPD requires LLT scaling");
     if (symm_kind == GEN && scale_kind != PLU) throw std::runtime_error("GEN requires PLU scaling (PLUQ is out of scope)");
     if (symm_kind == SYM) throw std::runtime_error("SYM/LDLT is out of scope (SURVEY.md section 2)");
@@ -1671,11 +1699,17 @@ void Tree::factorize() {
         family_ms[f] = 0;
         family_launches[f] = 0;
     }
-    std::vector<cudaEvent_t> ev(nlevels * 5);
-    for (auto& e : ev) CK(cudaEventCreate(&e));
-    cudaEvent_t ev_begin, ev_end;
-    CK(cudaEventCreate(&ev_begin));
-    CK(cudaEventCreate(&ev_end));
+    struct Events {  // destroyed on every exit path (a non-SPD pivot throws out of the level loop)
+        std::vector<cudaEvent_t> v;
+        ~Events() {
+            for (auto e : v)
+                if (e) cudaEventDestroy(e);
+        }
+    } evs;
+    evs.v.assign(nlevels * 5 + 2, nullptr);
+    for (auto& e : evs.v) CK(cudaEventCreate(&e));
+    cudaEvent_t* ev = evs.v.data();
+    cudaEvent_t ev_begin = evs.v[nlevels * 5], ev_end = evs.v[nlevels * 5 + 1];
     CK(cudaEventRecord(ev_begin, st_));
     bool stopped = false;
     int last_level = -1;
@@ -1765,9 +1799,6 @@ void Tree::factorize() {
                    l, log[l].t_elim, log[l].t_scale, log[l].t_spars, log[l].t_merge, log[l].t_host,
                    log[l].dofs_left_elim, log[l].dofs_left_spars, log[l].launches, log[l].wavefronts);
     }
-    for (auto& e : ev) cudaEventDestroy(e);
-    cudaEventDestroy(ev_begin);
-    cudaEventDestroy(ev_end);
     stager_.reset();
     scratch_->reset();
     factorized_ = !stopped;
@@ -1780,6 +1811,7 @@ void Tree::finalize_logs() {
     logs_final_ = true;
     const bool plu = scale_kind == PLU;
     nnz_ = 0;
+    flop_log_.clear();
     for (int l = 0; l < nlevels; l++) {
         if (!phases_done_[l]) break;
         LevelLog& lg = log[l];
@@ -1791,6 +1823,9 @@ void Tree::finalize_logs() {
         const std::vector<int>& post = size_post_[l];
         auto P = [&](int c) { return (double)pre[c - first]; };
         auto Q = [&](int c) { return (double)post[c - first]; };
+        auto tuple = [&](int kind, double rows, double cols, double inner) {
+            if (monitor_flops) flop_log_.push_back({(long long)l, (long long)kind, (long long)rows, (long long)cols, (long long)inner});
+        };
         lg.fl_pivot = lg.fl_panel = lg.fl_schur = lg.fl_rrqr_rank = lg.fl_rrqr_full = 0;
         lg.by_scale = lg.by_rrqr = lg.by_merge = 0;
         lg.rank_before = lg.rank_after = 0;
@@ -1800,14 +1835,17 @@ void Tree::finalize_logs() {
         // eliminate
         for (int s : L.E) {
             const double n = P(s);
+            tuple(0, n, 0, 0);
             lg.fl_pivot += (plu ? 2.0 : 1.0) * n * n * n / 3.0;
             nz += plu ? (long long)(n * n + 2 * n) : (long long)(n * (n + 1) / 2);
         }
         for (const SymTrsm& t : L.e_out) {
+            tuple(1, P(t.cm), P(t.cn), 0);
             lg.fl_panel += P(t.cm) * P(t.cn) * P(t.cn);
             nz += (long long)(P(t.cm) * P(t.cn));
         }
         for (const SymTrsm& t : L.e_in) {
+            tuple(1, P(t.cm), P(t.cn), 0);
             lg.fl_panel += P(t.cm) * P(t.cn) * P(t.cn);
             nz += (long long)(P(t.cm) * P(t.cn));
         }
@@ -1816,6 +1854,7 @@ void Tree::finalize_logs() {
             for (int ci = 0; ci < g.nc; ci++) {
                 const SymCon& c = L.e_con[g.c0 + ci];
                 const double k = P(plan_.en1[c.e1]);
+                tuple(2, m, n, k);
                 if (plan_.symmetric && plan_.en2[c.e1] == plan_.en2[c.e2]) lg.fl_schur += m * (m + 1) * k;
                 else lg.fl_schur += 2.0 * m * n * k;
             }
@@ -1824,12 +1863,15 @@ void Tree::finalize_logs() {
         if (phases_done_[l] & 2) {
             for (int c : L.S) {
                 const double n = P(c);
+                tuple(0, n, 0, 0);
                 lg.fl_pivot += (plu ? 2.0 : 1.0) * n * n * n / 3.0;
                 nz += plu ? (long long)(n * n + 2 * n) : (long long)(n * (n + 1) / 2);
                 lg.by_scale += 16.0 * n * n;
             }
             for (const SymTrsm& t : L.s_right) {
                 const double rows = P(t.cm), cols = P(t.cn);
+                tuple(1, rows, cols, 0);  // the two triangular solves of a scaled block (trsm_potf_edgeOut / edgeIn)
+                tuple(1, cols, rows, 0);
                 lg.fl_panel += rows * cols * cols + cols * rows * rows;
                 lg.by_scale += 16.0 * rows * cols;
             }
@@ -1847,6 +1889,7 @@ void Tree::finalize_logs() {
                 }
                 double rf = std::min(r, cc);
                 if (tol >= 1.0 || cc == 0) rf = 0;
+                tuple(3, r, cc, 0);  // pushed after every geqp3 call, empty panels included (tree.cpp:1312)
                 lg.rank_before += (long long)r;
                 lg.nspars++;
                 lg.nbrs += (long long)cc;
@@ -1854,6 +1897,9 @@ void Tree::finalize_logs() {
                 lg.fl_rrqr_rank += 4 * r * cc * rk - 2 * (r + cc) * rk * rk + (4.0 / 3.0) * rk * rk * rk;
                 lg.by_rrqr += 8 * r * cc + 8 * rk * cc + 8 * r * rk;
                 if (rk < r) {
+                    // the reference eliminates the dropped sibling right away (tree.cpp:1342 -> potf_cluster :592 pushes a
+                    // pivot tuple for its identity pivot); nothing is computed for it here, the tuple is listed only
+                    tuple(0, r - rk, 0, 0);
                     nz += (long long)(r * r);  // Orthogonal (operations.cpp:159-161)
                     const double m = r - rk;
                     // Scaling op of the dropped sibling (tree.cpp:1342): ScalingLLT(I) or ScalingPLUQ(I, I, id, id)
@@ -1901,6 +1947,7 @@ int Tree::get_stop() const {
 // SOLVE — src/tree.cpp:1610-1635: all fwd() in record order, then all bwd() in reverse
 // ------------------------------------------------------------------------------------------------
 void Tree::solve_device(double* x_dev) {
+    DeviceGuard dev_guard(device);
     if (!factorized_) throw std::runtime_error("solve: call factorize first");
     double* xleaf = d_xleaf_;
     launch_gather(N, d_perm_, x_dev, xleaf, st_);  // b = P^T x
@@ -1936,6 +1983,7 @@ void Tree::solve_device(double* x_dev) {
 }
 
 void Tree::solve(double* x_host) {
+    DeviceGuard dev_guard(device);
     if (!factorized_) throw std::runtime_error("solve: call factorize first");
     CK(cudaMemcpyAsync(d_xnat_, x_host, sizeof(double) * N, cudaMemcpyHostToDevice, st_));
     solve_device(d_xnat_);
@@ -1945,7 +1993,9 @@ void Tree::solve(double* x_host) {
 
 // src/is.cpp:39-121 with every vector resident in HBM
 int Tree::cg(const SpMat& A, const double* rhs, double* x, int iters, double tol_, bool verbose, double* seconds) {
+    DeviceGuard dev_guard(device);
     if (!factorized_) throw std::runtime_error("cg: call factorize first");
+    if (A.rows != N || A.cols != N) throw std::runtime_error("cg: the matrix does not have the size of the factorized one");
     int n = A.cols;
     SpMat At = transpose(A);  // CSR of A = CSC of A^T
     int *d_rp, *d_ci;
@@ -2028,7 +2078,9 @@ int Tree::cg(const SpMat& A, const double* rhs, double* x, int iters, double tol
 // back the k + 1 leading entries of the new column once per iteration (the only synchronisation).
 int Tree::gmres(const SpMat& A, const double* rhs, double* x, int iters, int restart, double tol_, bool verbose,
                 double* seconds) {
+    DeviceGuard dev_guard(device);
     if (!factorized_) throw std::runtime_error("gmres: call factorize first");
+    if (A.rows != N || A.cols != N) throw std::runtime_error("gmres: the matrix does not have the size of the factorized one");
     const int m = A.cols;
     if (restart < 1) throw std::runtime_error("gmres: restart must be >= 1");
     if (restart > m) restart = m;
@@ -2187,6 +2239,7 @@ int Tree::gmres(const SpMat& A, const double* rhs, double* x, int iters, int res
 // src/tree.cpp:1730-1763 (permuted ordering; both triangles for symmetric kinds). The live blocks at the point
 // where factorize() stopped (parity-test hook) are read off the plan.
 SpMat Tree::trailing_mat() {
+    DeviceGuard dev_guard(device);
     std::vector<Triplet> t;
     std::vector<double> hb;
     if (!assembled_) throw std::runtime_error("trailing_mat: call assemble first");

@@ -88,8 +88,14 @@ class Tree {
     int scale_kind = LLT;
     bool use_want_sparsify = true;
     bool monitor_flops = false;
+    // per-call flop tuples (level, kind 0 pivot / 1 panel / 2 gemm / 3 rrqr, rows, cols, inner): what the reference
+    // pushes at every BLAS call when set_monitor_flops is on (tree.cpp:592,648,662,792,1312, written by
+    // write_log_flops tree.cpp:60-77); here they are listed from the plan after the factorization (finalize_logs)
+    struct FlopTuple { long long lvl, kind, rows, cols, inner; };
+    const std::vector<FlopTuple>& flop_log() { finalize_logs(); return flop_log_; }
     int stop_level = -1, stop_phase = -1;  // parity-test hook (see oracle)
     int device = 0;
+    bool device_in_use() const { return st_ != nullptr; }
     // per-kernel-family device timing (CUDA events around every launch of the family on the factorization
     // stream); off by default because the extra events serialise nothing but cost host time
     bool profile_families = false;
@@ -134,7 +140,9 @@ class Tree {
     void plan_live_edges(int level, int phase, std::vector<int>& n1, std::vector<int>& n2) const;
     void plan_counts(int level, long long out[12]) const;
     double t_factorize_device = 0;  // seconds, CUDA events
-    size_t arena_bytes() const { return arena_ ? arena_->used() : 0; }
+    // device bytes holding blocks and factors: the private arena plus, when sharded, this rank's share of the
+    // peer-mapped arena (where the blocks it owns live)
+    size_t arena_bytes() const { return (arena_ ? arena_->used() : 0) + (mg_nranks > 1 ? mg_top_[mg_rank] : 0); }
     long long launches_total = 0;
 
    private:
@@ -197,6 +205,8 @@ class Tree {
     void build_clusters();
     bool plan_host_valid_ = false;
 
+    struct DeviceGuard;
+    std::vector<FlopTuple> flop_log_;
     cudaStream_t st_ = nullptr;
     static constexpr int kSide = 4;  // side streams for independent launches of one wavefront
     cudaStream_t side_[kSide] = {nullptr, nullptr, nullptr, nullptr};

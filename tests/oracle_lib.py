@@ -186,6 +186,20 @@ class OracleTree:
         out = out.reshape(self.nlevels, len(LOG_FIELDS))
         return {k: out[:, i].copy() for i, k in enumerate(LOG_FIELDS)}
 
+    def set_monitor_flops(self, on):
+        self._l.orc_set_monitor_flops.argtypes = [_p, _i]
+        self._l.orc_set_monitor_flops(self._h, int(on))
+
+    def flops_log(self):
+        fn = self._l.orc_get_flops_log
+        fn.restype = C.c_longlong
+        fn.argtypes = [_p, C.c_void_p]
+        n = fn(self._h, None)
+        out = np.zeros((n, 5), dtype=np.int64)
+        if n:
+            fn(self._h, out.ctypes.data)
+        return out
+
     def trailing_mat(self):
         import scipy.sparse as sp
         nnz = self._l.orc_trailing(self._h, None, None, None)

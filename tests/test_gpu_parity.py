@@ -543,3 +543,23 @@ def test_plu_row_pivoting_matters():
     assert ro <= 1e-8, ro  # the oracle solves it: the test matrix is usable
     assert rg <= max(100 * ro, 1e-9), (rg, ro)
     assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) <= 1e-6
+
+
+@pytest.mark.parametrize("n,d,L,tol", [(20, 2, 4, 0.0), (12, 3, 4, 0.0), (15, 3, 5, 1e-14)])
+def test_flop_tuple_log_matches_oracle(n, d, L, tol):
+    """set_monitor_flops / write_log_flops (reference src/tree.cpp:60-77, pushes at :592,648,662,792,1312): the
+    (level, kind, rows, cols, inner) tuples listed from the plan are the ones the oracle pushes call by call."""
+    A, g, o = _pair(n, d, L, tol)
+    g.set_monitor_flops(True)
+    o.set_monitor_flops(True)
+    g.assemble(A)
+    o.assemble(A)
+    g.factorize()
+    o.factorize()
+    assert np.array_equal(g.stats()[2], o.stats()[2])  # same ranks on these configurations
+    fg, fo = g.flops_log(), o.flops_log()
+    import collections
+    cg_, co_ = collections.Counter(map(tuple, fg.tolist())), collections.Counter(map(tuple, fo.tolist()))
+    only_g, only_o = cg_ - co_, co_ - cg_
+    assert not only_g and not only_o, f"only in the product's log: {dict(only_g)}; only in the oracle's: {dict(only_o)}"
+    assert len(fg) > 0
