@@ -388,8 +388,6 @@ def main():
     t = S.Tree(L)
     t.set_device(local_rank)
     if gen:
-        if world > 1:
-            raise SystemExit("bench.py: sub-tree sharding covers the SPD/LLT path only; run C5 with --gpus 1")
         t.set_symm_kind(S.GEN)
         t.set_scaling_kind(S.PLU)
     if world > 1:

@@ -551,7 +551,6 @@ void Tree::assemble_impl(const SpMat* Afull, int n_in, const int* colptr, const 
         // Symmetric layout of every rank's shared arena: [flags | cluster sizes | leaf solution segments | the leaf
         // blocks (every rank assembles all of them, only the owner's copy is used) | blocks created later].
         if (!mg_peers_set_) throw std::runtime_error("assemble: mg_setup / mg_set_peers must be called first");
-        if (scale_kind == PLU) throw std::runtime_error("multi-GPU sharding is built for the SPD/LLT path only");
         auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
         mg_off_csize_ = 4096;
         const size_t off_xleaf = up(mg_off_csize_ + sizeof(int) * ncl);
@@ -1101,9 +1100,18 @@ void Tree::run_rowperm(std::vector<RowPermTask>& tasks, LevelLog& lg) {
 
 void Tree::alloc_plu(int c) {
     size_t n = std::max(1, h_csize_[c]);
-    h_ud_[c] = arena_->alloc_n<double>(n);
-    h_ipiv_[c] = arena_->alloc_n<int>(n);
-    h_pperm_[c] = arena_->alloc_n<int>(n);
+    if (!mg()) {
+        h_ud_[c] = arena_->alloc_n<double>(n);
+        h_ipiv_[c] = arena_->alloc_n<int>(n);
+        h_pperm_[c] = arena_->alloc_n<int>(n);
+        return;
+    }
+    // sharded: diag(U) and the row permutation of a pivot are read by the owners of the blocks in its row / column
+    // (peer memory), so they live in the owner's shared arena; every rank replays the allocation
+    const int o = h_owner_[c];
+    h_ud_[c] = alloc_block(o, n);
+    h_ipiv_[c] = reinterpret_cast<int*>(alloc_block(o, (n + 1) / 2));
+    h_pperm_[c] = reinterpret_cast<int*>(alloc_block(o, (n + 1) / 2));
 }
 
 void Tree::phase_eliminate_plu(LevelLog& lg, SolveLevel& sl) {
@@ -1115,26 +1123,34 @@ void Tree::phase_eliminate_plu(LevelLog& lg, SolveLevel& sl) {
     std::vector<RowPermTask> rperm;
     std::vector<TrsmTask> left, right;
     std::vector<TrsvTask> trsv;
+    // Sharded over several GPUs: a pivot is factored by the owner of its cluster, a block is transformed / updated by
+    // the owner of its column cluster (which reads the factor and the permutation of the row cluster through peer
+    // memory); the solve batches keep every entry, with size 0 on the ranks that do not own the segment.
     for (size_t i = 0; i < L.E.size(); i++) {
         const int s = L.E[i], piv = L.e_piv[i];
         alloc_plu(s);
-        getrf.push_back({h_eptr_[piv], h_eld_[piv], h_csize_[s], h_ud_[s], h_ipiv_[s], h_pperm_[s]});
-        trsv.push_back({h_eptr_[piv], h_xptr_[s], h_eld_[piv], h_csize_[s], h_ud_[s], h_pperm_[s]});
+        if (mine(s)) getrf.push_back({h_eptr_[piv], h_eld_[piv], h_csize_[s], h_ud_[s], h_ipiv_[s], h_pperm_[s]});
+        trsv.push_back({h_eptr_[piv], h_xptr_[s], h_eld_[piv], mine(s) ? h_csize_[s] : 0, h_ud_[s], h_pperm_[s]});
     }
     for (const SymTrsm& t : L.e_in) {  // A[s,n] <- L^-1 P^T A[s,n]   (tree.cpp:668-676)
+        if (!mine(plan_.en1[t.eB])) continue;
         rperm.push_back({h_eptr_[t.eB], h_eld_[t.eB], h_csize_[t.cn], h_csize_[t.cm], h_pperm_[t.cn]});
         left.push_back(host_trsm(t, nullptr));
     }
-    for (const SymTrsm& t : L.e_out) right.push_back(host_trsm(t, h_ud_[t.cn]));  // A[n,s] <- A[n,s] U^-1 (tree.cpp:681-689)
+    for (const SymTrsm& t : L.e_out)  // A[n,s] <- A[n,s] U^-1 (tree.cpp:681-689)
+        if (mine(plan_.en1[t.eB])) right.push_back(host_trsm(t, h_ud_[t.cn]));
     run_getrf(getrf, lg);
+    mg_barrier();  // the in-edges of a pivot may belong to other ranks
     run_rowperm(rperm, lg);
     run_trsm(TRSM_LLN, left, lg);
     run_trsm(TRSM_RUN, right, lg);
+    mg_barrier();  // a Schur target is updated by its owner, which reads the panels of other ranks
     // Schur complement A[n1,n2] -= A[n1,s] A[s,n2] (tree.cpp:943-947)
     {
         std::vector<GemmTask> tasks;
         std::vector<GemmContrib> con;
         for (const SymGemm& g : L.e_gemm) {
+            if (!mine(plan_.en1[g.target])) continue;
             GemmTask t;
             t.C = h_eptr_[g.target];
             t.ldc = h_eld_[g.target];
@@ -1177,18 +1193,20 @@ void Tree::phase_scale_plu(LevelLog& lg, SolveLevel& sl) {
     for (size_t i = 0; i < L.S.size(); i++) {
         const int c = L.S[i], piv = L.s_piv[i];
         alloc_plu(c);
-        getrf.push_back({h_eptr_[piv], h_eld_[piv], h_csize_[c], h_ud_[c], h_ipiv_[c], h_pperm_[c]});
-        trsv.push_back({h_eptr_[piv], h_xptr_[c], h_eld_[piv], h_csize_[c], h_ud_[c], h_pperm_[c]});
+        if (mine(c)) getrf.push_back({h_eptr_[piv], h_eld_[piv], h_csize_[c], h_ud_[c], h_ipiv_[c], h_pperm_[c]});
+        trsv.push_back({h_eptr_[piv], h_xptr_[c], h_eld_[piv], mine(c) ? h_csize_[c] : 0, h_ud_[c], h_pperm_[c]});
     }
     for (size_t i = 0; i < L.s_right.size(); i++) {
         // block A[n2,n1] (|n2| x |n1|): out-edge of n1 -> B U_n1^-1 ; in-edge of n2 -> L_n2^-1 P_n2^T B
         const SymTrsm& r = L.s_right[i];
         const SymTrsm& l = L.s_left[i];
+        if (!mine(plan_.en1[r.eB])) continue;  // both transformations of a block run on the owner of its column cluster
         right.push_back(host_trsm(r, h_ud_[r.cn]));
         rperm.push_back({h_eptr_[l.eB], h_eld_[l.eB], h_csize_[l.cn], h_csize_[l.cm], h_pperm_[l.cn]});
         left.push_back(host_trsm(l, nullptr));
     }
     run_getrf(getrf, lg);
+    mg_barrier();  // a block needs the factor and the permutation of its row cluster too, possibly from another rank
     run_trsm(TRSM_RUN, right, lg);
     run_rowperm(rperm, lg);
     run_trsm(TRSM_LLN, left, lg);

@@ -14,10 +14,13 @@ sys.path.insert(0, ROOT)
 import spand_public_b200 as S  # noqa: E402
 
 
-def run(n, d, L, tol, sharded, local_rank):
-    A = S.neglapl(n, d)
+def run(n, d, L, tol, sharded, local_rank, gen=False):
+    A = S.aniso_convdiff(n) if gen else S.neglapl(n, d)
     t = S.Tree(L)
     t.set_device(local_rank)
+    if gen:
+        t.set_symm_kind(S.GEN)
+        t.set_scaling_kind(S.PLU)
     if sharded:
         t.mg_init(dist, device=local_rank, arena_gb=float(os.environ.get("SPAND_MG_ARENA_GB", "8")))
     t.set_tol(tol)
@@ -29,7 +32,7 @@ def run(n, d, L, tol, sharded, local_rank):
     b = S.random(A.shape[0], 2019)
     x = t.solve(b)
     x2 = t.solve(b)
-    it, xc = t.cg(A, b, 200, 1e-12)
+    it, xc = t.gmres(A, b, 200, 100, 1e-12) if gen else t.cg(A, b, 200, 1e-12)
     return dict(A=A, b=b, x=x, x2=x2, ranks=t.stats()[2].copy(), nnz=t.nnz(), it=it, xc=xc,
                 tfact=t.factorize_seconds(), tree=t)
 
@@ -41,11 +44,20 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     out = []
     # the last one (64^3, 13 levels) is large enough for the streaming RRQR shapes (wavefronts of >= 48 panels > 300 KB)
-    for (n, d, L, tol) in [(16, 3, 6, 1e-2), (32, 2, 6, 0.0), (24, 3, 8, 1e-2), (64, 3, 13, 1e-2)]:
-        sh = run(n, d, L, tol, True, local_rank)
-        one = run(n, d, L, tol, False, local_rank)
+    # negative L marks the GEN / PLU family (anisotropic convection-diffusion, GMRES): config C5's path
+    for (n, d, L, tol) in [(16, 3, 6, 1e-2), (32, 2, 6, 0.0), (24, 3, 8, 1e-2), (64, 3, 13, 1e-2), (16, 3, -6, 1e-2),
+                           (24, 3, -8, 1e-2)]:
+        gen = L < 0
+        L = abs(L)
+        sh = run(n, d, L, tol, True, local_rank, gen)
+        one = run(n, d, L, tol, False, local_rank, gen)
         res = float(np.linalg.norm(sh["A"] @ sh["x"] - sh["b"]) / np.linalg.norm(sh["b"]))
-        rec = dict(cfg=[n, d, L, tol], rank=rank, world=world, same_ranks=bool(np.array_equal(sh["ranks"], one["ranks"])),
+        dr = sh["ranks"].astype(int) - one["ranks"].astype(int)
+        rec = dict(cfg=[n, d, L, tol], gen=gen, rank=rank, world=world, same_ranks=bool(np.array_equal(sh["ranks"], one["ranks"])),
+                   ranks_differ=int((dr != 0).sum()), ranks_maxdiff=int(abs(dr).max()), nclusters=int(len(dr)),
+                   nnz_rel=float(abs(sh["nnz"] - one["nnz"]) / max(1, one["nnz"])), it_sharded=int(sh["it"]),
+                   it_single=int(one["it"]),
+                   cg_x_rel=float(np.linalg.norm(sh["xc"] - one["xc"]) / np.linalg.norm(one["xc"])),
                    same_nnz=bool(sh["nnz"] == one["nnz"]), same_x=bool(np.array_equal(sh["x"], one["x"])),
                    repeat_x=bool(np.array_equal(sh["x"], sh["x2"])), same_cg=bool(sh["it"] == one["it"]),
                    same_cg_x=bool(np.array_equal(sh["xc"], one["xc"])), residual=res,
