@@ -377,62 +377,92 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 // One 64x64 tile of one target; contributions come through fetch(ci) in a fixed order (deterministic sums).
-template <class Fetch>
+// Software pipeline over the k chunks of all contributions: the global loads of chunk i + 1 are in flight (registers)
+// while the tensor cores work on chunk i out of one of two shared-memory buffers; one block barrier per chunk.
+// NBUF = 1 (callers that need the shared memory for themselves): one buffer, a second barrier per chunk.
+template <int NBUF = 2, class Fetch>
 __device__ __forceinline__ void gemm_tile64(double* C, int ldc, int m, int n, int flags, int row0, int col0, int nc,
                                             Fetch fetch) {
-    bool nn = (flags & GEMM_NN) != 0;
-    __shared__ double As[GK * GLD];
-    __shared__ double Bs[GK * GLD];
-    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int wm = warp & 3, wn = warp >> 2;
+    const bool nn = (flags & GEMM_NN) != 0;
+    __shared__ double As[NBUF][GK * GLD];
+    __shared__ double Bs[NBUF][GK * GLD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
     double acc[2][4][2];
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[a][c][0] = acc[a][c][1] = 0.0;
 
-    int arow = tid & 63, ak = tid >> 6;  // A loader: rows contiguous
-    int bk_nn = tid & 15, bj_nn = tid >> 4;
+    const int arow = tid & 63, ak = tid >> 6;  // A loader: rows contiguous
+    const int bk_nn = tid & 15, bj_nn = tid >> 4;
 
-    for (int ci = 0; ci < nc; ci++) {
-        GemmContrib c = fetch(ci);
-        for (int k0 = 0; k0 < c.k; k0 += GK) {
-            double ra[4], rb[4];
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                int kk = k0 + ak + 4 * s;
-                int gi = row0 + arow;
-                ra[s] = (gi < m && kk < c.k) ? c.A[gi + (size_t)kk * c.lda] : 0.0;
-                if (!nn) {
-                    int gj = col0 + arow;
-                    rb[s] = (gj < n && kk < c.k) ? c.B[gj + (size_t)kk * c.ldb] : 0.0;
-                } else {
-                    int kk2 = k0 + bk_nn, gj = col0 + bj_nn + 16 * s;
-                    rb[s] = (gj < n && kk2 < c.k) ? c.B[kk2 + (size_t)gj * c.ldb] : 0.0;
-                }
+    int ci = 0, k0 = 0;
+    GemmContrib c{};
+    bool valid = false;
+    auto seek = [&]() {  // first chunk at or after (ci, k0) that exists
+        valid = false;
+        while (ci < nc) {
+            if (k0 == 0) c = fetch(ci);
+            if (k0 < c.k) {
+                valid = true;
+                return;
             }
-            __syncthreads();
+            ci++;
+            k0 = 0;
+        }
+    };
+    double ra[4], rb[4];
+    auto load = [&]() {
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                As[(ak + 4 * s) * GLD + arow] = ra[s];
-                if (!nn) Bs[(ak + 4 * s) * GLD + arow] = rb[s];
-                else Bs[bk_nn * GLD + bj_nn + 16 * s] = rb[s];
-            }
-            __syncthreads();
-#pragma unroll
-            for (int kk = 0; kk < GK; kk += 4) {
-                double fa[2], fb[4];
-                int kr = (kk + (lane & 3)) * GLD;
-#pragma unroll
-                for (int mi = 0; mi < 2; mi++) fa[mi] = As[kr + wm * 16 + mi * 8 + (lane >> 2)];
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) fb[ni] = Bs[kr + wn * 32 + ni * 8 + (lane >> 2)];
-#pragma unroll
-                for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], fa[mi], fb[ni]);
+        for (int s = 0; s < 4; s++) {
+            const int kk = k0 + ak + 4 * s;
+            const int gi = row0 + arow;
+            ra[s] = (gi < m && kk < c.k) ? c.A[gi + (size_t)kk * c.lda] : 0.0;
+            if (!nn) {
+                const int gj = col0 + arow;
+                rb[s] = (gj < n && kk < c.k) ? c.B[gj + (size_t)kk * c.ldb] : 0.0;
+            } else {
+                const int kk2 = k0 + bk_nn, gj = col0 + bj_nn + 16 * s;
+                rb[s] = (gj < n && kk2 < c.k) ? c.B[kk2 + (size_t)gj * c.ldb] : 0.0;
             }
         }
+    };
+    seek();
+    if (valid) load();
+    int buf = 0;
+    while (valid) {
+        double* as = As[buf];
+        double* bs = Bs[buf];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            as[(ak + 4 * s) * GLD + arow] = ra[s];
+            if (!nn) bs[(ak + 4 * s) * GLD + arow] = rb[s];
+            else bs[bk_nn * GLD + bj_nn + 16 * s] = rb[s];
+        }
+        __syncthreads();
+        k0 += GK;
+        if (k0 >= c.k) {
+            ci++;
+            k0 = 0;
+        }
+        seek();
+        if (valid) load();  // in flight during the tensor-core work below
+#pragma unroll
+        for (int kk = 0; kk < GK; kk += 4) {
+            double fa[2], fb[4];
+            const int kr = (kk + (lane & 3)) * GLD;
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) fa[mi] = as[kr + wm * 16 + mi * 8 + (lane >> 2)];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) fb[ni] = bs[kr + wn * 32 + ni * 8 + (lane >> 2)];
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], fa[mi], fb[ni]);
+        }
+        if (NBUF == 2) buf ^= 1;
+        else __syncthreads();
     }
     bool zero = (flags & GEMM_ZERO_INIT) != 0, lower = (flags & GEMM_LOWER) != 0, pos = (flags & GEMM_POS) != 0;
 #pragma unroll
@@ -529,20 +559,20 @@ __global__ void __launch_bounds__(256) trsm_strip_kernel(const TrsmTask* __restr
             double* C = Bs + (size_t)j0 * t.ldb;
             if (j > 0) {
                 c = GemmContrib{Bs, t.T + j0, t.ldb, t.ldt, j0};
-                gemm_tile64(C, t.ldb, fw, nb, 0, 0, 0, 1, [c](int) { return c; });
+                gemm_tile64<1>(C, t.ldb, fw, nb, 0, 0, 0, 1, [c](int) { return c; });
             }
             c = GemmContrib{C, inv, t.ldb, NB, nb};
-            gemm_tile64(C, t.ldb, fw, nb, GEMM_ZERO_INIT | GEMM_POS, 0, 0, 1, [c](int) { return c; });
+            gemm_tile64<1>(C, t.ldb, fw, nb, GEMM_ZERO_INIT | GEMM_POS, 0, 0, 1, [c](int) { return c; });
         } else {
             // X_j = inv(L_jj) (B_j - L_{j,0:j} X_{0:j}) on the column strip [f0, f0 + fw)
             double* Bs = t.B + (size_t)f0 * t.ldb;
             double* C = Bs + j0;
             if (j > 0) {
                 c = GemmContrib{t.T + j0, Bs, t.ldt, t.ldb, j0};
-                gemm_tile64(C, t.ldb, nb, fw, GEMM_NN, 0, 0, 1, [c](int) { return c; });
+                gemm_tile64<1>(C, t.ldb, nb, fw, GEMM_NN, 0, 0, 1, [c](int) { return c; });
             }
             c = GemmContrib{inv, C, NB, t.ldb, nb};
-            gemm_tile64(C, t.ldb, nb, fw, GEMM_NN | GEMM_ZERO_INIT | GEMM_POS, 0, 0, 1, [c](int) { return c; });
+            gemm_tile64<1>(C, t.ldb, nb, fw, GEMM_NN | GEMM_ZERO_INIT | GEMM_POS, 0, 0, 1, [c](int) { return c; });
         }
     }
 }
