@@ -11,7 +11,7 @@ lines = [l for l in open(src) if l.startswith('"')]
 per = collections.OrderedDict()  # launch id -> {name, time_us, rd, wr}
 for r in csv.DictReader(lines):
     i = int(r["ID"])
-    name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("spand::<unnamed>::", "").replace("spand::", "")
+    name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("spand::<unnamed>::", "").replace("spand::", "").replace("<unnamed>::", "").replace("unnamed>::", "")
     e = per.setdefault(i, {"name": name, "us": 0.0, "rd": 0.0, "wr": 0.0})
     v = float(r["Metric Value"].replace(",", ""))
     u = r["Metric Unit"]
