@@ -79,7 +79,8 @@ int spand_gmres(spand_tree* t, int N, const int* colptr, const int* rowind, cons
  * min(rows, cols), unit diagonal implicit) and tau hold the Householder reflectors. G / nthreads / in_smem / nb select
  * the launch shape (cluster width, CTA size, panel in shared (1) or global (0) memory, block size); theta > 0 selects the
  * hot / cold variant for global panels; in_smem = 2 selects the hot-set kernel (nb = capacity of its shared-memory hot
- * set, in columns). Kernel-level parity tests drive every shape through this entry. */
+ * set, in columns); in_smem = 3 selects the column kernel (rows <= 64, one thread per column, nthreads = 128 or 256).
+ * Kernel-level parity tests drive every shape through this entry. */
 int spand_geqp3_truncated(int rows, int cols, const double* A, int nsrc, int transposed, double tol, int G,
                           int nthreads, int in_smem, int nb, double theta, int* rank, double* R, double* V, double* tau);
 

@@ -123,7 +123,8 @@ def _csc(A):
             np.ascontiguousarray(A.data, dtype=np.float64))
 
 
-def geqp3_truncated(A, tol, nsrc=1, transposed=False, G=1, nthreads=256, in_smem=False, nb=8, theta=0.5, hot=0):
+def geqp3_truncated(A, tol, nsrc=1, transposed=False, G=1, nthreads=256, in_smem=False, nb=8, theta=0.5, hot=0,
+                    col=False):
     """geqp3 + choose_rank + triu(R[:rank]) P^T of one dense matrix through the batched sparsification kernel
     (reference src/util.cpp:383-452, src/tree.cpp:1334-1335). Returns (rank, AsnP or None when rank >= rows, V, tau)."""
     A = np.asarray(A, dtype=np.float64)
@@ -141,6 +142,8 @@ def geqp3_truncated(A, tol, nsrc=1, transposed=False, G=1, nthreads=256, in_smem
     fn.argtypes = [_i, _i, _dp, _i, _i, _d, _i, _i, _i, _i, _d, C.POINTER(C.c_int), _dp, _dp, _dp]
     if hot > 0:  # hot-set kernel (rrqr_hc2.cu): in_smem = 2, nb carries the capacity of the hot set
         in_smem, nb = 2, hot
+    if col:  # column kernel (rows <= 64, one thread per column): in_smem = 3
+        in_smem = 3
     rc = fn(rows, cols, np.ascontiguousarray(flat), nsrc, int(transposed), float(tol), G, nthreads, int(in_smem), nb,
             float(theta), C.byref(rank), R, V, tau)
     if rc != 0:

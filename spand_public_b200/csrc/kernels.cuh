@@ -188,6 +188,12 @@ size_t hc2_exchange_doubles(int rows, int G);
 void launch_rrqr_hc2(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int row_pairs, int smem,
                      double theta, cudaStream_t st);
 void hc2_stats(unsigned long long* out16, bool reset);  // -DSPAND_RRQR_TIMING builds
+// Column kernel (rrqr_hc2.cu): panels of at most 64 rows resident in the shared memory of one CTA, one thread per
+// column (no reductions over the short rows). t.ld = rrqr_col_ld(rows).
+int rrqr_col_ld(int rows);
+size_t rrqr_col_smem_bytes(int rows, int maxcols, int nsrc);
+void launch_rrqr_col(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int nthreads, int smem,
+                     cudaStream_t st);
 int rrqr_max_smem();
 // one dense matrix through the batch kernels (kernel-level tests); see rrqr.cu
 int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transposed, double tol, int G, int nthreads,

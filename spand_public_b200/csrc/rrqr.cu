@@ -941,19 +941,29 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc_kernel(const QrTask* __restr
                 for (int mt = 0; mt < MT; mt++) y0[mt][0] = y0[mt][1] = y1[mt][0] = y1[mt][1] = 0.0;
                 const bool colok = first + g < ncl;
                 const double2* pc2 = reinterpret_cast<const double2*>(P + (size_t)(first + (colok ? g : 0)) * ld);
-#pragma unroll 2
-                for (int r = kb0 & ~7; r < ldv; r += 8) {
-                    const int rr = r + 2 * q;
-                    const bool rok = rr < ldv;
-                    double2 b = make_double2(0.0, 0.0);
-                    if (colok && rok) b = pc2[rr >> 1];
+                // eight 16-byte loads in flight per lane (64 rows of the strip) before the tensor-core work on them
+                for (int rb = kb0 & ~7; rb < ldv; rb += 64) {
+                    double2 bq[8];
 #pragma unroll
-                    for (int mt = 0; mt < MT; mt++) {
-                        const int tt = mt * 8 + g;
-                        double2 a = make_double2(0.0, 0.0);
-                        if (tt < jc && rok) a = *reinterpret_cast<const double2*>(Vs + rr + (size_t)tt * ldv);
-                        dmma_f64(y0[mt][0], y0[mt][1], a.x, b.x);
-                        dmma_f64(y1[mt][0], y1[mt][1], a.y, b.y);
+                    for (int u = 0; u < 8; u++) {
+                        const int rr = rb + 8 * u + 2 * q;
+                        bq[u] = make_double2(0.0, 0.0);
+                        if (colok && rr < ldv) bq[u] = pc2[rr >> 1];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int rr = rb + 8 * u + 2 * q;
+                        const bool rok = rr < ldv;
+#pragma unroll
+                        for (int mt = 0; mt < MT; mt++) {
+                            if (mt * 8 < jc) {  // uniform
+                                const int tt = mt * 8 + g;
+                                double2 a = make_double2(0.0, 0.0);
+                                if (tt < jc && rok) a = *reinterpret_cast<const double2*>(Vs + rr + (size_t)tt * ldv);
+                                dmma_f64(y0[mt][0], y0[mt][1], a.x, bq[u].x);
+                                dmma_f64(y1[mt][0], y1[mt][1], a.y, bq[u].y);
+                            }
+                        }
                     }
                 }
 #pragma unroll
@@ -986,40 +996,37 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc_kernel(const QrTask* __restr
             double* colB = colA + ld;
             double nA = 0.0, nB = 0.0;
             const int r_lo = (cm ? kb0 : kend) & ~7;
-            for (int r = r_lo; r < rows; r += 16) {
-                const int row0 = r + g, row1 = r + 8 + g;
-                const bool okA0 = actA && row0 >= loA && row0 < rows, okA1 = actA && row1 >= loA && row1 < rows;
-                const bool okB0 = actB && row0 >= loB && row0 < rows, okB1 = actB && row1 >= loB && row1 < rows;
-                double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-                if (okA0) c00 = colA[row0];
-                if (okB0) c01 = colB[row0];
-                if (okA1) c10 = colA[row1];
-                if (okB1) c11 = colB[row1];
+            for (int r = r_lo; r < rows; r += 32) {  // four tiles of 8 rows: eight loads in flight per lane
+                double cA[4], cB[4];
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const int row = r + 8 * h + g;
+                    cA[h] = (actA && row >= loA && row < rows) ? colA[row] : 0.0;
+                    cB[h] = (actB && row >= loB && row < rows) ? colB[row] : 0.0;
+                }
 #pragma unroll
                 for (int kk = 0; kk < QNB / 4; kk++) {
                     const int tt = kk * 4 + q;
                     if (kk * 4 < jc) {  // uniform
-                        const double a0 = (tt < jc && row0 < ldv) ? -Vs[row0 + (size_t)tt * ldv] : 0.0;
-                        const double a1 = (tt < jc && row1 < ldv) ? -Vs[row1 + (size_t)tt * ldv] : 0.0;
-                        dmma_f64(c00, c01, a0, bf[kk]);
-                        dmma_f64(c10, c11, a1, bf[kk]);
+#pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            const int row = r + 8 * h + g;
+                            const double av = (tt < jc && row < ldv) ? -Vs[row + (size_t)tt * ldv] : 0.0;
+                            dmma_f64(cA[h], cB[h], av, bf[kk]);
+                        }
                     }
                 }
-                if (okA0) {
-                    colA[row0] = c00;
-                    if (row0 >= kend) nA = fma(c00, c00, nA);
-                }
-                if (okB0) {
-                    colB[row0] = c01;
-                    if (row0 >= kend) nB = fma(c01, c01, nB);
-                }
-                if (okA1) {
-                    colA[row1] = c10;
-                    if (row1 >= kend) nA = fma(c10, c10, nA);
-                }
-                if (okB1) {
-                    colB[row1] = c11;
-                    if (row1 >= kend) nB = fma(c11, c11, nB);
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const int row = r + 8 * h + g;
+                    if (actA && row >= loA && row < rows) {
+                        colA[row] = cA[h];
+                        if (row >= kend) nA = fma(cA[h], cA[h], nA);
+                    }
+                    if (actB && row >= loB && row < rows) {
+                        colB[row] = cB[h];
+                        if (row >= kend) nB = fma(cB[h], cB[h], nB);
+                    }
                 }
             }
             if (cm) {  // exact squared norms of the cold columns (sum over the 8 row groups, fixed order)
@@ -1566,6 +1573,18 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
         t.ld = ld = (rows + 1) & ~1;
         smem = hc2_smem_bytes(rows, cols, G, t.hcap, nsrc);
     }
+    const bool colk = in_smem == 3;  // column kernel: rows <= 64, panel in the shared memory of one CTA
+    if (colk) {
+        if (rows > 64 || G != 1) {
+            err = "rrqr_single: the column kernel takes panels of at most 64 rows on one CTA";
+            return -1;
+        }
+        t.in_smem = 1;
+        t.L = 1;
+        t.nb = 1;
+        t.ld = ld = rrqr_col_ld(rows);
+        smem = rrqr_col_smem_bytes(rows, cols, nsrc);
+    }
     if (smem > (size_t)rrqr_max_smem()) {
         err = "rrqr_single: shape does not fit the shared memory of one CTA";
         return -1;
@@ -1657,7 +1676,8 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
         try {
             for (int rep = 0; rep < 2; rep++) {
                 if (rep == 1) cudaEventRecord(e0, 0);
-                if (hc2) launch_rrqr_hc2(bt + rep * copies, copies, bs, bcs, tol, G, hc2_row_pairs(rows), sm, theta, 0);
+                if (colk) launch_rrqr_col(bt + rep * copies, copies, bs, bcs, tol, nthreads, sm, 0);
+                else if (hc2) launch_rrqr_hc2(bt + rep * copies, copies, bs, bcs, tol, G, hc2_row_pairs(rows), sm, theta, 0);
                 else launch_rrqr(bt + rep * copies, copies, bs, bcs, tol, G, nthreads, in_smem != 0, sm, 0, theta);
             }
             cudaEventRecord(e1, 0);
@@ -1677,7 +1697,9 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
     }
     int rc = 0;
     try {
-        if (hc2)
+        if (colk)
+            launch_rrqr_col(dt, 1, ds, dcs, tol, nthreads, (int)((smem + 1023) & ~(size_t)1023), 0);
+        else if (hc2)
             launch_rrqr_hc2(dt, 1, ds, dcs, tol, G, hc2_row_pairs(rows), (int)((smem + 1023) & ~(size_t)1023), theta, 0);
         else
             launch_rrqr(dt, 1, ds, dcs, tol, G, nthreads, in_smem != 0, (int)((smem + 1023) & ~(size_t)1023), 0, theta);

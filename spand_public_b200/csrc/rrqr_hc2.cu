@@ -1065,6 +1065,256 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
     HT(9)
 }
 
+// ------------------------------------------------------------------------------------------------
+// Short panels (rows <= 64) that fit the shared memory of one CTA: one THREAD per column.
+// The lower levels have tens of thousands of panels of 9-47 rows and 100-600 columns. With lanes along the rows
+// (the other kernels) such a panel pays warp reductions and several block barriers per Householder step for a few
+// flops; here a thread owns whole columns and runs down their (short) rows serially: no reduction over rows at all,
+// the reflector is rebuilt by every thread from the pivot column (broadcast reads), two block barriers per step.
+// Unblocked QRCP with dlaqp2's arithmetic: reflector applied at once, partial norms downdated with the dlaqps /
+// dlaqp2 safeguard (exact recomputation), LAPACK's first-index tie-breaking through virtual positions; stops at the
+// first |R_kk| / |R_00| < tol (geqp3 + choose_rank, src/util.cpp:383-452).
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) rrqr_col_kernel(const QrTask* __restrict__ tasks, const QrSrc* __restrict__ srcs,
+                                                       int* csize, double tol) {
+    constexpr int NW = NT / 32;
+    const QrTask t = tasks[blockIdx.x];
+    const QrSrc* src = srcs + t.src0;
+    const int rows = t.rows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ Cand wbest[2][NW];
+    __shared__ double rdiag[64];
+    extern __shared__ __align__(16) double dsm[];
+    const int ld = t.ld;  // odd: threads walk down neighbouring columns without bank conflicts
+    const int mce = (t.maxcols + 3) & ~3;
+    double* A = dsm;                               // ld x maxcols
+    double* n1 = A + (((size_t)ld * t.maxcols + 1) & ~(size_t)1);
+    double* n2 = n1 + mce;
+    int* pos = (int*)(n2 + mce);
+    int* soff = pos + mce;
+    for (int s = tid; s < t.nsrc; s += NT) soff[s + 1] = csize[src[s].nbr];
+    if (tid == 0) soff[0] = 0;
+    __syncthreads();
+    if (warp == 0) {
+        const int per = (t.nsrc + 31) / 32;
+        const int lo = 1 + lane * per, hi = min(t.nsrc + 1, lo + per);
+        int sum = 0;
+        for (int i = lo; i < hi; i++) sum += soff[i];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int run = incl - sum;
+        for (int i = lo; i < hi; i++) {
+            run += soff[i];
+            soff[i] = run;
+        }
+    }
+    __syncthreads();
+    const int cols = soff[t.nsrc];
+    if (rows == 0) return;
+    if (tol >= 1.0 || cols == 0) {
+        if (tid == 0) csize[t.cluster] = 0;
+        return;
+    }
+    const int mn = min(rows, cols);
+    // ---- gather (one warp per source block) ----
+    for (int s = warp; s < t.nsrc; s += NW) {
+        const int c0 = soff[s], nc = soff[s + 1] - c0;
+        if (nc <= 0) continue;
+        const QrSrc q = src[s];
+        double* dst = A + (size_t)c0 * ld;
+        const int sld = q.ld;
+        if (!q.transposed) {
+            const double* sp = q.blk;
+            warp_tile_copy(rows, nc, lane, [&](int i, int jj) { return sp[i + (size_t)jj * sld]; },
+                           [&](int i, int jj, double v) { dst[i + (size_t)jj * ld] = v; });
+        } else {
+            const double* sp = q.blk;
+            warp_tile_copy(nc, rows, lane, [&](int jj, int i) { return sp[jj + (size_t)i * sld]; },
+                           [&](int jj, int i, double v) { dst[i + (size_t)jj * ld] = v; });
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < cols; c += NT) {
+        const double* a = A + (size_t)c * ld;
+        double sm = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < rows; i++) sm = fma(a[i], a[i], sm);
+        n1[c] = sm;
+        n2[c] = sm;
+        pos[c] = c;
+    }
+    const double tol3z = sqrt(DBL_EPSILON);
+    double r00 = 0.0;
+    int rank = mn;
+    for (int k = 0; k < mn; k++) {
+        // ---- pivot: largest partial norm, smallest position on ties ----
+        Cand b{-1.0, INT_MAX, -1};
+        for (int c = tid; c < cols; c += NT) {
+            const int p = pos[c];
+            if (p >= k) {
+                const double v = n1[c];
+                if (better(v, p, b.val, b.pos)) b = Cand{v, p, c};
+            }
+        }
+        {
+            const int par = k & 1;
+            b = warp_best(b);
+            if (lane == 0) wbest[par][warp] = b;
+            __syncthreads();  // also: every column update of the previous step is visible
+            Cand bb = (lane < NW) ? wbest[par][lane] : Cand{-1.0, INT_MAX, -1};
+            b = warp_best(bb);
+        }
+        const int pc = b.col, ppos = b.pos;
+        if (pc < 0) {
+            rank = k;
+            break;
+        }
+        // ---- its reflector, rebuilt by every thread from the pivot column (nobody writes that column any more) ----
+        const double* pv = A + (size_t)pc * ld;
+        const double alpha = pv[k];
+        double ss;
+        {  // four independent partial sums: the serial runs down a column are latency chains otherwise
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int i = k + 1;
+            for (; i + 3 < rows; i += 4) {
+                s0 = fma(pv[i], pv[i], s0);
+                s1 = fma(pv[i + 1], pv[i + 1], s1);
+                s2 = fma(pv[i + 2], pv[i + 2], s2);
+                s3 = fma(pv[i + 3], pv[i + 3], s3);
+            }
+            for (; i < rows; i++) s0 = fma(pv[i], pv[i], s0);
+            ss = (s0 + s1) + (s2 + s3);
+        }
+        double beta, tau, scal;
+        if (ss == 0.0) {
+            beta = alpha;
+            tau = 0.0;
+            scal = 0.0;
+        } else {
+            beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+            tau = (beta - alpha) / beta;
+            scal = 1.0 / (alpha - beta);
+        }
+        if (k == 0) r00 = fabs(beta);
+        if (tol != 0.0 && !(fabs(beta) / r00 >= tol)) {
+            rank = k;
+            break;
+        }
+        if (tid == 0) {
+            rdiag[k] = beta;
+            t.tau[k] = tau;
+        }
+        for (int i = k + 1 + tid; i < rows; i += NT) t.V[i + (size_t)k * rows] = pv[i] * scal;
+        // ---- apply it to the own columns, downdate their norms ----
+        for (int c = tid; c < cols; c += NT) {
+            int p = pos[c];
+            if (c == pc) {
+                pos[c] = k;
+                continue;
+            }
+            if (p == k) {  // virtual swap: the column at position k takes the pivot's old place
+                p = ppos;
+                pos[c] = p;
+            }
+            if (p < k) continue;
+            double* a = A + (size_t)c * ld;
+            double w;
+            {
+                double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+                int i = k + 1;
+                for (; i + 3 < rows; i += 4) {
+                    w0 = fma(pv[i], a[i], w0);
+                    w1 = fma(pv[i + 1], a[i + 1], w1);
+                    w2 = fma(pv[i + 2], a[i + 2], w2);
+                    w3 = fma(pv[i + 3], a[i + 3], w3);
+                }
+                for (; i < rows; i++) w0 = fma(pv[i], a[i], w0);
+                w = (w0 + w1) + (w2 + w3);
+            }
+            w = fma(w, scal, a[k]);
+            const double f = tau * w;
+            const double ak = a[k] - f;
+            a[k] = ak;
+            const double fs = f * scal;
+            double q;
+            {
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+                int i = k + 1;
+                for (; i + 3 < rows; i += 4) {
+                    const double x0 = fma(-fs, pv[i], a[i]), x1 = fma(-fs, pv[i + 1], a[i + 1]);
+                    const double x2 = fma(-fs, pv[i + 2], a[i + 2]), x3 = fma(-fs, pv[i + 3], a[i + 3]);
+                    a[i] = x0;
+                    a[i + 1] = x1;
+                    a[i + 2] = x2;
+                    a[i + 3] = x3;
+                    q0 = fma(x0, x0, q0);
+                    q1 = fma(x1, x1, q1);
+                    q2 = fma(x2, x2, q2);
+                    q3 = fma(x3, x3, q3);
+                }
+                for (; i < rows; i++) {
+                    const double x = fma(-fs, pv[i], a[i]);
+                    a[i] = x;
+                    q0 = fma(x, x, q0);
+                }
+                q = (q0 + q1) + (q2 + q3);
+            }
+            const double o1 = n1[c];
+            if (o1 != 0.0) {
+                double nn = fmax(0.0, o1 - ak * ak);
+                if (nn <= tol3z * n2[c]) {  // dlaqps / dlaqp2 safeguard: exact norm of the updated column
+                    nn = q;
+                    n2[c] = q;
+                }
+                n1[c] = nn;
+            }
+        }
+        // (the barrier of the next pivot search orders these updates before anybody reads them)
+        if (k + 1 >= mn) __syncthreads();
+    }
+    __syncthreads();
+    if (rank >= rows) return;  // nothing to do (tree.cpp:1317-1319); csize unchanged
+    // ---- scatter triu(R[:rank,:]) P^T back into the edge blocks, in place (one warp per source block) ----
+    for (int s = warp; s < t.nsrc; s += NW) {
+        const int c0 = soff[s], nc = soff[s + 1] - c0;
+        if (nc <= 0) continue;
+        const QrSrc q = src[s];
+        const int sld = q.ld;
+        double* dp = q.blk;
+        auto value = [&](int i, int jj) {
+            const int p = pos[c0 + jj];
+            if (p < rank) {
+                if (i > p) return 0.0;
+                if (i == p) return rdiag[p];
+            }
+            return A[i + (size_t)(c0 + jj) * ld];
+        };
+        if (!q.transposed)
+            warp_tile_copy(rank, nc, lane, [&](int i, int jj) { return value(i, jj); },
+                           [&](int i, int jj, double v) { dp[i + (size_t)jj * sld] = v; });
+        else
+            warp_tile_copy(nc, rank, lane, [&](int jj, int i) { return value(i, jj); },
+                           [&](int jj, int i, double v) { dp[jj + (size_t)i * sld] = v; });
+    }
+    if (tid == 0) csize[t.cluster] = rank;
+}
+
+template <int NT>
+void launch_col(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int smem, cudaStream_t st) {
+    auto kern = rrqr_col_kernel<NT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<nt, NT, smem, st>>>(t, s, csize, tol);
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+        throw std::runtime_error(std::string("rrqr (column kernel) launch failed (threads=") + std::to_string(NT) +
+                                 ", smem=" + std::to_string(smem) + "): " + cudaGetErrorString(err));
+}
+
 template <int G, int NT, int NB, int RP, int MINB>
 void launch_one_hc2(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, double theta2, int smem,
                     cudaStream_t st) {
@@ -1140,6 +1390,21 @@ void hc2_stats(unsigned long long* out16, bool reset) {
         unsigned long long z[16] = {};
         cudaMemcpyToSymbol(g_hc2_stat, z, sizeof(z));
     }
+}
+
+// ---- column kernel (rows <= 64, panel in the shared memory of one CTA) ----
+int rrqr_col_ld(int rows) { return rows | 1; }
+size_t rrqr_col_smem_bytes(int rows, int maxcols, int nsrc) {
+    const size_t ld = (size_t)rrqr_col_ld(rows), mce = ((size_t)maxcols + 3) & ~(size_t)3;
+    const size_t doubles = ((ld * maxcols + 1) & ~(size_t)1) + 2 * mce;
+    return doubles * sizeof(double) + (mce + (size_t)nsrc + 2) * sizeof(int);
+}
+void launch_rrqr_col(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int nthreads, int smem,
+                     cudaStream_t st) {
+    if (nt <= 0) return;
+    if (nthreads <= 128) launch_col<128>(t, nt, s, csize, tol, smem, st);
+    else if (nthreads <= 256) launch_col<256>(t, nt, s, csize, tol, smem, st);
+    else launch_col<512>(t, nt, s, csize, tol, smem, st);
 }
 
 void launch_rrqr_hc2(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int row_pairs, int smem,

@@ -1348,6 +1348,8 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         // hot-set kernel (rrqr_hc2.cu) for panels in global memory: on unless SPAND_RRQR_HC2=0; per-CTA shared memory
         // budget (two 256-thread CTAs per SM by default), CTAs wanted per wavefront, smallest panel it takes
         const bool hc2_on = !getenv("SPAND_RRQR_HC2") || atoi(getenv("SPAND_RRQR_HC2")) != 0;
+        const bool colk_on = !getenv("SPAND_RRQR_COL") || atoi(getenv("SPAND_RRQR_COL")) != 0;
+        const long colk_max = (getenv("SPAND_RRQR_COLKB") ? atol(getenv("SPAND_RRQR_COLKB")) : 200) * 1024;
         const bool force_hc2 = getenv("SPAND_RRQR_HC2") && atoi(getenv("SPAND_RRQR_HC2")) == 2;  // every eligible panel
         const int hc2_tmin = getenv("SPAND_HC2_TMIN") ? atoi(getenv("SPAND_HC2_TMIN")) : 48;
         const int hc2_maxrows = getenv("SPAND_HC2_MAXROWS") ? atoi(getenv("SPAND_HC2_MAXROWS")) : 256;
@@ -1387,6 +1389,20 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 while (b < kNB - 1 && nd > kBuckets[b]) b++;
                 return b;
             };
+            // Short panels (the lower levels: tens of thousands of panels of 9-47 rows) that fit the shared memory of
+            // one CTA: one thread per column, no reductions over the rows (rrqr_col_kernel)
+            if (colk_on && !force_global && force_g == 0 && !smem_mode && t.rows <= 64 && t.rows > 0 && t.maxcols > 0) {
+                const long cb = (long)rrqr_col_smem_bytes(t.rows, t.maxcols, t.nsrc);
+                if (cb <= colk_max) {
+                    t.ld = rrqr_col_ld(t.rows);
+                    t.L = 1;
+                    t.nb = 1;
+                    t.in_smem = 1;
+                    klass[i] = (6 << 8) | ((t.maxcols <= 128 ? 0 : (t.maxcols <= 256 ? 1 : 2)) << 4) | bucket_of(cb);
+                    smem_need[i] = (int)cb;
+                    continue;
+                }
+            }
             long nd = config(128, 1, true);
             if (!force_global && force_g == 0 && t.rows <= 64 && nd <= kBuckets[2]) {
                 klass[i] = bucket_of(nd);
@@ -1550,7 +1566,9 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                         CK(cudaEventCreate(&tr1));
                         CK(cudaEventRecord(tr0, s));
                     }
-                    if (mode == 5) {
+                    if (mode == 6) {
+                        launch_rrqr_col(dt + b, (int)(e - b), ds, d_csize_, tol, 128 << ((k >> 4) & 15), smem, s);
+                    } else if (mode == 5) {
                         static const int kRowPairs[4] = {2, 4, 6, 10};
                         launch_rrqr_hc2(dt + b, (int)(e - b), ds, d_csize_, tol, G, kRowPairs[k & 15], smem, hc2_theta, s);
                     } else

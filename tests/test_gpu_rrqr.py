@@ -55,6 +55,15 @@ SHAPES = [
     (400, 2400, 0.975, 1e-2, dict(G=16, nthreads=512, in_smem=False, nb=16, theta=0.5, nsrc=2)),
     (400, 2400, 0.975, 1e-2, dict(G=16, nthreads=512, in_smem=False, nb=16, theta=0.0)),
     (629, 2600, 0.985, 1e-2, dict(G=16, nthreads=512, in_smem=False, nb=16, theta=0.5)),
+    # column kernel (rows <= 64, one thread per column, panel in the shared memory of one CTA)
+    (9, 116, 0.6, 1e-2, dict(col=True, nthreads=128)),
+    (9, 116, 0.95, 1e-2, dict(col=True, nthreads=128, nsrc=4)),           # full rank: nothing happens
+    (17, 200, 0.8, 1e-2, dict(col=True, nthreads=128, nsrc=5, transposed=True)),
+    (31, 516, 0.85, 1e-2, dict(col=True, nthreads=256, nsrc=3)),
+    (47, 462, 0.88, 1e-2, dict(col=True, nthreads=256, nsrc=6, transposed=True)),
+    (64, 380, 0.9, 1e-2, dict(col=True, nthreads=256)),
+    (40, 30, 0.8, 1e-3, dict(col=True, nthreads=128)),                     # cols < rows
+    (33, 300, 0.8, 0.0, dict(col=True, nthreads=256)),                     # tol = 0
     # hot-set kernel (rrqr_hc2.cu): capacities from "everything hot" down to 1, all cluster widths, all row classes
     (60, 480, 0.85, 1e-2, dict(G=1, hot=64)),
     (60, 480, 0.85, 1e-2, dict(G=1, hot=300)),
@@ -114,6 +123,10 @@ def test_hot_cold_equals_full_sweep_on_tied_columns():
     A = np.concatenate([A, A], axis=1)
     r0, R0, _, _ = S.geqp3_truncated(A, 1e-2, G=2, nthreads=256, in_smem=False, nb=8, theta=0.0)
     r1, R1, _, _ = S.geqp3_truncated(A, 1e-2, G=2, nthreads=256, in_smem=False, nb=8, theta=0.5)
+    B = np.concatenate([A[:40, :150], A[:40, :150]], axis=1)  # 40 x 300, every column twice
+    rb0, RB0, _, _ = S.geqp3_truncated(B, 1e-2, G=1, nthreads=256, in_smem=True, nb=16)
+    rb1, RB1, _, _ = S.geqp3_truncated(B, 1e-2, col=True, nthreads=256)
+    assert rb0 == rb1 and np.abs(RB1 - RB0).max() <= 1e-11 * np.abs(RB0).max()
     r2, R2, _, _ = S.geqp3_truncated(A, 1e-2, G=2, hot=16)
     r3, R3, _, _ = S.geqp3_truncated(A, 1e-2, G=1, hot=200)
     rank_ref, R_ref, _ = _reference(A, 1e-2)
