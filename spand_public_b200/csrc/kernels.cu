@@ -1661,6 +1661,19 @@ void launch_scatter_values(const double* val, const unsigned* map, size_t n, dou
     if (n > 0) scatter_values_kernel<<<grid_for(n, 256), 256, 0, st>>>(val, map, n, dst);
 }
 
+__global__ void err_publish_kernel(const int* err, int* shared_word) { *shared_word = *err; }
+__global__ void err_or_kernel(PeerPtrs words, int nranks, int* err) {
+    int e = 0;
+    for (int r = 0; r < nranks; r++) e |= *reinterpret_cast<volatile int*>(words.p[r]);
+    *err |= e;
+}
+void launch_err_publish(const int* err, int* shared_word, cudaStream_t st) {
+    err_publish_kernel<<<1, 1, 0, st>>>(err, shared_word);
+}
+void launch_err_or(const PeerPtrs& words, int nranks, int* err, cudaStream_t st) {
+    err_or_kernel<<<1, 1, 0, st>>>(words, nranks, err);
+}
+
 void launch_peer_barrier(const PeerPtrs& flags, int rank, int nranks, unsigned epoch, cudaStream_t st) {
     peer_barrier_kernel<<<1, 32, 0, st>>>(flags, rank, nranks, epoch);
 }

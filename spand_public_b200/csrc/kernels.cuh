@@ -259,6 +259,10 @@ struct PeerPtrs {
     void* p[MG_MAX_RANKS];
 };
 void launch_peer_barrier(const PeerPtrs& flags, int rank, int nranks, unsigned epoch, cudaStream_t st);
+// Error flag of a sharded factorization: every rank publishes its flag word in its shared arena, then ORs the words
+// of all ranks into its own flag (between two peer barriers), so that all ranks report the same error together.
+void launch_err_publish(const int* err, int* shared_word, cudaStream_t st);
+void launch_err_or(const PeerPtrs& words, int nranks, int* err, cudaStream_t st);
 // csize[first, first + n) <- min over ranks (sizes only shrink: the replica that ran the RRQR holds the rank)
 void launch_csize_min(const PeerPtrs& csize, int rank, int nranks, int first, int n, cudaStream_t st);
 // x[idx[i]] = leaf_r[i] with r = dof_owner[i]: collects the solution segments from their owners

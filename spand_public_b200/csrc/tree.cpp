@@ -631,6 +631,17 @@ void Tree::check_error() {
     // launch-configuration errors are only reported by the launch itself / cudaGetLastError
     const cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) throw std::runtime_error(std::string("CUDA launch error: ") + cudaGetErrorString(le));
+    if (mg()) {
+        // Sharded: a non-SPD / singular pivot found by one rank must stop all of them at the same point (a rank that
+        // left the level loop alone would leave its peers spinning in the next peer barrier). Word 512 of every
+        // rank's shared arena carries its flag.
+        PeerPtrs words{};
+        for (int r = 0; r < mg_nranks; r++) words.p[r] = mg_base_[r] + 2048;
+        launch_err_publish(d_err_, reinterpret_cast<int*>(mg_base_[mg_rank] + 2048), st_);
+        mg_barrier();
+        launch_err_or(words, mg_nranks, d_err_, st_);
+        mg_barrier();  // nobody publishes again before everybody has read
+    }
     int err = 0;
     CK(cudaMemcpyAsync(&err, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));

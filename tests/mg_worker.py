@@ -65,6 +65,26 @@ def main():
         out.append(rec)
         del sh, one
         dist.barrier()
+    # error propagation: an indefinite matrix (non-SPD pivot on whichever rank owns the offending cluster) must make
+    # EVERY rank fail at the same point instead of leaving the others in a peer barrier
+    import scipy.sparse as sp
+    A = (S.neglapl(16, 3) - 5.5 * sp.identity(16**3, format="csc")).tocsc()
+    t = S.Tree(6)
+    t.set_device(local_rank)
+    t.mg_init(dist, device=local_rank, arena_gb=float(os.environ.get("SPAND_MG_ARENA_GB", "8")))
+    t.set_tol(1e-2)
+    t.set_use_geo(True)
+    t.set_Xcoo(S.linspace_nd(16, 3))
+    t.partition(S.symmetric_graph(A))
+    t.assemble(A)
+    msg = ""
+    try:
+        t.factorize()
+    except RuntimeError as ex:
+        msg = str(ex)
+    out.append(dict(cfg=[16, 3, 6, -1.0], error_case=True, raised="Non-SPD" in msg, message=msg.strip()))
+    del t
+    dist.barrier()
     allrec = [None] * world
     dist.all_gather_object(allrec, out)
     if rank == 0:

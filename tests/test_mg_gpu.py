@@ -26,6 +26,9 @@ def test_two_gpu_sharding_matches_one_gpu():
     assert len(per_rank) == nproc
     for recs in per_rank:
         for rec in recs:
+            if rec.get("error_case"):
+                assert rec["raised"], rec  # every rank reports the non-SPD pivot, nobody hangs
+                continue
             tol = rec["cfg"][3]
             assert rec["repeat_x"], rec                       # the sharded solve itself is reproducible
             assert rec["residual"] <= max(200 * tol, 1e-10), rec
