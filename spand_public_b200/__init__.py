@@ -142,8 +142,8 @@ def geqp3_truncated(A, tol, nsrc=1, transposed=False, G=1, nthreads=256, in_smem
     fn.argtypes = [_i, _i, _dp, _i, _i, _d, _i, _i, _i, _i, _d, C.POINTER(C.c_int), _dp, _dp, _dp]
     if hot > 0:  # hot-set kernel (rrqr_hc2.cu): in_smem = 2, nb carries the capacity of the hot set
         in_smem, nb = 2, hot
-    if col:  # column kernel (rows <= 64, one thread per column): in_smem = 3
-        in_smem = 3
+    if col:  # column kernel (one thread per column): in_smem = 3 (panel in shared memory) / 4 ("gp": panel in L2)
+        in_smem = 4 if col == "gp" else 3
     rc = fn(rows, cols, np.ascontiguousarray(flat), nsrc, int(transposed), float(tol), G, nthreads, int(in_smem), nb,
             float(theta), C.byref(rank), R, V, tau)
     if rc != 0:

@@ -191,9 +191,10 @@ void hc2_stats(unsigned long long* out16, bool reset);  // -DSPAND_RRQR_TIMING b
 // Column kernel (rrqr_hc2.cu): panels of at most 64 rows resident in the shared memory of one CTA, one thread per
 // column (no reductions over the short rows). t.ld = rrqr_col_ld(rows).
 int rrqr_col_ld(int rows);
-size_t rrqr_col_smem_bytes(int rows, int maxcols, int nsrc);
+int rrqr_col_max_rows();
+size_t rrqr_col_smem_bytes(int rows, int maxcols, int nsrc, bool global_panel);
 void launch_rrqr_col(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int nthreads, int smem,
-                     cudaStream_t st);
+                     bool global_panel, cudaStream_t st);
 int rrqr_max_smem();
 // one dense matrix through the batch kernels (kernel-level tests); see rrqr.cu
 int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transposed, double tol, int G, int nthreads,

@@ -1573,17 +1573,18 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
         t.ld = ld = (rows + 1) & ~1;
         smem = hc2_smem_bytes(rows, cols, G, t.hcap, nsrc);
     }
-    const bool colk = in_smem == 3;  // column kernel: rows <= 64, panel in the shared memory of one CTA
+    const bool colk = in_smem == 3 || in_smem == 4;  // column kernel; 4: panel in global scratch instead of shared memory
+    const bool colgp = in_smem == 4;
     if (colk) {
-        if (rows > 64 || G != 1) {
-            err = "rrqr_single: the column kernel takes panels of at most 64 rows on one CTA";
+        if (rows > rrqr_col_max_rows() || G != 1) {
+            err = "rrqr_single: the column kernel takes panels of at most 128 rows on one CTA";
             return -1;
         }
-        t.in_smem = 1;
+        t.in_smem = colgp ? 0 : 1;
         t.L = 1;
         t.nb = 1;
         t.ld = ld = rrqr_col_ld(rows);
-        smem = rrqr_col_smem_bytes(rows, cols, nsrc);
+        smem = rrqr_col_smem_bytes(rows, cols, nsrc, colgp);
     }
     if (smem > (size_t)rrqr_max_smem()) {
         err = "rrqr_single: shape does not fit the shared memory of one CTA";
@@ -1676,7 +1677,7 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
         try {
             for (int rep = 0; rep < 2; rep++) {
                 if (rep == 1) cudaEventRecord(e0, 0);
-                if (colk) launch_rrqr_col(bt + rep * copies, copies, bs, bcs, tol, nthreads, sm, 0);
+                if (colk) launch_rrqr_col(bt + rep * copies, copies, bs, bcs, tol, nthreads, sm, colgp, 0);
                 else if (hc2) launch_rrqr_hc2(bt + rep * copies, copies, bs, bcs, tol, G, hc2_row_pairs(rows), sm, theta, 0);
                 else launch_rrqr(bt + rep * copies, copies, bs, bcs, tol, G, nthreads, in_smem != 0, sm, 0, theta);
             }
@@ -1698,7 +1699,7 @@ int rrqr_single(int rows, int cols, const double* A_host, int nsrc, int transpos
     int rc = 0;
     try {
         if (colk)
-            launch_rrqr_col(dt, 1, ds, dcs, tol, nthreads, (int)((smem + 1023) & ~(size_t)1023), 0);
+            launch_rrqr_col(dt, 1, ds, dcs, tol, nthreads, (int)((smem + 1023) & ~(size_t)1023), colgp, 0);
         else if (hc2)
             launch_rrqr_hc2(dt, 1, ds, dcs, tol, G, hc2_row_pairs(rows), (int)((smem + 1023) & ~(size_t)1023), theta, 0);
         else

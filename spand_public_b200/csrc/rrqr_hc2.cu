@@ -100,6 +100,7 @@ __device__ __forceinline__ Cand warp_best(Cand b) {
 //   hdr[0] best squared norm, hdr[1] = (pos, col) of it, hdr[2] = (count, -) , hdr[3] = local coldmax,
 //   hdr[8 .. 8 + HC2_BINS / 2) histogram (two bins per double); then entry e: [n1, (col, pos)]
 constexpr int HC2_BINS = 64;
+constexpr int COL_MAXROWS = 128;  // tallest panel of the column kernel
 // Doubles of the hot-column area of a CTA: the hot set itself, or (block end) the scratch of the cold refresh
 // followed by at least two TMA stages of one strip (8 columns) each.
 __host__ __device__ inline size_t hc2_scratch_doubles(int nw) {
@@ -1066,7 +1067,7 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// Short panels (rows <= 64) that fit the shared memory of one CTA: one THREAD per column.
+// Short panels (rows <= 128): one THREAD per column; panel in the shared memory of one CTA, or in L2 (GP).
 // The lower levels have tens of thousands of panels of 9-47 rows and 100-600 columns. With lanes along the rows
 // (the other kernels) such a panel pays warp reductions and several block barriers per Householder step for a few
 // flops; here a thread owns whole columns and runs down their (short) rows serially: no reduction over rows at all,
@@ -1075,7 +1076,9 @@ __global__ void __launch_bounds__(NT, MINB) rrqr_hc2_kernel(const QrTask* __rest
 // dlaqp2 safeguard (exact recomputation), LAPACK's first-index tie-breaking through virtual positions; stops at the
 // first |R_kk| / |R_00| < tol (geqp3 + choose_rank, src/util.cpp:383-452).
 // ------------------------------------------------------------------------------------------------
-template <int NT>
+// GP: the panel lives in global scratch (t.W, L2-resident) instead of shared memory: for panels that do not fit one
+// CTA's shared memory; a thread re-reads its own columns every step, which the L1 serves.
+template <int NT, bool GP>
 __global__ void __launch_bounds__(NT) rrqr_col_kernel(const QrTask* __restrict__ tasks, const QrSrc* __restrict__ srcs,
                                                        int* csize, double tol) {
     constexpr int NW = NT / 32;
@@ -1084,12 +1087,12 @@ __global__ void __launch_bounds__(NT) rrqr_col_kernel(const QrTask* __restrict__
     const int rows = t.rows;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ Cand wbest[2][NW];
-    __shared__ double rdiag[64];
+    __shared__ double rdiag[COL_MAXROWS];
     extern __shared__ __align__(16) double dsm[];
     const int ld = t.ld;  // odd: threads walk down neighbouring columns without bank conflicts
     const int mce = (t.maxcols + 3) & ~3;
-    double* A = dsm;                               // ld x maxcols
-    double* n1 = A + (((size_t)ld * t.maxcols + 1) & ~(size_t)1);
+    double* A = GP ? t.W : dsm;                    // ld x maxcols
+    double* n1 = GP ? dsm : dsm + (((size_t)ld * t.maxcols + 1) & ~(size_t)1);
     double* n2 = n1 + mce;
     int* pos = (int*)(n2 + mce);
     int* soff = pos + mce;
@@ -1304,9 +1307,9 @@ __global__ void __launch_bounds__(NT) rrqr_col_kernel(const QrTask* __restrict__
     if (tid == 0) csize[t.cluster] = rank;
 }
 
-template <int NT>
+template <int NT, bool GP>
 void launch_col(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int smem, cudaStream_t st) {
-    auto kern = rrqr_col_kernel<NT>;
+    auto kern = rrqr_col_kernel<NT, GP>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     kern<<<nt, NT, smem, st>>>(t, s, csize, tol);
     const cudaError_t err = cudaGetLastError();
@@ -1394,17 +1397,24 @@ void hc2_stats(unsigned long long* out16, bool reset) {
 
 // ---- column kernel (rows <= 64, panel in the shared memory of one CTA) ----
 int rrqr_col_ld(int rows) { return rows | 1; }
-size_t rrqr_col_smem_bytes(int rows, int maxcols, int nsrc) {
+int rrqr_col_max_rows() { return COL_MAXROWS; }
+size_t rrqr_col_smem_bytes(int rows, int maxcols, int nsrc, bool global_panel) {
     const size_t ld = (size_t)rrqr_col_ld(rows), mce = ((size_t)maxcols + 3) & ~(size_t)3;
-    const size_t doubles = ((ld * maxcols + 1) & ~(size_t)1) + 2 * mce;
+    const size_t doubles = (global_panel ? 0 : ((ld * maxcols + 1) & ~(size_t)1)) + 2 * mce;
     return doubles * sizeof(double) + (mce + (size_t)nsrc + 2) * sizeof(int);
 }
 void launch_rrqr_col(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int nthreads, int smem,
-                     cudaStream_t st) {
+                     bool global_panel, cudaStream_t st) {
     if (nt <= 0) return;
-    if (nthreads <= 128) launch_col<128>(t, nt, s, csize, tol, smem, st);
-    else if (nthreads <= 256) launch_col<256>(t, nt, s, csize, tol, smem, st);
-    else launch_col<512>(t, nt, s, csize, tol, smem, st);
+    if (global_panel) {
+        if (nthreads <= 128) launch_col<128, true>(t, nt, s, csize, tol, smem, st);
+        else if (nthreads <= 256) launch_col<256, true>(t, nt, s, csize, tol, smem, st);
+        else launch_col<512, true>(t, nt, s, csize, tol, smem, st);
+    } else {
+        if (nthreads <= 128) launch_col<128, false>(t, nt, s, csize, tol, smem, st);
+        else if (nthreads <= 256) launch_col<256, false>(t, nt, s, csize, tol, smem, st);
+        else launch_col<512, false>(t, nt, s, csize, tol, smem, st);
+    }
 }
 
 void launch_rrqr_hc2(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, int G, int row_pairs, int smem,

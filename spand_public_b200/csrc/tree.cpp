@@ -1359,8 +1359,16 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         // hot-set kernel (rrqr_hc2.cu) for panels in global memory: on unless SPAND_RRQR_HC2=0; per-CTA shared memory
         // budget (two 256-thread CTAs per SM by default), CTAs wanted per wavefront, smallest panel it takes
         const bool hc2_on = !getenv("SPAND_RRQR_HC2") || atoi(getenv("SPAND_RRQR_HC2")) != 0;
+        const int top_g = getenv("SPAND_RRQR_GTOP") ? atoi(getenv("SPAND_RRQR_GTOP")) : 0;
+        const int gtop_switch = getenv("SPAND_RRQR_GTOP_SWITCH") ? atoi(getenv("SPAND_RRQR_GTOP_SWITCH")) : 8;
+        const int cluster_ctas = getenv("SPAND_RRQR_WANT") ? atoi(getenv("SPAND_RRQR_WANT")) : 296;
+        const int colk_maxrows = std::min(rrqr_col_max_rows(),
+                                          getenv("SPAND_RRQR_COLROWS") ? atoi(getenv("SPAND_RRQR_COLROWS")) : 64);
+        // panel of the column kernel in L2 instead of shared memory: 0 never (default: measured 2.7x slower at level 3 of
+        // C4, thread-private column walks thrash the L1), 1 always, 2 when it does not fit shared memory
+        const int colk_gp = getenv("SPAND_RRQR_COLGP") ? atoi(getenv("SPAND_RRQR_COLGP")) : 0;
         const bool colk_on = !getenv("SPAND_RRQR_COL") || atoi(getenv("SPAND_RRQR_COL")) != 0;
-        const long colk_max = (getenv("SPAND_RRQR_COLKB") ? atol(getenv("SPAND_RRQR_COLKB")) : 200) * 1024;
+        const long colk_max = (getenv("SPAND_RRQR_COLKB") ? atol(getenv("SPAND_RRQR_COLKB")) : 222) * 1024;
         const bool force_hc2 = getenv("SPAND_RRQR_HC2") && atoi(getenv("SPAND_RRQR_HC2")) == 2;  // every eligible panel
         const int hc2_tmin = getenv("SPAND_HC2_TMIN") ? atoi(getenv("SPAND_HC2_TMIN")) : 48;
         const int hc2_maxrows = getenv("SPAND_HC2_MAXROWS") ? atoi(getenv("SPAND_HC2_MAXROWS")) : 256;
@@ -1402,15 +1410,20 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             };
             // Short panels (the lower levels: tens of thousands of panels of 9-47 rows) that fit the shared memory of
             // one CTA: one thread per column, no reductions over the rows (rrqr_col_kernel)
-            if (colk_on && !force_global && force_g == 0 && !smem_mode && t.rows <= 64 && t.rows > 0 && t.maxcols > 0) {
-                const long cb = (long)rrqr_col_smem_bytes(t.rows, t.maxcols, t.nsrc);
-                if (cb <= colk_max) {
+            if (colk_on && !force_global && force_g == 0 && !smem_mode && t.rows <= colk_maxrows && t.rows > 0 &&
+                t.maxcols > 0) {
+                const long cb = (long)rrqr_col_smem_bytes(t.rows, t.maxcols, t.nsrc, false);
+                const bool gp = colk_gp == 1 || (colk_gp != 0 && cb > colk_max);  // panel in L2 when it does not fit
+                if (gp || cb <= colk_max) {
+                    const long need = gp ? (long)rrqr_col_smem_bytes(t.rows, t.maxcols, t.nsrc, true) : cb;
                     t.ld = rrqr_col_ld(t.rows);
                     t.L = 1;
                     t.nb = 1;
-                    t.in_smem = 1;
-                    klass[i] = (6 << 8) | ((t.maxcols <= 128 ? 0 : (t.maxcols <= 256 ? 1 : 2)) << 4) | bucket_of(cb);
-                    smem_need[i] = (int)cb;
+                    t.in_smem = gp ? 0 : 1;
+                    if (gp) t.W = scratch_->alloc_n<double>((size_t)t.ld * t.maxcols);
+                    klass[i] = ((gp ? 7 : 6) << 8) | ((t.maxcols <= 128 ? 0 : (t.maxcols <= 256 ? 1 : 2)) << 4) |
+                               bucket_of(need);
+                    smem_need[i] = (int)need;
                     continue;
                 }
             }
@@ -1500,7 +1513,7 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             // Cluster size: wide enough that the wavefront fills the GPU (about two CTAs per SM), at least what the
             // panel needs to stay in shared memory.
             int want = 1;
-            while (want < 16 && per_color[task_color[i]] * want < 296) want *= 2;
+            while (want < 16 && per_color[task_color[i]] * want < cluster_ctas) want *= 2;
             if (force_g > 0) want = force_g;
             int g = 0;
             while ((1 << g) < want) g++;
@@ -1523,15 +1536,24 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                 smem_need[i] = (int)nd;
                 continue;
             }
-            // panel stays in the scratch arena: 16 CTAs stream their slabs from L2
-            nd = config(512, 16, false);
+            // panel stays in the scratch arena: a cluster of 512-thread CTAs streams its slabs from L2. 16 CTAs for
+            // the narrowest wavefronts; a 16-CTA cluster needs a whole GPC (8 of them), so wavefronts of more than
+            // gtop_switch panels use 8 (two clusters per GPC, shorter cluster barriers)
+            int gtop = top_g > 0 ? top_g : (per_color_own[task_color[i]] > gtop_switch ? 8 : 16);
+            nd = config(512, gtop, false);
+            while (nd > MAXS && gtop < 16) {
+                gtop *= 2;
+                nd = config(512, gtop, false);
+            }
             while (nd > MAXS && t.nb > 2) {
                 t.nb /= 2;
-                nd = config(512, 16, false);
+                nd = config(512, gtop, false);
             }
             if (nd > MAXS) throw std::runtime_error("sparsify: interface cluster too large for the RRQR kernel");
             t.W = scratch_->alloc_n<double>((size_t)t.ld * t.maxcols);
-            klass[i] = (2 << 8) | (4 << 4) | bucket_of(nd);
+            int glog = 0;
+            while ((1 << glog) < gtop) glog++;
+            klass[i] = (2 << 8) | (glog << 4) | bucket_of(nd);
             smem_need[i] = (int)nd;
         }
         // order tasks by (colour, class), stable
@@ -1577,8 +1599,8 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
                         CK(cudaEventCreate(&tr1));
                         CK(cudaEventRecord(tr0, s));
                     }
-                    if (mode == 6) {
-                        launch_rrqr_col(dt + b, (int)(e - b), ds, d_csize_, tol, 128 << ((k >> 4) & 15), smem, s);
+                    if (mode == 6 || mode == 7) {
+                        launch_rrqr_col(dt + b, (int)(e - b), ds, d_csize_, tol, 128 << ((k >> 4) & 15), smem, mode == 7, s);
                     } else if (mode == 5) {
                         static const int kRowPairs[4] = {2, 4, 6, 10};
                         launch_rrqr_hc2(dt + b, (int)(e - b), ds, d_csize_, tol, G, kRowPairs[k & 15], smem, hc2_theta, s);

@@ -62,6 +62,10 @@ SHAPES = [
     (31, 516, 0.85, 1e-2, dict(col=True, nthreads=256, nsrc=3)),
     (47, 462, 0.88, 1e-2, dict(col=True, nthreads=256, nsrc=6, transposed=True)),
     (64, 380, 0.9, 1e-2, dict(col=True, nthreads=256)),
+    (49, 692, 0.88, 1e-2, dict(col="gp", nthreads=512, nsrc=4)),           # panel in L2 (does not fit shared memory)
+    (89, 948, 0.93, 1e-2, dict(col="gp", nthreads=512, nsrc=6, transposed=True)),
+    (128, 700, 0.95, 1e-2, dict(col="gp", nthreads=256)),
+    (100, 200, 0.9, 1e-2, dict(col=True, nthreads=256)),
     (40, 30, 0.8, 1e-3, dict(col=True, nthreads=128)),                     # cols < rows
     (33, 300, 0.8, 0.0, dict(col=True, nthreads=256)),                     # tol = 0
     # hot-set kernel (rrqr_hc2.cu): capacities from "everything hot" down to 1, all cluster widths, all row classes
