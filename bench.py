@@ -312,12 +312,12 @@ def main():
             probe[th] = tt[0]
         cores = min(probe, key=probe.get)
         # Like for like: the workload itself whenever (steps + warmup) repetitions of it fit the time budget of this
-        # arm (SPAND_REF_BUDGET_S, default 1200 s), otherwise the largest member of the same family that does. Cost
+        # arm (SPAND_REF_BUDGET_S, default 900 s), otherwise the largest member of the same family that does. Cost
         # of one factorize() relative to C2, measured with the oracle on two hosts (tests/golden/*_oracle.json.gz:
         # 64^3 14.9 s, 128^3 176 s where C2 takes 0.6 s; the GPU boxes run the same ratios 2.3x faster).
         rel = {"c1": 0.02, "c2": 1.0, "c3": 8.0, "s48": 8.0, "s64": 25.0, "s80": 55.0, "s96": 105.0, "c4": 300.0,
                "a48": 14.0, "c5s": 230.0, "c5": 1500.0}
-        budget = float(os.environ.get("SPAND_REF_BUDGET_S", "1200"))
+        budget = float(os.environ.get("SPAND_REF_BUDGET_S", "900"))
         reps = max(1, args.steps + args.warmup)
         family = ["c5", "c5s", "a48"] if args.config in ANISO else (
             [args.config] if args.config in ("c1", "c2", "c3") else ["c4", "s96", "s80", "s64", "s48"])

@@ -1539,17 +1539,19 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             // panel stays in the scratch arena: a cluster of 512-thread CTAs streams its slabs from L2. 16 CTAs for
             // the narrowest wavefronts; a 16-CTA cluster needs a whole GPC (8 of them), so wavefronts of more than
             // gtop_switch panels use 8 (two clusters per GPC, shorter cluster barriers)
+            // (the hot/cold kernel keeps 20 KB of static shared memory: per-warp Y tiles, T, records)
+            const long MAXS_HC = MAXS - 24 * 1024;
             int gtop = top_g > 0 ? top_g : (per_color_own[task_color[i]] > gtop_switch ? 8 : 16);
             nd = config(512, gtop, false);
-            while (nd > MAXS && gtop < 16) {
+            while (nd > MAXS_HC && gtop < 16) {
                 gtop *= 2;
                 nd = config(512, gtop, false);
             }
-            while (nd > MAXS && t.nb > 2) {
+            while (nd > MAXS_HC && t.nb > 2) {
                 t.nb /= 2;
                 nd = config(512, gtop, false);
             }
-            if (nd > MAXS) throw std::runtime_error("sparsify: interface cluster too large for the RRQR kernel");
+            if (nd > MAXS_HC) throw std::runtime_error("sparsify: interface cluster too large for the RRQR kernel");
             t.W = scratch_->alloc_n<double>((size_t)t.ld * t.maxcols);
             int glog = 0;
             while ((1 << glog) < gtop) glog++;

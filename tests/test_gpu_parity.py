@@ -164,7 +164,12 @@ def test_full_factorization_vs_oracle(n, d, L, tol, coords):
     assert np.linalg.norm(A @ xg - b) / np.linalg.norm(b) < 1e-11
 
 
-@pytest.mark.parametrize("env", [{"SPAND_RRQR_FORCE_GLOBAL": "1"}, {"SPAND_RRQR_FORCE_G": "1"}, {"SPAND_RRQR_FORCE_G": "2"},
+@pytest.mark.parametrize("env", [{"SPAND_RRQR_FORCE_GLOBAL": "1"}, {"SPAND_RRQR_FORCE_GLOBAL": "1", "SPAND_RRQR_GTOP": "8"},
+                                 {"SPAND_RRQR_FORCE_GLOBAL": "1", "SPAND_RRQR_GTOP": "2", "SPAND_RRQR_THETA": "0.9"},
+                                 {"SPAND_RRQR_COL": "0"}, {"SPAND_RRQR_COL": "0", "SPAND_RRQR_HC2": "2", "SPAND_HC2_MINKB": "0"},
+                                 {"SPAND_RRQR_COL": "0", "SPAND_RRQR_HC2": "2", "SPAND_HC2_MINKB": "0", "SPAND_HC2_TMA": "1"},
+                                 {"SPAND_RRQR_COLGP": "1", "SPAND_RRQR_COLROWS": "128"},
+                                 {"SPAND_RRQR_FORCE_G": "1"}, {"SPAND_RRQR_FORCE_G": "2"},
                                  {"SPAND_RRQR_FORCE_G": "4"}, {"SPAND_RRQR_FORCE_G": "8"}, {"SPAND_RRQR_FORCE_G": "16"},
                                  {"SPAND_RRQR_MODE": "smem"},
                                  {"SPAND_RRQR_TMIN": "1", "SPAND_RRQR_SMEM1KB": "0"},
