@@ -1349,6 +1349,13 @@ template <int G>
 void launch_hc2_g(const QrTask* t, int nt, const QrSrc* s, int* csize, double tol, double th2, int rp, int smem,
                   cudaStream_t st) {
     // 512 threads, one CTA per SM (128 registers per thread, up to 224 KB of shared memory for the hot set)
+    // SPAND_HC2_NT=256: panels of up to 256 rows on 256-thread CTAs, two per SM (the pivot loop of one overlaps the
+    // cold refresh of the other), with half the shared memory for the hot set
+    if (rp <= 4 && hc2_threads(128) == 256) {
+        if (rp <= 2) launch_one_hc2<G, 256, HC2_NB, 2, 2>(t, nt, s, csize, tol, th2, smem, st);
+        else launch_one_hc2<G, 256, HC2_NB, 4, 2>(t, nt, s, csize, tol, th2, smem, st);
+        return;
+    }
     if (rp <= 2) launch_one_hc2<G, 512, HC2_NB, 2, 1>(t, nt, s, csize, tol, th2, smem, st);
     else if (rp <= 4) launch_one_hc2<G, 512, HC2_NB, 4, 1>(t, nt, s, csize, tol, th2, smem, st);
     else if (rp <= 6) launch_one_hc2<G, 512, HC2_NB, 6, 1>(t, nt, s, csize, tol, th2, smem, st);
@@ -1366,7 +1373,10 @@ int hc2_row_pairs(int rows) {
     return 0;  // too tall for the register-resident reflector: use the other kernels
 }
 
-int hc2_threads(int rows) { (void)rows; return 512; }
+int hc2_threads(int rows) {
+    static const int nt_small = getenv("SPAND_HC2_NT") ? atoi(getenv("SPAND_HC2_NT")) : 512;
+    return (nt_small == 256 && hc2_row_pairs(rows) <= 4 && hc2_row_pairs(rows) > 0) ? 256 : 512;
+}
 
 size_t hc2_smem_bytes(int rows, int maxcols, int G, int hcap, int nsrc) {
     const size_t ldv = ((size_t)rows + 1) & ~(size_t)1;

@@ -1444,7 +1444,7 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             const bool hc2_fits = force_hc2 || (per_color_own[task_color[i]] >= hc2_tmin && t.rows <= hc2_maxrows);
             if (hc2_on && hc2_fits && !smem_mode && !force_global && force_g == 0 && rp > 0 &&
                 8.0 * t.rows * t.maxcols >= hc2_min_bytes) {
-                const bool big = true;  // 512 threads, one CTA per SM
+                const bool big = hc2_threads(t.rows) == 512;  // 512 threads, one CTA per SM; else 256 threads, two per SM
                 const long budget = big ? hc2_budget_big : hc2_budget;
                 const long ldv = (t.rows + 1) & ~1;
                 auto hcap_for = [&](int G) {  // largest hot set that fits the budget with this cluster width
