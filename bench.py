@@ -491,6 +491,14 @@ def main():
     pk = peaks()
     hbm_peak = pk.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in pk else "fallback (B200_PROFILING.md)"
+    fp64_peak_1gpu = fp64_peak
+    if world > 1:
+        # sharded: the bytes / flops below are those of the whole matrix and the family times the slowest rank's, so
+        # `achieved` is an aggregate over the ranks: it is compared with the aggregate peak of the N GPUs
+        hbm_peak *= world
+        hbm_src += " x %d GPUs (aggregate)" % world
+        if fp64_peak:
+            fp64_peak *= world
     # Dominant kernel family and its roofline. Algorithmic bytes / flops are SURVEY.md 8(d)'s per-unit figures summed
     # over the factorization; the duration is the family's kernel time from CUDA events around each of its launches.
     fam_s = {k: v[0] * 1e-3 for k, v in fam.items()}
@@ -504,6 +512,7 @@ def main():
         roof = {"bound": "tensor", "kernel": kern[dom], "achieved": fl / fam_s[dom] / 1e12, "peak": fp64_peak or 40.0,
                 "unit": "TFLOP/s",
                 "peak_source": ("cuBLAS DGEMM 8192^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)"
+                                + (" x %d GPUs (aggregate)" % world if world > 1 else "")
                                 if fp64_peak else "nominal 40 TFLOP/s (vendor)")}
     else:
         roof = {"bound": "hbm", "kernel": kern[dom], "achieved": float(by[dom]) / fam_s[dom] / 1e9, "peak": hbm_peak,
@@ -577,7 +586,7 @@ def main():
                    "symbolic": "block structure of all levels analysed once per pattern in the first assemble() "
                                "(untimed: %.2f s) and reused by every later assemble()/factorize()" % t.analyze_seconds()},
         "factorize_time_s": tdev / args.steps, "fp64_tflops": flops / (tdev / args.steps) / 1e12,
-        "gflop_per_factorization": flops / 1e9, "fp64_dgemm_peak_tflops": fp64_peak,
+        "gflop_per_factorization": flops / 1e9, "fp64_dgemm_peak_tflops": fp64_peak_1gpu,
         "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "seconds_per_step": te2e / args.steps, "assemble_s": float(np.mean(tassm)),
                 "solve_s": float(np.mean(tsolve))},

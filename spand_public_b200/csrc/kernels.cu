@@ -4,6 +4,7 @@
 #include <cfloat>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -484,21 +485,39 @@ __device__ __forceinline__ void gemm_tile64(double* C, int ldc, int m, int n, in
 
 __global__ void __launch_bounds__(256) gemm_tiled_kernel(const GemmTask* __restrict__ tasks, int nt,
                                                          const GemmContrib* __restrict__ contribs,
-                                                         const int* __restrict__ tile_prefix) {
+                                                         const int* __restrict__ tile_prefix,
+                                                         const int* __restrict__ tile_task) {
     int b = blockIdx.x;
     int lo = 0, hi = nt - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (tile_prefix[mid] <= b) lo = mid;
-        else hi = mid - 1;
-    }
+    if (tile_task != nullptr) lo = tile_task[b];
+    else
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (tile_prefix[mid] <= b) lo = mid;
+            else hi = mid - 1;
+        }
     GemmTask t = tasks[lo];
     int local = b - tile_prefix[lo];
     int tm = (t.m + GT - 1) / GT;
     int tile_r = local % tm, tile_c = local / tm;
     if ((t.flags & GEMM_LOWER) && tile_c > tile_r) return;
     const GemmContrib* cc = contribs + t.c0;
-    gemm_tile64(t.C, t.ldc, t.m, t.n, t.flags, tile_r * GT, tile_c * GT, t.nc, [cc](int ci) { return cc[ci]; });
+    // triangular operand: the inner index of this tile stops where the triangle ends
+    const int klim = (t.flags & GEMM_TRIB) ? (tile_c + 1) * GT : ((t.flags & GEMM_TRIA) ? (tile_r + 1) * GT : INT_MAX);
+    gemm_tile64(t.C, t.ldc, t.m, t.n, t.flags, tile_r * GT, tile_c * GT, t.nc, [cc, klim](int ci) {
+        GemmContrib c = cc[ci];
+        c.k = min(c.k, klim);
+        return c;
+    });
+}
+
+__global__ void __launch_bounds__(256) eye_kernel(const EyeTask* __restrict__ tasks) {
+    const EyeTask t = tasks[blockIdx.x];
+    const size_t total = (size_t)t.n * t.n;
+    for (size_t x = (size_t)blockIdx.y * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.y * blockDim.x) {
+        const int i = (int)(x % t.n), j = (int)(x / t.n);
+        t.W[i + (size_t)j * t.ld] = (i == j) ? 1.0 : 0.0;
+    }
 }
 
 
@@ -515,7 +534,8 @@ __global__ void __launch_bounds__(NB) trtri_kernel(const TrtriTask* __restrict__
     for (int p = 0; p < nb; p++)
         if (c >= p && c < nb) S[p * LDS + c] = T[c + (size_t)p * t.ldt];
     __syncthreads();
-    double* out = t.inv + (size_t)blockIdx.y * NB * NB + (size_t)c * NB;
+    const bool compact = t.ldw > 0;  // one n x n block (n <= 64) with leading dimension ldw
+    double* out = compact ? t.inv + (size_t)c * t.ldw : t.inv + (size_t)blockIdx.y * NB * NB + (size_t)c * NB;
     double x[NB];
 #pragma unroll
     for (int i = 0; i < NB; i++) x[i] = 0.0;
@@ -530,6 +550,14 @@ __global__ void __launch_bounds__(NB) trtri_kernel(const TrtriTask* __restrict__
                 x[i] = v / S[i * LDS + i];
             }
         }
+    }
+    if (compact) {
+        if (c < nb) {
+#pragma unroll
+            for (int i = 0; i < NB; i++)
+                if (i < nb) out[i] = x[i];
+        }
+        return;
     }
 #pragma unroll
     for (int i = 0; i < NB; i++) out[i] = x[i];
@@ -549,7 +577,10 @@ __global__ void __launch_bounds__(256) trsm_strip_kernel(const TrsmTask* __restr
     const int f0 = (b - strip_prefix[lo]) * NB;
     const int fw = min(NB, t.m - f0);
     const int nblk = (t.n + NB - 1) / NB;
-    for (int j = 0; j < nblk; j++) {
+    // block lower triangular B (LLN): rows above the strip's own block are zero and stay zero
+    const int jfirst = (MODE == TRSM_LLN && t.tri) ? f0 / NB : 0;
+    const int r0 = jfirst * NB;
+    for (int j = jfirst; j < nblk; j++) {
         const int j0 = j * NB, nb = min(NB, t.n - j0);
         GemmContrib c;
         const double* inv = t.inv + (size_t)j * NB * NB;
@@ -567,8 +598,8 @@ __global__ void __launch_bounds__(256) trsm_strip_kernel(const TrsmTask* __restr
             // X_j = inv(L_jj) (B_j - L_{j,0:j} X_{0:j}) on the column strip [f0, f0 + fw)
             double* Bs = t.B + (size_t)f0 * t.ldb;
             double* C = Bs + j0;
-            if (j > 0) {
-                c = GemmContrib{t.T + j0, Bs, t.ldt, t.ldb, j0};
+            if (j > jfirst) {
+                c = GemmContrib{t.T + j0 + (size_t)r0 * t.ldt, Bs + r0, t.ldt, t.ldb, j0 - r0};
                 gemm_tile64<1>(C, t.ldb, nb, fw, GEMM_NN, 0, 0, 1, [c](int) { return c; });
             }
             c = GemmContrib{inv, C, NB, t.ldb, nb};
@@ -1202,9 +1233,102 @@ __global__ void __launch_bounds__(NB) trsm_mid_kernel(DevTables T, const SymTrsm
     }
 }
 
+// Right-looking substitution on a tile Bs (64 x 64, Bs[col * LDS + row]) by the 8 warps of a 256-thread CTA against the
+// lower triangle Ls[p * LDS + q] = L(q, p) (zero-filled outside the triangle and beyond nt). A "unit" is a row of the
+// tile for B <- B L^-T (ROWS) or a column for B <- L^-1 B: units are independent, unit u = 8 * warp + (lane >> 2)
+// lives on four lanes of one warp, lane c of the four holds the entries q = 4k + c in registers. Step p: the holder of
+// entry p divides by L(p, p) and shuffles x_p to its three neighbours, everybody subtracts x_p L(q, p) from its
+// entries q > p. Every entry sees v <- fma(-x_p, L(q, p), v) for p = 0..q-1 in this order and one division: the
+// arithmetic (and its rounding) of the row-by-row substitution it replaces (trsm_tile64), with 16 independent updates
+// per thread and step instead of one dependent chain per thread.
+template <bool ROWS, int NTM>  // NTM: compile-time bound of the triangle dimension (multiple of 4)
+__device__ __forceinline__ void tile_solve_rl_n(double* Bs, const double* Ls, int nt, int nu) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (8 * warp >= nu) return;  // no unit on this warp
+    const int u = 8 * warp + (lane >> 2), c = lane & 3;
+    constexpr int NK = NTM / 4;
+    double v[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        const int q = 4 * k + c;
+        v[k] = (q < nt && u < nu) ? (ROWS ? Bs[q * LDS + u] : Bs[u * LDS + q]) : 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < NTM; p++) {
+        if (p < nt) {  // uniform
+            double x = v[p >> 2] / Ls[p * LDS + p];
+            x = __shfl_sync(FULLM, x, (lane & ~3) | (p & 3));
+            if (c == (p & 3)) v[p >> 2] = x;
+            const double* lp = Ls + p * LDS + c;
+#pragma unroll
+            for (int k = p >> 2; k < NK; k++)
+                if (4 * k + c > p) v[k] = fma(-x, lp[4 * k], v[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        const int q = 4 * k + c;
+        if (q < nt && u < nu) {
+            if (ROWS) Bs[q * LDS + u] = v[k];
+            else Bs[u * LDS + q] = v[k];
+        }
+    }
+}
+template <bool ROWS>
+__device__ __forceinline__ void tile_solve_rl(double* Bs, const double* Ls, int nt, int nu) {
+    if (nt <= 16) tile_solve_rl_n<ROWS, 16>(Bs, Ls, nt, nu);
+    else if (nt <= 32) tile_solve_rl_n<ROWS, 32>(Bs, Ls, nt, nu);
+    else if (nt <= 48) tile_solve_rl_n<ROWS, 48>(Bs, Ls, nt, nu);
+    else tile_solve_rl_n<ROWS, 64>(Bs, Ls, nt, nu);
+}
+
+// B tile (rows x cols) and lower triangle (n x n) into shared memory, zero-filled up to 64 x 64
+__device__ __forceinline__ void tile_load_b(double* Bs, const double* B, int ldb, int rows, int cols) {
+    for (int x = threadIdx.x; x < NB * NB; x += blockDim.x) {
+        const int i = x & (NB - 1), j = x >> 6;
+        Bs[j * LDS + i] = (i < rows && j < cols) ? B[i + (size_t)j * ldb] : 0.0;
+    }
+}
+__device__ __forceinline__ void tile_load_l(double* Ls, const double* L, int ldl, int n) {
+    for (int x = threadIdx.x; x < NB * NB; x += blockDim.x) {
+        const int i = x & (NB - 1), j = x >> 6;
+        Ls[j * LDS + i] = (i < n && j <= i) ? L[i + (size_t)j * ldl] : 0.0;
+    }
+}
+__device__ __forceinline__ void tile_store_b(const double* Bs, double* B, int ldb, int rows, int cols) {
+    for (int x = threadIdx.x; x < NB * NB; x += blockDim.x) {
+        const int i = x & (NB - 1), j = x >> 6;
+        if (i < rows && j < cols) B[i + (size_t)j * ldb] = Bs[j * LDS + i];
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) trsm_mid256_kernel(DevTables T, const SymTrsm* __restrict__ tasks,
+                                                       const int* __restrict__ mid, const int* __restrict__ cnt) {
+    extern __shared__ double trsm_smem[];
+    double* Bs = trsm_smem;
+    double* Ls = trsm_smem + NB * LDS;
+    const int nmid = *cnt;
+    for (int q = blockIdx.x; q < nmid; q += gridDim.x) {
+        const SymTrsm t = tasks[mid[q]];
+        const int m = T.csize[t.cm], n = T.csize[t.cn];  // free dimension, triangle
+        double* B = T.eptr[t.eB];
+        const int ldb = T.eld[t.eB];
+        const int rows = MODE == TRSM_RLT ? m : n, cols = MODE == TRSM_RLT ? n : m;
+        tile_load_b(Bs, B, ldb, rows, cols);
+        tile_load_l(Ls, T.eptr[t.eT], T.eld[t.eT], n);
+        __syncthreads();
+        tile_solve_rl<MODE == TRSM_RLT>(Bs, Ls, n, m);
+        __syncthreads();
+        tile_store_b(Bs, B, ldb, rows, cols);
+        __syncthreads();
+    }
+}
+
 // Two-sided scaling of one off-diagonal block: B (|c2| x |c1|) <- L_c2^-1 (B L_c1^-T)   (src/tree.cpp:796-856)
 __global__ void __launch_bounds__(128) scale_sym_kernel(DevTables T, const SymTrsm* __restrict__ right,
-                                                        const SymTrsm* __restrict__ left, int nt, int* mid, int* cnt) {
+                                                        const SymTrsm* __restrict__ left, int nt, int* mid, int* cnt,
+                                                        int warp_only) {
     __shared__ double Sw[4][32 * WLD];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * 4 + w;
@@ -1214,7 +1338,7 @@ __global__ void __launch_bounds__(128) scale_sym_kernel(DevTables T, const SymTr
     const int rows = T.csize[r.cm], cols = T.csize[r.cn];
     if (rows <= 0 || cols <= 0 || rows > SMALL_DIM || cols > SMALL_DIM) return;
     if (rows > 32 || cols > 32) {
-        if (lane == 0) push_mid(mid, cnt, ti);
+        if (lane == 0 && !warp_only) push_mid(mid, cnt, ti);
         return;
     }
     const int eL = left[ti].eT;
@@ -1243,6 +1367,33 @@ __global__ void __launch_bounds__(NB) scale_mid_kernel(DevTables T, const SymTrs
         const int ldb = T.eld[r.eB];
         trsm_tile64<TRSM_RLT>(T.eptr[r.eT], T.eld[r.eT], nullptr, B, ldb, rows, cols, trsm_smem);
         trsm_tile64<TRSM_LLN>(T.eptr[eL], T.eld[eL], nullptr, B, ldb, cols, rows, trsm_smem);
+    }
+}
+
+__global__ void __launch_bounds__(256, 3) scale_mid256_kernel(DevTables T, const SymTrsm* __restrict__ right,
+                                                        const SymTrsm* __restrict__ left, const int* __restrict__ mid,
+                                                        const int* __restrict__ cnt) {
+    extern __shared__ double trsm_smem[];
+    double* Bs = trsm_smem;
+    double* Ls = trsm_smem + NB * LDS;
+    const int nmid = *cnt;
+    for (int q = blockIdx.x; q < nmid; q += gridDim.x) {
+        const SymTrsm r = right[mid[q]];
+        const int eL = left[mid[q]].eT;
+        const int rows = T.csize[r.cm], cols = T.csize[r.cn];
+        double* B = T.eptr[r.eB];
+        const int ldb = T.eld[r.eB];
+        tile_load_b(Bs, B, ldb, rows, cols);
+        tile_load_l(Ls, T.eptr[r.eT], T.eld[r.eT], cols);
+        __syncthreads();
+        tile_solve_rl<true>(Bs, Ls, cols, rows);  // B <- B L_c1^-T
+        __syncthreads();
+        tile_load_l(Ls, T.eptr[eL], T.eld[eL], rows);
+        __syncthreads();
+        tile_solve_rl<false>(Bs, Ls, rows, cols);  // B <- L_c2^-1 B
+        __syncthreads();
+        tile_store_b(Bs, B, ldb, rows, cols);
+        __syncthreads();
     }
 }
 
@@ -1497,6 +1648,9 @@ void launch_trtri(const TrtriTask* t, int nt, int max_n, cudaStream_t st) {
     dim3 grid(nt, (max_n + NB - 1) / NB);
     trtri_kernel<<<grid, NB, 0, st>>>(t);
 }
+void launch_eye(const EyeTask* t, int nt, cudaStream_t st) {
+    if (nt > 0) eye_kernel<<<dim3(nt, 8), 256, 0, st>>>(t);
+}
 void launch_trsm_strip(int mode, const TrsmTask* t, int nt, const int* strip_prefix, int total_strips, cudaStream_t st) {
     if (nt <= 0 || total_strips <= 0) return;
     if (mode == TRSM_RLT) trsm_strip_kernel<TRSM_RLT><<<total_strips, 256, 0, st>>>(t, nt, strip_prefix);
@@ -1535,8 +1689,8 @@ void launch_rowperm(const RowPermTask* t, int nt, cudaStream_t st) {
 }
 
 void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const int* tile_prefix, int total_tiles,
-                       cudaStream_t st) {
-    if (nt > 0 && total_tiles > 0) gemm_tiled_kernel<<<total_tiles, 256, 0, st>>>(t, nt, c, tile_prefix);
+                       cudaStream_t st, const int* tile_task) {
+    if (nt > 0 && total_tiles > 0) gemm_tiled_kernel<<<total_tiles, 256, 0, st>>>(t, nt, c, tile_prefix, tile_task);
 }
 
 void launch_gemm_small(const GemmTask* t, int nt, const GemmContrib* c, cudaStream_t st) {
@@ -1597,12 +1751,24 @@ void launch_scatter(int n, const int* idx, const double* src, double* dst, cudaS
 namespace {
 constexpr int kMidGrid = 148 * 8;
 constexpr int kTrsmSmem = 2 * NB * LDS * sizeof(double);
+// SPAND_MID256 (default 1): right-looking 256-thread kernels for the 33..64 class; 0: one thread per row / column
+bool mid256() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("SPAND_MID256");
+        v = e ? std::atoi(e) : 1;
+    }
+    return v != 0;
+}
 void configure_mid_smem() {
     static bool configured = false;
     if (configured) return;
     cudaFuncSetAttribute(trsm_mid_kernel<TRSM_RLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
     cudaFuncSetAttribute(trsm_mid_kernel<TRSM_LLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
     cudaFuncSetAttribute(scale_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(trsm_mid256_kernel<TRSM_RLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(trsm_mid256_kernel<TRSM_LLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(scale_mid256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
     configured = true;
 }
 }  // namespace
@@ -1618,18 +1784,22 @@ void launch_trsm_sym(int mode, const DevTables& T, const SymTrsm* tasks, int nt,
     configure_mid_smem();
     if (mode == TRSM_RLT) {
         trsm_sym_kernel<TRSM_RLT><<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, mid, cnt);
-        trsm_mid_kernel<TRSM_RLT><<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+        if (mid256()) trsm_mid256_kernel<TRSM_RLT><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+        else trsm_mid_kernel<TRSM_RLT><<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, tasks, mid, cnt);
     } else {
         trsm_sym_kernel<TRSM_LLN><<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, mid, cnt);
-        trsm_mid_kernel<TRSM_LLN><<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+        if (mid256()) trsm_mid256_kernel<TRSM_LLN><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+        else trsm_mid_kernel<TRSM_LLN><<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, tasks, mid, cnt);
     }
 }
 void launch_scale_sym(const DevTables& T, const SymTrsm* right, const SymTrsm* left, int nt, int* mid, int* cnt,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool warp_only) {
     if (nt <= 0) return;
     configure_mid_smem();
-    scale_sym_kernel<<<(nt + 3) / 4, 128, 0, st>>>(T, right, left, nt, mid, cnt);
-    scale_mid_kernel<<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, right, left, mid, cnt);
+    scale_sym_kernel<<<(nt + 3) / 4, 128, 0, st>>>(T, right, left, nt, mid, cnt, warp_only ? 1 : 0);
+    if (warp_only) return;
+    if (mid256()) scale_mid256_kernel<<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, right, left, mid, cnt);
+    else scale_mid_kernel<<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, right, left, mid, cnt);
 }
 void launch_gemm_sym(const DevTables& T, const SymGemm* tasks, int nt, const SymCon* con, int* mid, int* cnt,
                      cudaStream_t st) {

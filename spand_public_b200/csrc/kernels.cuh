@@ -42,12 +42,20 @@ struct TrsmTask {
     int n;  // triangle dimension
     const double* diag;  // nullptr: diagonal of T; else the n diagonal entries (PLU keeps diag(U) beside the block)
     const double* inv;   // strip kernels only: inverses of the 64 x 64 diagonal blocks of T, 4096 doubles each
+    int tri;             // strip kernel, TRSM_LLN only: B is block lower triangular (rows above the strip's first column
+                         // block are zero and stay zero), e.g. B = I when the whole inverse of T is wanted
 };
 
 struct TrtriTask {  // inverses of the diagonal blocks of one triangle
     const double* T;
     int ldt, n;
     double* inv;
+    int ldw;  // 0: 64 x 64 blocks of 4096 doubles each; > 0 (n <= 64 only): one n x n block with this leading dimension
+};
+
+struct EyeTask {  // W (n x n, leading dimension ld) <- I
+    double* W;
+    int n, ld;
 };
 
 // PLU pivot (src/util.cpp:183-227): on exit A holds L (lower, with its non-unit diagonal |d|^1/2) and the strictly
@@ -72,7 +80,9 @@ struct GemmContrib {
     int lda, ldb, k;
 };
 
-enum GemmFlags { GEMM_LOWER = 1, GEMM_ZERO_INIT = 2, GEMM_NN = 4, GEMM_POS = 8 };  // POS: C = (0|C) + sum
+// POS: C = (0|C) + sum. TRIB (NT form): B_c is lower triangular (n x n), the inner index of a tile stops at its last
+// column; TRIA (NN form): A_c is lower triangular (m x m), the inner index of a tile stops at its last row.
+enum GemmFlags { GEMM_LOWER = 1, GEMM_ZERO_INIT = 2, GEMM_NN = 4, GEMM_POS = 8, GEMM_TRIB = 16, GEMM_TRIA = 32 };
 
 struct GemmTask {
     double* C;  // m x n, C = (ZERO_INIT ? 0 : C) - sum_c A_c op(B_c)
@@ -156,6 +166,7 @@ void launch_trsm_step(int mode, const TrsmTask* t, int nt, int j0, int max_m, cu
 // the 64-wide blocks of the triangle, X_j = (B_j - sum_{p<j} X_p T_jp^T) inv(T_jj)^T. strip_prefix: nt + 1 exclusive
 // prefix of ceil(m / 64).
 void launch_trtri(const TrtriTask* t, int nt, int max_n, cudaStream_t st);
+void launch_eye(const EyeTask* t, int nt, cudaStream_t st);
 void launch_trsm_strip(int mode, const TrsmTask* t, int nt, const int* strip_prefix, int total_strips, cudaStream_t st);
 // GETRF with partial pivoting. n <= 64: one launch does everything (factor, split_LU, perm). Larger: right-looking
 // over 64-wide panels: launch_getrf_panel (pivoting inside the panel) -> launch_getrf_laswp (row swaps outside the
@@ -166,9 +177,10 @@ void launch_getrf_panel(const GetrfTask* t, int nt, int j0, int* err, cudaStream
 void launch_getrf_laswp(const GetrfTask* t, int nt, int j0, int max_n, cudaStream_t st);
 void launch_getrf_finish(const GetrfTask* t, int nt, cudaStream_t st);
 void launch_rowperm(const RowPermTask* t, int nt, cudaStream_t st);
-// tile_prefix: nt + 1 exclusive prefix of ceil(m/64)*ceil(n/64); total_tiles = tile_prefix[nt]
+// tile_prefix: nt + 1 exclusive prefix of ceil(m/64)*ceil(n/64); total_tiles = tile_prefix[nt]; tile_task (optional):
+// task of every tile (replaces the binary search in tile_prefix when a launch has 10^5 tasks)
 void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const int* tile_prefix, int total_tiles,
-                       cudaStream_t st);
+                       cudaStream_t st, const int* tile_task = nullptr);
 void launch_gemm_small(const GemmTask* t, int nt, const GemmContrib* c, cudaStream_t st);
 // csize: device array of current cluster sizes (read for neighbours, written with the rank)
 // One thread-block cluster of G CTAs per task. Launch shapes: (128 threads, G = 1, panel in shared memory),
@@ -238,9 +250,10 @@ constexpr int COPY_SMALL = 4096;   // largest block (elements) copied by one war
 void launch_potrf_sym(const DevTables& T, const int* clusters, const int* piv, int nt, int* mid, int* cnt, int* err,
                       cudaStream_t st);
 void launch_trsm_sym(int mode, const DevTables& T, const SymTrsm* tasks, int nt, int* mid, int* cnt, cudaStream_t st);
-// two-sided scaling of a block: B <- L_row^-1 (B L_col^-T); right[i] / left[i] describe the same block
+// two-sided scaling of a block: B <- L_row^-1 (B L_col^-T); right[i] / left[i] describe the same block.
+// warp_only: blocks with a dimension above 32 are left to the caller (explicit-inverse GEMM path of the host driver)
 void launch_scale_sym(const DevTables& T, const SymTrsm* right, const SymTrsm* left, int nt, int* mid, int* cnt,
-                      cudaStream_t st);
+                      cudaStream_t st, bool warp_only = false);
 void launch_gemm_sym(const DevTables& T, const SymGemm* tasks, int nt, const SymCon* con, int* mid, int* cnt,
                      cudaStream_t st);
 void launch_copy_sym(const DevTables& T, const SymCopy* tasks, int nt, int pivots_identity, cudaStream_t st);

@@ -7,6 +7,7 @@
 #include <ctime>
 #include <stdexcept>
 
+#include "host/parallel.hpp"
 #include "kernels.cuh"
 
 namespace spand {
@@ -61,7 +62,9 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
     plan.nleaf_edges = (int)en1.size();
 
     std::vector<int> task_of_edge;
-    std::vector<int> slot(ncl, -1), tlist, color;
+    std::vector<int> color;
+    std::vector<std::vector<int>> slots(kMaxHostThreads);  // per host thread: parent -> new edge index during a merge
+    std::vector<char> edge_dead;
     double tsec[6] = {0, 0, 0, 0, 0, 0};
     auto nowf = [] {
         struct timespec ts;
@@ -188,39 +191,41 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
             }
         }
         lap(2);
-        // set_eliminated (cluster.cpp:32-45)
+        // set_eliminated (cluster.cpp:32-45): the edges of the eliminated clusters leave the lists of their other end
+        // (every touched cluster edits its own lists: host threads)
         {
-            std::vector<char> dead_mark;
             std::vector<int> touched;
-            std::vector<int> dead;
+            if (edge_dead.size() < en1.size()) edge_dead.resize(en1.size(), 0);
             for (int s : L.E) {
                 for (int e : out[s]) {
-                    dead.push_back(e);
+                    edge_dead[e] = 1;
                     if (en2[e] != s) touched.push_back(en2[e]);
                 }
                 for (int e : in[s]) {
-                    dead.push_back(e);
+                    edge_dead[e] = 1;
                     touched.push_back(en1[e]);
                 }
                 eliminated[s] = 1;
             }
-            std::sort(dead.begin(), dead.end());
-            auto is_dead = [&](int e) { return std::binary_search(dead.begin(), dead.end(), e); };
+            auto is_dead = [&](int e) { return edge_dead[e] != 0; };
             for (int s : L.E) {
                 out[s].clear();
                 in[s].clear();
             }
             std::sort(touched.begin(), touched.end());
             touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
-            for (int n : touched) {
-                if (eliminated[n]) continue;
-                auto& i_ = in[n];
-                i_.erase(std::remove_if(i_.begin(), i_.end(), is_dead), i_.end());
-                if (!symmetric) {
-                    auto& o = out[n];
-                    o.erase(std::remove_if(o.begin(), o.end(), is_dead), o.end());
+            parallel_chunks(touched.size(), [&](int, size_t b0, size_t e0) {
+                for (size_t x = b0; x < e0; x++) {
+                    const int n = touched[x];
+                    if (eliminated[n]) continue;
+                    auto& i_ = in[n];
+                    i_.erase(std::remove_if(i_.begin(), i_.end(), is_dead), i_.end());
+                    if (!symmetric) {
+                        auto& o = out[n];
+                        o.erase(std::remove_if(o.begin(), o.end(), is_dead), o.end());
+                    }
                 }
-            }
+            }, 4096);
         }
         lap(3);
         // ---------------- scale ----------------
@@ -229,20 +234,32 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
             L.S.push_back(c);
             L.s_piv.push_back(out[c][0]);
         }
-        for (int c : L.S) {
-            const int piv = out[c][0];
-            for (size_t k = 1; k < out[c].size(); k++) {
-                int e = out[c][k];
-                int c2 = en2[e];
-                L.s_right.push_back({e, piv, c2, c});
-                L.s_left.push_back({e, out[c2][0], c, c2});
-            }
+        {
+            std::vector<size_t> off(L.S.size() + 1, 0);
+            for (size_t i = 0; i < L.S.size(); i++) off[i + 1] = off[i] + out[L.S[i]].size() - 1;
+            L.s_right.resize(off.back());
+            L.s_left.resize(off.back());
+            parallel_chunks(L.S.size(), [&](int, size_t b0, size_t e0) {
+                for (size_t i = b0; i < e0; i++) {
+                    const int c = L.S[i];
+                    const int piv = out[c][0];
+                    size_t w = off[i];
+                    for (size_t k = 1; k < out[c].size(); k++, w++) {
+                        const int e = out[c][k];
+                        const int c2 = en2[e];
+                        L.s_right[w] = {e, piv, c2, c};
+                        L.s_left[w] = {e, out[c2][0], c, c2};
+                    }
+                }
+            }, 4096);
         }
         // ---------------- sparsify: wavefronts of the Gauss-Seidel order (tree.cpp:1523-1527, :1194-1200) ----------------
         {
             int first = bottom.empty() ? 0 : bottom.front();
             int span = bottom.empty() ? 0 : bottom.back() - first + 1;
             color.assign(span, -1);
+            // tasks and their source ranges in list order, sources filled by host threads
+            size_t nsrc_total = 0;
             for (int s : L.S) {
                 bool want = want_flag ? cl[s].sparsify : true;
                 if (!want) {
@@ -251,20 +268,31 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
                 }
                 SymQr t;
                 t.cluster = s;
-                t.src0 = (int)L.qs.size();
-                int col = 0;
-                auto visit = [&](int nbr, int e, int transposed) {
-                    int cn = color[nbr - first];
-                    if (cn >= 0) col = std::max(col, cn + 1);  // earlier in list order and sparsified
-                    L.qs.push_back({e, nbr, transposed});
-                };
-                for (int e : in[s]) visit(en1[e], e, 0);
-                for (size_t k = 1; k < out[s].size(); k++) visit(en2[out[s][k]], out[s][k], 1);
-                t.nsrc = (int)L.qs.size() - t.src0;
-                t.color = col;
-                color[s - first] = col;
-                L.ncolors = std::max(L.ncolors, col + 1);
+                t.src0 = (int)nsrc_total;
+                t.nsrc = (int)(in[s].size() + out[s].size() - 1);
+                t.color = 0;
+                nsrc_total += t.nsrc;
                 L.q.push_back(t);
+            }
+            L.qs.resize(nsrc_total);
+            parallel_chunks(L.q.size(), [&](int, size_t b0, size_t e0) {
+                for (size_t i = b0; i < e0; i++) {
+                    const int s = L.q[i].cluster;
+                    size_t w = L.q[i].src0;
+                    for (int e : in[s]) L.qs[w++] = {e, en1[e], 0};
+                    for (size_t k = 1; k < out[s].size(); k++) L.qs[w++] = {out[s][k], en2[out[s][k]], 1};
+                }
+            }, 4096);
+            // colours: a task comes after the neighbours sparsified earlier in list order
+            for (SymQr& t : L.q) {
+                int col = 0;
+                for (int k = t.src0; k < t.src0 + t.nsrc; k++) {
+                    const int cn = color[L.qs[k].nbr - first];
+                    if (cn >= 0) col = std::max(col, cn + 1);
+                }
+                t.color = col;
+                color[t.cluster - first] = col;
+                L.ncolors = std::max(L.ncolors, col + 1);
             }
         }
         lap(4);
@@ -273,48 +301,78 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
         if (l < nlevels - 1) {
             const std::vector<int>& parents = bottoms[l + 1];
             struct NewEdge { int n1, n2; };
-            std::vector<NewEdge> ne;
             struct Pending { int edge_old, newidx; };
-            std::vector<Pending> pend;
-            for (int p : parents) {
-                tlist.clear();
-                for (int c = cl[p].child_begin; c < cl[p].child_end; c++)
-                    for (int e : out[c]) {
-                        int q = cl[en2[e]].parent;
-                        if (slot[q] == -1) {
-                            slot[q] = -2;
-                            tlist.push_back(q);
+            // the parents are independent (their new edges are numbered parent by parent): chunks of parents on host
+            // threads with private slot tables, stitched together in parent order
+            struct Part {
+                std::vector<NewEdge> ne;
+                std::vector<Pending> pend;  // newidx local to the chunk
+            };
+            std::vector<Part> parts(kMaxHostThreads);
+            const int nth = parallel_chunks(parents.size(), [&](int t, size_t b0, size_t e0) {
+                Part& P = parts[t];
+                if (slots[t].empty()) slots[t].assign(ncl, -1);
+                std::vector<int>& slot = slots[t];
+                std::vector<int> tlist;
+                for (size_t x = b0; x < e0; x++) {
+                    const int p = parents[x];
+                    tlist.clear();
+                    for (int c = cl[p].child_begin; c < cl[p].child_end; c++)
+                        for (int e : out[c]) {
+                            int q = cl[en2[e]].parent;
+                            if (slot[q] == -1) {
+                                slot[q] = -2;
+                                tlist.push_back(q);
+                            }
                         }
-                    }
-                std::sort(tlist.begin(), tlist.end());
-                slot[p] = (int)ne.size();
-                ne.push_back({p, p});  // pivot first, then by increasing order
-                for (int q : tlist)
-                    if (q != p) {
-                        slot[q] = (int)ne.size();
-                        ne.push_back({p, q});
-                    }
-                for (int c = cl[p].child_begin; c < cl[p].child_end; c++)
-                    for (int e : out[c]) pend.push_back({e, slot[cl[en2[e]].parent]});
-                for (int q : tlist) slot[q] = -1;
-                slot[p] = -1;
-            }
-            for (auto& n : ne) {
-                int e = new_edge(n.n1, n.n2);
-                if (n.n1 == n.n2) out[n.n1].insert(out[n.n1].begin(), e);
-                else {
-                    out[n.n1].push_back(e);
-                    in[n.n2].push_back(e);
+                    std::sort(tlist.begin(), tlist.end());
+                    slot[p] = (int)P.ne.size();
+                    P.ne.push_back({p, p});  // pivot first, then by increasing order
+                    for (int q : tlist)
+                        if (q != p) {
+                            slot[q] = (int)P.ne.size();
+                            P.ne.push_back({p, q});
+                        }
+                    for (int c = cl[p].child_begin; c < cl[p].child_end; c++)
+                        for (int e : out[c]) P.pend.push_back({e, slot[cl[en2[e]].parent]});
+                    for (int q : tlist) slot[q] = -1;
+                    slot[p] = -1;
                 }
+            }, 2048);
+            size_t npend = 0;
+            std::vector<size_t> pend_off(nth + 1, 0), ne_off(nth + 1, 0);
+            for (int t = 0; t < nth; t++) {
+                ne_off[t + 1] = ne_off[t] + parts[t].ne.size();
+                pend_off[t + 1] = pend_off[t] + parts[t].pend.size();
             }
+            npend = pend_off[nth];
+            for (int t = 0; t < nth; t++)
+                for (auto& n : parts[t].ne) {
+                    int e = new_edge(n.n1, n.n2);
+                    if (n.n1 == n.n2) out[n.n1].insert(out[n.n1].begin(), e);
+                    else {
+                        out[n.n1].push_back(e);
+                        in[n.n2].push_back(e);
+                    }
+                }
             L.medge1 = (int)en1.size();
-            L.m_copy.reserve(pend.size());
-            for (auto& pc : pend) L.m_copy.push_back({pc.edge_old, L.medge0 + pc.newidx, en1[pc.edge_old], en2[pc.edge_old]});
-            for (int p : parents)
-                for (int c = cl[p].child_begin; c < cl[p].child_end; c++) {
-                    out[c].clear();
-                    in[c].clear();
+            L.m_copy.resize(npend);
+            parallel_chunks((size_t)nth, [&](int, size_t b0, size_t e0) {
+                for (size_t t = b0; t < e0; t++) {
+                    size_t w = pend_off[t];
+                    for (auto& pc : parts[t].pend)
+                        L.m_copy[w++] = {pc.edge_old, L.medge0 + (int)ne_off[t] + pc.newidx, en1[pc.edge_old], en2[pc.edge_old]};
                 }
+            }, 2);
+            parallel_chunks(parents.size(), [&](int, size_t b0, size_t e0) {
+                for (size_t x = b0; x < e0; x++) {
+                    const int p = parents[x];
+                    for (int c = cl[p].child_begin; c < cl[p].child_end; c++) {
+                        out[c].clear();
+                        in[c].clear();
+                    }
+                }
+            }, 4096);
         }
         lap(5);
     }

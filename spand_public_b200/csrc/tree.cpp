@@ -1,4 +1,5 @@
 #include "tree.hpp"
+#include "host/parallel.hpp"
 
 #include <sys/time.h>
 
@@ -12,8 +13,11 @@
 #include <unordered_map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 namespace spand {
+
+
 
 namespace {
 double wtime() {
@@ -130,7 +134,7 @@ void Tree::ensure_device() {
     arena_ = new DeviceArena((size_t)1 << 30);
     scratch_ = new DeviceArena((size_t)256 << 20);
     sym_arena_ = new DeviceArena((size_t)256 << 20);
-    stager_.reserve((size_t)64 << 20);
+    stager_.reserve((size_t)256 << 20);
     CK(cudaMalloc((void**)&d_err_, sizeof(int)));
     CK(cudaMalloc((void**)&d_cnt_, sizeof(int) * 64));
     for (int i = 0; i < kSide; i++) {
@@ -263,67 +267,97 @@ void Tree::analyze_host(const SpMat& A, std::vector<unsigned>& valmap) {
     for (int i = 0; i < N; i++) pinv[ord.perm[i]] = i;
     for (int c : bottoms_[0])
         for (int k = cl_[c].start; k < cl_[c].start + cl_[c].size; k++) cmap[k] = c;
-    // pass 1: neighbours of every leaf column cluster, pivot first then increasing order (cluster.cpp:113-176)
+    // pass 1: neighbours of every leaf column cluster, pivot first then increasing order (cluster.cpp:113-176);
+    // the leaves are independent: chunks of them on host threads, stitched together in leaf order afterwards
     std::vector<int> leaf_n1, leaf_n2;
     std::vector<int> blk_begin(ncl + 1, 0);
     leaf_off_.clear();
     size_t total = 0;
     {
-        std::vector<int> mark(ncl, -1), nb;
-        for (int s : bottoms_[0]) {
-            nb.clear();
-            const Cluster& cs = cl_[s];
-            for (int pj = cs.start; pj < cs.start + cs.size; pj++) {
-                const int j = ord.perm[pj];
-                for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) {
-                    const int pi = pinv[A.rowind[k]];
-                    if (symm && pi < pj) continue;
-                    const int n = cmap[pi];
-                    if (mark[n] != s) {
-                        mark[n] = s;
-                        nb.push_back(n);
+        const std::vector<int>& leaves = bottoms_[0];
+        struct Part {
+            std::vector<int> n2;     // neighbour lists, pivot first
+            std::vector<int> count;  // per leaf
+        };
+        std::vector<Part> parts(8);
+        const int nth = parallel_chunks(leaves.size(), [&](int t, size_t b, size_t e) {
+            Part& P = parts[t];
+            std::vector<int> mark(ncl, -1), nb;
+            for (size_t x = b; x < e; x++) {
+                const int s = leaves[x];
+                nb.clear();
+                const Cluster& cs = cl_[s];
+                for (int pj = cs.start; pj < cs.start + cs.size; pj++) {
+                    const int j = ord.perm[pj];
+                    for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) {
+                        const int pi = pinv[A.rowind[k]];
+                        if (symm && pi < pj) continue;
+                        const int n = cmap[pi];
+                        if (mark[n] != s) {
+                            mark[n] = s;
+                            nb.push_back(n);
+                        }
                     }
                 }
-            }
-            if (mark[s] != s) {
                 mark[s] = s;
-                nb.push_back(s);
+                std::sort(nb.begin(), nb.end());
+                const size_t before = P.n2.size();
+                P.n2.push_back(s);
+                for (int n : nb)
+                    if (n != s) P.n2.push_back(n);
+                P.count.push_back((int)(P.n2.size() - before));
             }
-            std::sort(nb.begin(), nb.end());
-            blk_begin[s] = (int)leaf_n1.size();
-            leaf_n1.push_back(s);
-            leaf_n2.push_back(s);
-            leaf_off_.push_back(total);
-            total += (((size_t)cs.size * cs.size) + 31) & ~(size_t)31;
-            for (int n : nb)
-                if (n != s) {
+        }, 4096);
+        size_t nblocks = 0;
+        for (int t = 0; t < nth; t++) nblocks += parts[t].n2.size();
+        leaf_n1.reserve(nblocks);
+        leaf_n2.reserve(nblocks);
+        leaf_off_.reserve(nblocks);
+        size_t x = 0;
+        for (int t = 0; t < nth; t++) {
+            const Part& P = parts[t];
+            size_t q = 0;
+            for (size_t i = 0; i < P.count.size(); i++, x++) {
+                const int s = leaves[x];
+                const size_t ssz = cl_[s].size;
+                blk_begin[s] = (int)leaf_n1.size();
+                for (int c = 0; c < P.count[i]; c++, q++) {
+                    const int n = P.n2[q];
                     leaf_n1.push_back(s);
                     leaf_n2.push_back(n);
                     leaf_off_.push_back(total);
-                    total += (((size_t)cl_[n].size * cs.size) + 31) & ~(size_t)31;
+                    total += (((size_t)cl_[n].size * ssz) + 31) & ~(size_t)31;
                 }
-            blk_begin[s + 1] = (int)leaf_n1.size();
+                blk_begin[s + 1] = (int)leaf_n1.size();
+            }
         }
     }
     if (total >= 0xffffffffull) throw std::runtime_error("assemble: leaf blocks exceed the 32-bit value map");
     leaf_total_ = total;
     lap("leaf block structure");
-    // pass 2: value map
+    // pass 2: value map (independent per leaf: host threads)
     valmap.assign(A.nnz(), 0xffffffffu);
-    for (int s : bottoms_[0]) {
-        const Cluster& cs = cl_[s];
-        const int b0 = blk_begin[s], b1 = blk_begin[s + 1];
-        for (int pj = cs.start; pj < cs.start + cs.size; pj++) {
-            const int j = ord.perm[pj];
-            for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) {
-                const int pi = pinv[A.rowind[k]];
-                if (symm && pi < pj) continue;
-                const int n = cmap[pi];
-                int b = b0;
-                if (n != s) b = (int)(std::lower_bound(leaf_n2.begin() + b0 + 1, leaf_n2.begin() + b1, n) - leaf_n2.begin());
-                valmap[k] = (unsigned)(leaf_off_[b] + (size_t)(pi - cl_[n].start) + (size_t)(pj - cs.start) * cl_[n].size);
+    {
+        const std::vector<int>& leaves = bottoms_[0];
+        parallel_chunks(leaves.size(), [&](int, size_t b, size_t e) {
+            for (size_t x = b; x < e; x++) {
+                const int s = leaves[x];
+                const Cluster& cs = cl_[s];
+                const int b0 = blk_begin[s], b1 = blk_begin[s + 1];
+                for (int pj = cs.start; pj < cs.start + cs.size; pj++) {
+                    const int j = ord.perm[pj];
+                    for (int k = A.colptr[j]; k < A.colptr[j + 1]; k++) {
+                        const int pi = pinv[A.rowind[k]];
+                        if (symm && pi < pj) continue;
+                        const int n = cmap[pi];
+                        int bb = b0;
+                        if (n != s)
+                            bb = (int)(std::lower_bound(leaf_n2.begin() + b0 + 1, leaf_n2.begin() + b1, n) - leaf_n2.begin());
+                        valmap[k] = (unsigned)(leaf_off_[bb] + (size_t)(pi - cl_[n].start) + (size_t)(pj - cs.start) * cl_[n].size);
+                    }
+                }
             }
-        }
+        }, 4096);
     }
     lap("value map");
     // plan
@@ -1251,11 +1285,20 @@ void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
         run_potrf(bp, lg);
     }
     mg_barrier();  // a block needs the factor of its row cluster too, possibly from another rank
+    if (scale_inv_mode_ < 0) {
+        const char* e = std::getenv("SPAND_SCALE_INV");
+        scale_inv_mode_ = e ? std::atoi(e) : 1;
+    }
+    const int lmax = level_max_size();
+    // blocks with a dimension above inv_dim go through the explicit-inverse GEMM path (0: none on this level)
+    const int inv_dim = scale_inv_mode_ == 2 ? (lmax > 32 ? 32 : 0) : (scale_inv_mode_ == 1 && big ? SMALL_DIM : 0);
     ev = fam_begin(F_TRSM);
-    launch_scale_sym(tab_, D.s_right, D.s_left, (int)L.s_right.size(), d_mid_, next_counter(), st_);
+    launch_scale_sym(tab_, D.s_right, D.s_left, (int)L.s_right.size(), d_mid_, next_counter(), st_, inv_dim == 32);
     fam_end(F_TRSM, ev);
     lg.launches += 2;
-    if (big) {
+    if (inv_dim > 0) {
+        run_scale_inv(inv_dim, lg);
+    } else if (big) {
         std::vector<TrsmTask> right, left;
         for (size_t i = 0; i < L.s_right.size(); i++) {
             const SymTrsm& r = L.s_right[i];
@@ -1273,6 +1316,133 @@ void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
     sl.s_trsv = arena_->alloc_n<TrsvTask>(L.S.size());
     launch_expand_trsv(tab_, D.S, D.s_piv, sl.n_s_trsv, sl.s_trsv, st_);
     lg.launches++;
+}
+
+// Two-sided scaling of the blocks with a dimension above min_dim (src/tree.cpp:796-856: two cblas_dtrsm per block)
+// as products with the explicit inverses W_c = L_c^-1 of the scaled pivots: Y = B W_c1^T into scratch, then
+// B = W_c2 Y in place. Both passes are ONE grouped tensor-core GEMM launch over all blocks of the level with nothing
+// sequential inside a block (a triangular solve sweeps the 64-wide steps of the triangle one after the other); the
+// triangular shape of W is used through the inner limits GEMM_TRIB / GEMM_TRIA, so the flop count is that of the
+// solves. W_c is computed once per cluster: triangles up to 64 by forward substitution on I (trtri_kernel), larger
+// ones by the strip solve L X = I on top of the inverted diagonal blocks. When sharded, a rank inverts the pivots its
+// own blocks need (the factor of a remote row cluster is read through peer memory, after the barrier above).
+void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
+    const SymLevel& L = plan_.lv[ilvl_];
+    const size_t nb_all = L.s_right.size();
+    if (nb_all == 0) return;
+    // 1. blocks of this rank above the size class of the warp kernel (threaded scan of the level's block list)
+    std::vector<std::vector<int>> part(8);
+    const int nth = parallel_chunks(nb_all, [&](int t, size_t b, size_t e) {
+        std::vector<int>& out = part[t];
+        for (size_t i = b; i < e; i++) {
+            const SymTrsm& r = L.s_right[i];
+            const int m = h_csize_[r.cm], n = h_csize_[r.cn];
+            if ((m > min_dim || n > min_dim) && m > 0 && n > 0 && mine(plan_.en1[r.eB])) out.push_back((int)i);
+        }
+    });
+    std::vector<int> idx;
+    for (int t = 0; t < nth; t++) idx.insert(idx.end(), part[t].begin(), part[t].end());
+    const size_t nt = idx.size();
+    if (nt == 0) return;
+    // 2. inverses of the pivots these blocks touch
+    struct Inv {
+        const double* W = nullptr;
+        int ld = 0;
+    };
+    std::unordered_map<int, Inv> inv;
+    std::vector<TrtriTask> tt;
+    std::vector<EyeTask> eye;
+    std::vector<TrsmTask> solve;
+    std::vector<int> sprefix(1, 0);
+    int max_n = 0;
+    auto need = [&](int c, int eT) {
+        if (inv.count(c)) return;
+        const int n = h_csize_[c];
+        Inv w;
+        if (n <= NB) {
+            const int ld = (n + 1) & ~1;
+            double* W = scratch_->alloc_n<double>((size_t)ld * n);
+            tt.push_back({h_eptr_[eT], h_eld_[eT], n, W, ld});
+            w.W = W;
+            w.ld = ld;
+        } else {
+            const int nblk = (n + NB - 1) / NB;
+            double* blocks = scratch_->alloc_n<double>((size_t)nblk * NB * NB);
+            double* W = scratch_->alloc_n<double>((size_t)n * n);
+            tt.push_back({h_eptr_[eT], h_eld_[eT], n, blocks, 0});
+            eye.push_back({W, n, n});
+            TrsmTask s{};
+            s.B = W;
+            s.ldb = n;
+            s.T = h_eptr_[eT];
+            s.ldt = h_eld_[eT];
+            s.m = n;
+            s.n = n;
+            s.inv = blocks;
+            s.tri = 1;
+            solve.push_back(s);
+            sprefix.push_back(sprefix.back() + nblk);
+            w.W = W;
+            w.ld = n;
+        }
+        max_n = std::max(max_n, n);
+        inv.emplace(c, w);
+    };
+    for (size_t q = 0; q < nt; q++) {
+        need(L.s_right[idx[q]].cn, L.s_right[idx[q]].eT);
+        need(L.s_left[idx[q]].cn, L.s_left[idx[q]].eT);
+    }
+    // 3. the two grouped products
+    std::vector<size_t> yoff(nt + 1, 0);
+    std::vector<int> prefix(nt + 1, 0);
+    for (size_t q = 0; q < nt; q++) {
+        const SymTrsm& r = L.s_right[idx[q]];
+        const size_t m = h_csize_[r.cm], n = h_csize_[r.cn];
+        yoff[q + 1] = yoff[q] + ((m * n + 31) & ~(size_t)31);
+        prefix[q + 1] = prefix[q] + (int)(((m + 63) / 64) * ((n + 63) / 64));
+    }
+    double* Ybase = scratch_->alloc_n<double>(yoff[nt]);
+    std::vector<GemmTask> g1(nt), g2(nt);
+    std::vector<GemmContrib> c1(nt), c2(nt);
+    std::vector<int> tile_task(prefix[nt]);
+    parallel_chunks(nt, [&](int, size_t b, size_t e) {
+        for (size_t q = b; q < e; q++) {
+            const SymTrsm& r = L.s_right[idx[q]];
+            const SymTrsm& l = L.s_left[idx[q]];
+            const int m = h_csize_[r.cm], n = h_csize_[r.cn];
+            const Inv& w1 = inv.find(r.cn)->second;
+            const Inv& w2 = inv.find(l.cn)->second;
+            double* B = h_eptr_[r.eB];
+            const int ldb = h_eld_[r.eB];
+            double* Y = Ybase + yoff[q];
+            g1[q] = GemmTask{Y, m, m, n, (int)q, 1, GEMM_ZERO_INIT | GEMM_POS | GEMM_TRIB};
+            c1[q] = GemmContrib{B, w1.W, ldb, w1.ld, n};
+            g2[q] = GemmTask{B, ldb, m, n, (int)q, 1, GEMM_NN | GEMM_ZERO_INIT | GEMM_POS | GEMM_TRIA};
+            c2[q] = GemmContrib{w2.W, Y, w2.ld, m, m};
+            for (int x = prefix[q]; x < prefix[q + 1]; x++) tile_task[x] = (int)q;
+        }
+    });
+    TrtriTask* dtt = to_device(tt, scratch_);
+    EyeTask* deye = to_device(eye, scratch_);
+    TrsmTask* dsolve = to_device(solve, scratch_);
+    int* dsp = to_device(sprefix, scratch_);
+    GemmTask* dg1 = to_device(g1, scratch_);
+    GemmTask* dg2 = to_device(g2, scratch_);
+    GemmContrib* dc1 = to_device(c1, scratch_);
+    GemmContrib* dc2 = to_device(c2, scratch_);
+    int* dp = to_device(prefix, scratch_);
+    int* dtile = to_device(tile_task, scratch_);
+    auto ev = fam_begin(F_TRSM);
+    launch_trtri(dtt, (int)tt.size(), max_n, st_);
+    if (!solve.empty()) {
+        launch_eye(deye, (int)eye.size(), st_);
+        launch_trsm_strip(TRSM_LLN, dsolve, (int)solve.size(), dsp, sprefix.back(), st_);
+        lg.launches += 2;
+    }
+    launch_gemm_tiled(dg1, (int)nt, dc1, dp, prefix[nt], st_, dtile);
+    launch_gemm_tiled(dg2, (int)nt, dc2, dp, prefix[nt], st_, dtile);
+    fam_end(F_TRSM, ev);
+    lg.launches += 3;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -272,6 +272,9 @@ class Tree {
     void alloc_plu(int c);
     void run_potrf(std::vector<PotrfTask>& tasks, LevelLog& lg);
     void run_trsm(int mode, std::vector<TrsmTask>& tasks, LevelLog& lg);
+    // two-sided scaling through explicit inverses of the pivots' Cholesky factors (two grouped GEMM launches)
+    void run_scale_inv(int min_dim, LevelLog& lg);
+    int scale_inv_mode_ = -1;  // SPAND_SCALE_INV: 0 triangular solves, 1 blocks with a dimension > 64, 2 (default) > 32
     void run_gemm(std::vector<GemmTask>& tasks, std::vector<GemmContrib>& contribs, LevelLog& lg);
     void check_error();
     int ndofs_left() const;

@@ -247,3 +247,43 @@ def test_threaded_geometric_partition_matches_literal_restatement():
             new += [dofs[member(idl)], dofs[member(idr)]]
         doms = new
     assert np.array_equal(got, ids)
+
+
+def _plan_dump(n, d, L, threads):
+    """All plan counts and live edge lists of one configuration, built in a fresh process with a given thread cap."""
+    import json, os, subprocess, sys
+    code = f"""
+import json, sys
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import numpy as np
+import spand_public_b200 as S
+A = S.neglapl({n}, {d}); X = S.linspace_nd({n}, {d})
+g = S.Tree({L}); g.set_use_geo(True); g.set_Xcoo(X); g.partition(A); g.plan_analyze(A)
+out = []
+for lvl in range({L}):
+    out.append([[k, int(v)] for k, v in sorted(g.plan_counts(lvl).items())])
+    for phase in (0, 3):
+        if phase == 3 and lvl == {L} - 1: continue
+        n1, n2 = g.plan_live_edges(lvl, phase)
+        out.append([int(np.asarray(n1, dtype=np.int64).sum()), int(np.asarray(n2, dtype=np.int64).sum()), len(n1),
+                    int((np.asarray(n1, dtype=np.int64) * (np.arange(len(n1)) % 1009)).sum()),
+                    int((np.asarray(n2, dtype=np.int64) * (np.arange(len(n2)) % 1013)).sum())])
+print(json.dumps(out))
+"""
+    env = dict(os.environ)
+    if threads is None:
+        env.pop("SPAND_HOST_THREADS", None)
+    else:
+        env["SPAND_HOST_THREADS"] = str(threads)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_threaded_planner_equals_serial():
+    """Leaf structure, value map and the per-level lists of build_symbolic are built by chunks on host threads
+    (host/parallel.hpp); the plan must not depend on the thread count. 48^3 / 12 levels is large enough for every
+    threaded section to split (10^4-10^5 clusters per level)."""
+    serial = _plan_dump(48, 3, 12, 1)
+    assert serial == _plan_dump(48, 3, 12, None)
+    assert serial == _plan_dump(48, 3, 12, 3)
