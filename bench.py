@@ -290,6 +290,9 @@ def main():
     ap.add_argument("--config", default="c4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--algebraic", action="store_true",
+                    help="algebraic modified ND (METIS vertex separators, src/partition.cpp:51-97) instead of the "
+                         "geometric one: the reference's default when no coordinates are given (SURVEY 8d, config C2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -395,8 +398,11 @@ def main():
         # peer memory over NVLink); every rank makes the same calls
         t.mg_init(dist, device=local_rank)
     t.set_tol(tol)
-    t.set_use_geo(True)
-    t.set_Xcoo(X)
+    if args.algebraic:
+        t.set_use_geo(False)
+    else:
+        t.set_use_geo(True)
+        t.set_Xcoo(X)
     tp0 = time.perf_counter()
     t.partition(G)
     tpart = time.perf_counter() - tp0
@@ -477,7 +483,7 @@ def main():
 
     # the bench line carries its own correctness check (at every GPU count): one-solve residual within the reference's
     # ApproxTest bound (tests/tests.cpp:799-856) and the Krylov iteration count against the committed oracle golden
-    gold = golden_of(args.config)
+    gold = None if args.algebraic else golden_of(args.config)  # the goldens are geometric-partition runs
     check = {"residual_one_solve": res, "residual_bound": 200 * tol, "iterations": cg_it,
              "oracle_iterations": gold["iterations"] if gold else None,
              "oracle_residual_one_solve": gold["residual_one_solve"] if gold else None}
@@ -562,7 +568,7 @@ def main():
     roof["phase_seconds"] = {k: float(v) for k, v in phases.items()}
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.algebraic:
         # bounded live sample on this box's host cores (10-30 s of CPU work); the one-off run of the oracle on the
         # full workload is the committed golden (tests/golden/, measured on the build container's host)
         scfg = CONFIGS["s80"] if args.config == "c4" else (CONFIGS["a48"] if args.config in ANISO else cfg)
@@ -582,7 +588,8 @@ def main():
         "config": {"workload": desc, "N": N, "parallelism": "single GPU" if world == 1 else
                    f"one factorization sharded by ND sub-trees over {world} GPUs, peer memory over NVLink",
                    "l2": "inputs (assembled blocks and factors, ~%.1f GB over all ranks) are larger than L2" % (arena_b / 1e9),
-                   "partition": "geometric modified ND on linspace_nd coordinates (host, untimed: %.2f s)" % tpart,
+                   "partition": ("algebraic modified ND, METIS vertex separators (host, untimed: %.2f s)" if args.algebraic
+                                 else "geometric modified ND on linspace_nd coordinates (host, untimed: %.2f s)") % tpart,
                    "symbolic": "block structure of all levels analysed once per pattern in the first assemble() "
                                "(untimed: %.2f s) and reused by every later assemble()/factorize()" % t.analyze_seconds()},
         "factorize_time_s": tdev / args.steps, "fp64_tflops": flops / (tdev / args.steps) / 1e12,

@@ -1,4 +1,5 @@
 #include "partition.hpp"
+#include "parallel.hpp"
 
 #include <algorithm>
 #include <cstdio>
@@ -66,51 +67,95 @@ void separator_metis(const std::vector<int>& colptr, const std::vector<int>& row
     for (int i = 0; i < size; i++) parts[i] = (int)p64[i];
 }
 
+// fn(chunk, begin, end): loop [0, n) in contiguous, ordered chunks on `inner` host threads (the first depths of the bisection have fewer sub-domains
+// than cores: the loops over the dofs of ONE sub-domain are split instead)
+template <class F>
+void inner_chunks(int inner, size_t n, F fn) {
+    if (inner <= 1 || n < 32768) {
+        fn(0, (size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < inner; t++) pool.emplace_back(fn, t, n * t / inner, n * (t + 1) / inner);
+    fn(0, (size_t)0, n / inner);
+    for (auto& th : pool) th.join();
+}
+
 // src/partition.cpp:139-210
 void separator_geo(const std::vector<int>& colptr, const std::vector<int>& rowval, const std::vector<int>& dofs,
-                   std::vector<int>& parts, const DenseMat& X, std::vector<int>& invp) {
+                   std::vector<int>& parts, const DenseMat& X, std::vector<int>& invp, int inner) {
     int N = (int)dofs.size();
     if (N == 0) return;
     int bestdim = -1;
     double maxrange = -1.0;
-    for (int d = 0; d < X.rows; d++) {
-        double maxi = std::numeric_limits<double>::lowest(), mini = std::numeric_limits<double>::max();
-        for (int g : dofs) {
-            double x = X(d, g);
-            maxi = std::max(maxi, x);
-            mini = std::min(mini, x);
-        }
-        if (maxi - mini > maxrange) {
-            bestdim = d;
-            maxrange = maxi - mini;
+    {
+        const int D = X.rows;
+        const int nch = (inner <= 1 || N < 32768) ? 1 : inner;
+        std::vector<double> lo((size_t)nch * D, std::numeric_limits<double>::max());
+        std::vector<double> hi((size_t)nch * D, std::numeric_limits<double>::lowest());
+        inner_chunks(inner, (size_t)N, [&](int c, size_t b, size_t e) {
+            for (int d = 0; d < D; d++) {
+                double maxi = std::numeric_limits<double>::lowest(), mini = std::numeric_limits<double>::max();
+                for (size_t i = b; i < e; i++) {
+                    double x = X(d, dofs[i]);
+                    maxi = std::max(maxi, x);
+                    mini = std::min(mini, x);
+                }
+                lo[(size_t)c * D + d] = mini;
+                hi[(size_t)c * D + d] = maxi;
+            }
+        });
+        for (int d = 0; d < D; d++) {
+            double maxi = std::numeric_limits<double>::lowest(), mini = std::numeric_limits<double>::max();
+            for (int c = 0; c < nch; c++) {
+                maxi = std::max(maxi, hi[(size_t)c * D + d]);
+                mini = std::min(mini, lo[(size_t)c * D + d]);
+            }
+            if (maxi - mini > maxrange) {
+                bestdim = d;
+                maxrange = maxi - mini;
+            }
         }
     }
     // Median coordinate = value at rank N/2 (the reference sorts the dofs; only this value is used)
     std::vector<double> xs(N);
-    for (int i = 0; i < N; i++) xs[i] = X(bestdim, dofs[i]);
+    inner_chunks(inner, (size_t)N, [&](int, size_t b, size_t e) {
+        for (size_t i = b; i < e; i++) xs[i] = X(bestdim, dofs[i]);
+    });
     std::nth_element(xs.begin(), xs.begin() + N / 2, xs.end());
     double midv = xs[N / 2];
     for (int g : dofs) {
         invp[g] = -1;
         for (int k = colptr[g]; k < colptr[g + 1]; k++) invp[rowval[k]] = -1;
     }
-    for (int i = 0; i < N; i++) {
-        int g = dofs[i];
-        invp[g] = i;
-        parts[i] = (X(bestdim, g) < midv) ? 0 : 1;
-    }
-    for (int i = 0; i < N; i++) {
-        if (parts[i] == 0) continue;
-        int g = dofs[i];
-        for (int k = colptr[g]; k < colptr[g + 1]; k++) {
-            int in = invp[rowval[k]];
-            if (in == -1) continue;
-            if (parts[in] == 0) {
-                parts[i] = 2;
-                break;
+    inner_chunks(inner, (size_t)N, [&](int, size_t b, size_t e) {
+        for (size_t i = b; i < e; i++) {
+            int g = dofs[i];
+            invp[g] = (int)i;
+            parts[i] = (X(bestdim, g) < midv) ? 0 : 1;
+        }
+    });
+    // a dof of side 1 with a neighbour of side 0 goes to the separator (only sides 0 are looked at and they never
+    // change, so the chunks are independent; the flags are applied afterwards, nobody reads what another one writes)
+    std::vector<char> tosep(N, 0);
+    inner_chunks(inner, (size_t)N, [&](int, size_t b, size_t e) {
+        for (size_t i = b; i < e; i++) {
+            if (parts[i] == 0) continue;
+            int g = dofs[i];
+            for (int k = colptr[g]; k < colptr[g + 1]; k++) {
+                int in = invp[rowval[k]];
+                if (in == -1) continue;
+                if (parts[in] == 0) {
+                    tosep[i] = 1;
+                    break;
+                }
             }
         }
-    }
+    });
+    inner_chunks(inner, (size_t)N, [&](int, size_t b, size_t e) {
+        for (size_t i = b; i < e; i++)
+            if (tosep[i]) parts[i] = 2;
+    });
 }
 
 }  // namespace
@@ -144,7 +189,13 @@ std::vector<ClusterID> partition_modifiedND(const SpMat& A, int nlevels, const D
         std::vector<std::vector<int>> newdoms(2 * nseps);
         const int nthreads = (N >= 100000) ? std::min(max_threads, nseps) : 1;
         std::atomic<int> next(0);
-        part_prev = part;
+        // sub-domains of this depth go to the pool; while there are fewer of them than threads, the loops over the dofs
+        // of one sub-domain are split instead (inner threads)
+        const int inner = (N >= 100000 && nseps < max_threads) ? std::max(1, max_threads / nseps) : 1;
+        part_prev.resize(part.size());
+        parallel_chunks(part.size(), [&](int, size_t b, size_t e) {
+            std::copy(part.begin() + b, part.begin() + e, part_prev.begin() + b);
+        }, (size_t)(max_threads > 1 ? 262144 : ~(size_t)0 >> 1));
         auto run = [&](int tix) {
             Work& w = work[tix];
             if ((int)w.scratch.size() < N + 1) {
@@ -160,36 +211,50 @@ std::vector<ClusterID> partition_modifiedND(const SpMat& A, int nlevels, const D
                 SepID idself(level, sep);
                 std::vector<int>& dofs = doms[sep];
                 if (!std::is_sorted(dofs.begin(), dofs.end())) std::sort(dofs.begin(), dofs.end());
-                if (geo) separator_geo(colptr, rowval, dofs, parttmp, *Xcoo, scratch);
+                if (geo) separator_geo(colptr, rowval, dofs, parttmp, *Xcoo, scratch, inner);
                 else separator_metis(colptr, rowval, dofs, parttmp);
                 SepID idleft(level - 1, 2 * sep), idright(level - 1, 2 * sep + 1);
                 // A separator dof sits in two sub-domains (its l and r sides), i.e. two threads may hold it: each
                 // reads the ClusterID as it was when the depth started (part_prev, immutable) and writes back only the
                 // fields that carried its own separator id, which no other sub-domain of this depth can own.
-                long nnewsep = 0;
-                for (size_t i = 0; i < dofs.size(); i++) {
-                    const int g = dofs[i];
-                    const ClusterID& p0 = part_prev[g];
-                    ClusterID q = p0;
-                    int side = parttmp[i];
-                    if (side == 0 || side == 1) {
-                        const SepID& idside = (side == 0 ? idleft : idright);
-                        if (q.self == idself) q.self = idside;
-                        if (q.l == idself) q.l = idside;
-                        if (q.r == idself) q.r = idside;
-                    } else if (side == 2) {
-                        if (q.self == idself) {
-                            q.l = idleft;
-                            q.r = idright;
+                const int nch = (inner <= 1 || dofs.size() < 32768) ? 1 : inner;
+                std::vector<std::vector<int>> lefts(nch), rights(nch);
+                std::vector<long> newsep(nch, 0);
+                inner_chunks(inner, dofs.size(), [&](int c, size_t b, size_t e) {
+                    std::vector<int>& L = lefts[c];
+                    std::vector<int>& R = rights[c];
+                    long nnew = 0;
+                    for (size_t i = b; i < e; i++) {
+                        const int g = dofs[i];
+                        const ClusterID& p0 = part_prev[g];
+                        ClusterID q = p0;
+                        int side = parttmp[i];
+                        if (side == 0 || side == 1) {
+                            const SepID& idside = (side == 0 ? idleft : idright);
+                            if (q.self == idself) q.self = idside;
+                            if (q.l == idself) q.l = idside;
+                            if (q.r == idself) q.r = idside;
+                        } else if (side == 2) {
+                            if (q.self == idself) {
+                                q.l = idleft;
+                                q.r = idright;
+                            }
                         }
+                        ClusterID& p = part[g];
+                        if (!(q.self == p0.self)) p.self = q.self;
+                        if (!(q.l == p0.l)) p.l = q.l;
+                        if (!(q.r == p0.r)) p.r = q.r;
+                        if (q.self == idleft || q.l == idleft || q.r == idleft) L.push_back(g);
+                        if (q.self == idright || q.l == idright || q.r == idright) R.push_back(g);
+                        if (q.self == idself && q.l == idleft && q.r == idright) nnew++;
                     }
-                    ClusterID& p = part[g];
-                    if (!(q.self == p0.self)) p.self = q.self;
-                    if (!(q.l == p0.l)) p.l = q.l;
-                    if (!(q.r == p0.r)) p.r = q.r;
-                    if (q.self == idleft || q.l == idleft || q.r == idleft) newdoms[2 * sep].push_back(g);
-                    if (q.self == idright || q.l == idright || q.r == idright) newdoms[2 * sep + 1].push_back(g);
-                    if (q.self == idself && q.l == idleft && q.r == idright) nnewsep++;
+                    newsep[c] = nnew;
+                });
+                long nnewsep = 0;
+                for (int c = 0; c < nch; c++) {
+                    newdoms[2 * sep].insert(newdoms[2 * sep].end(), lefts[c].begin(), lefts[c].end());
+                    newdoms[2 * sep + 1].insert(newdoms[2 * sep + 1].end(), rights[c].begin(), rights[c].end());
+                    nnewsep += newsep[c];
                 }
                 w.sepmin = std::min(w.sepmin, nnewsep);
                 w.sepmax = std::max(w.sepmax, nnewsep);
@@ -211,6 +276,15 @@ std::vector<ClusterID> partition_modifiedND(const SpMat& A, int nlevels, const D
             septot += work[tix].septot;
         }
         doms.swap(newdoms);
+        if (getenv("SPAND_TIMING_DEPTH")) {
+            struct timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            static double tprev = 0;
+            double tn = ts.tv_sec + 1e-9 * ts.tv_nsec;
+            fprintf(stderr, "[spand] MND depth %d: %d sub-domains, %d threads x %d inner, +%.1f ms\n", depth, nseps, nthreads,
+                    inner, tprev > 0 ? (tn - tprev) * 1e3 : 0.0);
+            tprev = tn;
+        }
         if (verb)
             printf("  Depth %2d: (%5d separators, [%5ld %5ld], mean %6.1f)\n", depth + 1, nseps, sepmin, sepmax,
                    (double)septot / nseps);
