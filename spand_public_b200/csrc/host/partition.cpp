@@ -350,10 +350,35 @@ Ordering build_ordering(const SpMat& A, int nlevels, const DenseMat* Xcoo, bool 
     {
         std::vector<ClusterID> merged = gids;
         auto cmp = [&merged](int i, int j) { return merged[i] < merged[j]; };
-        std::stable_sort(gorder.begin(), gorder.end(), cmp);
+        // stable sort = stable sorts of contiguous chunks on host threads + stable merges of neighbouring runs
+        // (std::inplace_merge keeps the left run first on ties): the same permutation as one std::stable_sort
+        auto sort_stable = [&]() {
+            const size_t n = gorder.size();
+            std::vector<size_t> cut;
+            const int nth = parallel_chunks(n, [&](int, size_t b, size_t e) {
+                std::stable_sort(gorder.begin() + b, gorder.begin() + e, cmp);
+            }, 8192);
+            for (int t = 0; t <= nth; t++) cut.push_back(n * t / nth);
+            while (cut.size() > 2) {
+                std::vector<size_t> next;
+                std::vector<std::thread> pool;
+                for (size_t k = 0; k + 2 < cut.size(); k += 2) {
+                    pool.emplace_back([&, k] {
+                        std::inplace_merge(gorder.begin() + cut[k], gorder.begin() + cut[k + 1], gorder.begin() + cut[k + 2], cmp);
+                    });
+                }
+                for (auto& th : pool) th.join();
+                for (size_t k = 0; k < cut.size(); k += 2) next.push_back(cut[k]);
+                if (next.back() != n) next.push_back(n);
+                cut.swap(next);
+            }
+        };
+        sort_stable();
         for (int lvl = 1; lvl < nlevels; lvl++) {
-            for (auto& c : merged) c = merge_if(c, lvl);
-            std::stable_sort(gorder.begin(), gorder.end(), cmp);
+            parallel_chunks(merged.size(), [&](int, size_t b, size_t e) {
+                for (size_t i = b; i < e; i++) merged[i] = merge_if(merged[i], lvl);
+            }, 8192);
+            sort_stable();
         }
     }
     {

@@ -1152,23 +1152,37 @@ __global__ void __launch_bounds__(NB) potrf_mid_kernel(DevTables T, const int* _
 
 // In-warp triangular solves on a tile Bs[col * WLD + row] (rows x cols); the triangle is read from global memory
 // (uniform addresses: one broadcast transaction per load, L1-resident).
+// a / d given rinv = RN(1 / d): product, exact remainder (one FMA), one correction (Markstein's division step). Three
+// dependent operations instead of the ~25-instruction IEEE division sequence on the substitution chain; the result is
+// the correctly rounded quotient except in rare cases that are off by one ulp.
+__device__ __forceinline__ double div_by(double a, double d, double rinv) {
+    const double q = a * rinv;
+    const double r = fma(-d, q, a);
+    return fma(r, rinv, q);
+}
+template <bool FASTDIV>
 __device__ __forceinline__ void warp_solve_right_lt(double* Bs, int rows, int cols, const double* L, int ldl, int lane) {
     // B <- B L^-T : lane = row of B
     if (lane < rows)
         for (int j = 0; j < cols; j++) {
+            const double d = L[j + (size_t)j * ldl];
+            const double rinv = FASTDIV ? 1.0 / d : 0.0;  // off the dependent chain
             double v = Bs[j * WLD + lane];
             for (int p = 0; p < j; p++) v -= Bs[p * WLD + lane] * L[j + (size_t)p * ldl];
-            Bs[j * WLD + lane] = v / L[j + (size_t)j * ldl];
+            Bs[j * WLD + lane] = FASTDIV ? div_by(v, d, rinv) : v / d;
         }
 }
+template <bool FASTDIV>
 __device__ __forceinline__ void warp_solve_left_ln(double* Bs, int rows, int cols, const double* L, int ldl, int lane) {
     // B <- L^-1 B : lane = column of B
     if (lane < cols) {
         double* x = Bs + lane * WLD;
         for (int i = 0; i < rows; i++) {
+            const double d = L[i + (size_t)i * ldl];
+            const double rinv = FASTDIV ? 1.0 / d : 0.0;
             double v = x[i];
             for (int p = 0; p < i; p++) v -= L[i + (size_t)p * ldl] * x[p];
-            x[i] = v / L[i + (size_t)i * ldl];
+            x[i] = FASTDIV ? div_by(v, d, rinv) : v / d;
         }
     }
 }
@@ -1188,7 +1202,7 @@ __device__ __forceinline__ void warp_tile_store(const double* Bs, double* B, int
 // MODE: TRSM_RLT (B is cm x cn) or TRSM_LLN (B is cn x cm)
 template <int MODE>
 __global__ void __launch_bounds__(128) trsm_sym_kernel(DevTables T, const SymTrsm* __restrict__ tasks, int nt, int* mid,
-                                                       int* cnt) {
+                                                       int* cnt, int fastdiv) {
     __shared__ double Sw[4][32 * WLD];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * 4 + w;
@@ -1209,13 +1223,15 @@ __global__ void __launch_bounds__(128) trsm_sym_kernel(DevTables T, const SymTrs
     if (MODE == TRSM_RLT) {
         warp_tile_load(S, B, ldb, m, n, lane);
         __syncwarp();
-        warp_solve_right_lt(S, m, n, L, ldl, lane);
+        if (fastdiv) warp_solve_right_lt<true>(S, m, n, L, ldl, lane);
+        else warp_solve_right_lt<false>(S, m, n, L, ldl, lane);
         __syncwarp();
         warp_tile_store(S, B, ldb, m, n, lane);
     } else {
         warp_tile_load(S, B, ldb, n, m, lane);
         __syncwarp();
-        warp_solve_left_ln(S, n, m, L, ldl, lane);
+        if (fastdiv) warp_solve_left_ln<true>(S, n, m, L, ldl, lane);
+        else warp_solve_left_ln<false>(S, n, m, L, ldl, lane);
         __syncwarp();
         warp_tile_store(S, B, ldb, n, m, lane);
     }
@@ -1241,7 +1257,7 @@ __global__ void __launch_bounds__(NB) trsm_mid_kernel(DevTables T, const SymTrsm
 // entries q > p. Every entry sees v <- fma(-x_p, L(q, p), v) for p = 0..q-1 in this order and one division: the
 // arithmetic (and its rounding) of the row-by-row substitution it replaces (trsm_tile64), with 16 independent updates
 // per thread and step instead of one dependent chain per thread.
-template <bool ROWS, int NTM>  // NTM: compile-time bound of the triangle dimension (multiple of 4)
+template <bool ROWS, int NTM, bool FASTDIV>  // NTM: compile-time bound of the triangle dimension (multiple of 4)
 __device__ __forceinline__ void tile_solve_rl_n(double* Bs, const double* Ls, int nt, int nu) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (8 * warp >= nu) return;  // no unit on this warp
@@ -1256,7 +1272,8 @@ __device__ __forceinline__ void tile_solve_rl_n(double* Bs, const double* Ls, in
 #pragma unroll
     for (int p = 0; p < NTM; p++) {
         if (p < nt) {  // uniform
-            double x = v[p >> 2] / Ls[p * LDS + p];
+            // FASTDIV: 1 / L(p, p) sits in the padding row of the tile (tile_load_l)
+            double x = FASTDIV ? div_by(v[p >> 2], Ls[p * LDS + p], Ls[p * LDS + NB]) : v[p >> 2] / Ls[p * LDS + p];
             x = __shfl_sync(FULLM, x, (lane & ~3) | (p & 3));
             if (c == (p & 3)) v[p >> 2] = x;
             const double* lp = Ls + p * LDS + c;
@@ -1274,12 +1291,12 @@ __device__ __forceinline__ void tile_solve_rl_n(double* Bs, const double* Ls, in
         }
     }
 }
-template <bool ROWS>
+template <bool ROWS, bool FASTDIV>
 __device__ __forceinline__ void tile_solve_rl(double* Bs, const double* Ls, int nt, int nu) {
-    if (nt <= 16) tile_solve_rl_n<ROWS, 16>(Bs, Ls, nt, nu);
-    else if (nt <= 32) tile_solve_rl_n<ROWS, 32>(Bs, Ls, nt, nu);
-    else if (nt <= 48) tile_solve_rl_n<ROWS, 48>(Bs, Ls, nt, nu);
-    else tile_solve_rl_n<ROWS, 64>(Bs, Ls, nt, nu);
+    if (nt <= 16) tile_solve_rl_n<ROWS, 16, FASTDIV>(Bs, Ls, nt, nu);
+    else if (nt <= 32) tile_solve_rl_n<ROWS, 32, FASTDIV>(Bs, Ls, nt, nu);
+    else if (nt <= 48) tile_solve_rl_n<ROWS, 48, FASTDIV>(Bs, Ls, nt, nu);
+    else tile_solve_rl_n<ROWS, 64, FASTDIV>(Bs, Ls, nt, nu);
 }
 
 // B tile (rows x cols) and lower triangle (n x n) into shared memory, zero-filled up to 64 x 64
@@ -1292,7 +1309,9 @@ __device__ __forceinline__ void tile_load_b(double* Bs, const double* B, int ldb
 __device__ __forceinline__ void tile_load_l(double* Ls, const double* L, int ldl, int n) {
     for (int x = threadIdx.x; x < NB * NB; x += blockDim.x) {
         const int i = x & (NB - 1), j = x >> 6;
-        Ls[j * LDS + i] = (i < n && j <= i) ? L[i + (size_t)j * ldl] : 0.0;
+        const double v = (i < n && j <= i) ? L[i + (size_t)j * ldl] : 0.0;
+        Ls[j * LDS + i] = v;
+        if (i == j) Ls[j * LDS + NB] = (i < n) ? 1.0 / v : 1.0;  // reciprocal of the diagonal in the padding row
     }
 }
 __device__ __forceinline__ void tile_store_b(const double* Bs, double* B, int ldb, int rows, int cols) {
@@ -1302,7 +1321,7 @@ __device__ __forceinline__ void tile_store_b(const double* Bs, double* B, int ld
     }
 }
 
-template <int MODE>
+template <int MODE, bool FASTDIV>
 __global__ void __launch_bounds__(256) trsm_mid256_kernel(DevTables T, const SymTrsm* __restrict__ tasks,
                                                        const int* __restrict__ mid, const int* __restrict__ cnt) {
     extern __shared__ double trsm_smem[];
@@ -1318,7 +1337,7 @@ __global__ void __launch_bounds__(256) trsm_mid256_kernel(DevTables T, const Sym
         tile_load_b(Bs, B, ldb, rows, cols);
         tile_load_l(Ls, T.eptr[t.eT], T.eld[t.eT], n);
         __syncthreads();
-        tile_solve_rl<MODE == TRSM_RLT>(Bs, Ls, n, m);
+        tile_solve_rl<MODE == TRSM_RLT, FASTDIV>(Bs, Ls, n, m);
         __syncthreads();
         tile_store_b(Bs, B, ldb, rows, cols);
         __syncthreads();
@@ -1338,7 +1357,7 @@ __global__ void __launch_bounds__(128) scale_sym_kernel(DevTables T, const SymTr
     const int rows = T.csize[r.cm], cols = T.csize[r.cn];
     if (rows <= 0 || cols <= 0 || rows > SMALL_DIM || cols > SMALL_DIM) return;
     if (rows > 32 || cols > 32) {
-        if (lane == 0 && !warp_only) push_mid(mid, cnt, ti);
+        if (lane == 0 && !(warp_only & 1)) push_mid(mid, cnt, ti);
         return;
     }
     const int eL = left[ti].eT;
@@ -1347,9 +1366,15 @@ __global__ void __launch_bounds__(128) scale_sym_kernel(DevTables T, const SymTr
     double* S = Sw[w];
     warp_tile_load(S, B, ldb, rows, cols, lane);
     __syncwarp();
-    warp_solve_right_lt(S, rows, cols, T.eptr[r.eT], T.eld[r.eT], lane);
-    __syncwarp();
-    warp_solve_left_ln(S, rows, cols, T.eptr[eL], T.eld[eL], lane);
+    if (warp_only & 2) {  // bit 1: fast division
+        warp_solve_right_lt<true>(S, rows, cols, T.eptr[r.eT], T.eld[r.eT], lane);
+        __syncwarp();
+        warp_solve_left_ln<true>(S, rows, cols, T.eptr[eL], T.eld[eL], lane);
+    } else {
+        warp_solve_right_lt<false>(S, rows, cols, T.eptr[r.eT], T.eld[r.eT], lane);
+        __syncwarp();
+        warp_solve_left_ln<false>(S, rows, cols, T.eptr[eL], T.eld[eL], lane);
+    }
     __syncwarp();
     warp_tile_store(S, B, ldb, rows, cols, lane);
 }
@@ -1370,6 +1395,7 @@ __global__ void __launch_bounds__(NB) scale_mid_kernel(DevTables T, const SymTrs
     }
 }
 
+template <bool FASTDIV>
 __global__ void __launch_bounds__(256, 3) scale_mid256_kernel(DevTables T, const SymTrsm* __restrict__ right,
                                                         const SymTrsm* __restrict__ left, const int* __restrict__ mid,
                                                         const int* __restrict__ cnt) {
@@ -1386,11 +1412,11 @@ __global__ void __launch_bounds__(256, 3) scale_mid256_kernel(DevTables T, const
         tile_load_b(Bs, B, ldb, rows, cols);
         tile_load_l(Ls, T.eptr[r.eT], T.eld[r.eT], cols);
         __syncthreads();
-        tile_solve_rl<true>(Bs, Ls, cols, rows);  // B <- B L_c1^-T
+        tile_solve_rl<true, FASTDIV>(Bs, Ls, cols, rows);  // B <- B L_c1^-T
         __syncthreads();
         tile_load_l(Ls, T.eptr[eL], T.eld[eL], rows);
         __syncthreads();
-        tile_solve_rl<false>(Bs, Ls, rows, cols);  // B <- L_c2^-1 B
+        tile_solve_rl<false, FASTDIV>(Bs, Ls, rows, cols);  // B <- L_c2^-1 B
         __syncthreads();
         tile_store_b(Bs, B, ldb, rows, cols);
         __syncthreads();
@@ -1760,15 +1786,28 @@ bool mid256() {
     }
     return v != 0;
 }
+// SPAND_FASTDIV (default 0): divisions of the substitutions (blocks up to 64) as product + exact remainder + correction
+// with the reciprocal of the diagonal entry taken off the dependent chain (div_by)
+bool fastdiv() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("SPAND_FASTDIV");
+        v = e ? std::atoi(e) : 0;
+    }
+    return v != 0;
+}
 void configure_mid_smem() {
     static bool configured = false;
     if (configured) return;
     cudaFuncSetAttribute(trsm_mid_kernel<TRSM_RLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
     cudaFuncSetAttribute(trsm_mid_kernel<TRSM_LLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
     cudaFuncSetAttribute(scale_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
-    cudaFuncSetAttribute(trsm_mid256_kernel<TRSM_RLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
-    cudaFuncSetAttribute(trsm_mid256_kernel<TRSM_LLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
-    cudaFuncSetAttribute(scale_mid256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(trsm_mid256_kernel<TRSM_RLT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(trsm_mid256_kernel<TRSM_LLN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(scale_mid256_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(trsm_mid256_kernel<TRSM_RLT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(trsm_mid256_kernel<TRSM_LLN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+    cudaFuncSetAttribute(scale_mid256_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
     configured = true;
 }
 }  // namespace
@@ -1783,12 +1822,18 @@ void launch_trsm_sym(int mode, const DevTables& T, const SymTrsm* tasks, int nt,
     if (nt <= 0) return;
     configure_mid_smem();
     if (mode == TRSM_RLT) {
-        trsm_sym_kernel<TRSM_RLT><<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, mid, cnt);
-        if (mid256()) trsm_mid256_kernel<TRSM_RLT><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+        trsm_sym_kernel<TRSM_RLT><<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, mid, cnt, fastdiv() ? 1 : 0);
+        if (mid256() && fastdiv())
+            trsm_mid256_kernel<TRSM_RLT, true><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+        else if (mid256())
+            trsm_mid256_kernel<TRSM_RLT, false><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, tasks, mid, cnt);
         else trsm_mid_kernel<TRSM_RLT><<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, tasks, mid, cnt);
     } else {
-        trsm_sym_kernel<TRSM_LLN><<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, mid, cnt);
-        if (mid256()) trsm_mid256_kernel<TRSM_LLN><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+        trsm_sym_kernel<TRSM_LLN><<<(nt + 3) / 4, 128, 0, st>>>(T, tasks, nt, mid, cnt, fastdiv() ? 1 : 0);
+        if (mid256() && fastdiv())
+            trsm_mid256_kernel<TRSM_LLN, true><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, tasks, mid, cnt);
+        else if (mid256())
+            trsm_mid256_kernel<TRSM_LLN, false><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, tasks, mid, cnt);
         else trsm_mid_kernel<TRSM_LLN><<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, tasks, mid, cnt);
     }
 }
@@ -1796,9 +1841,12 @@ void launch_scale_sym(const DevTables& T, const SymTrsm* right, const SymTrsm* l
                       cudaStream_t st, bool warp_only) {
     if (nt <= 0) return;
     configure_mid_smem();
-    scale_sym_kernel<<<(nt + 3) / 4, 128, 0, st>>>(T, right, left, nt, mid, cnt, warp_only ? 1 : 0);
+    scale_sym_kernel<<<(nt + 3) / 4, 128, 0, st>>>(T, right, left, nt, mid, cnt, (warp_only ? 1 : 0) | (fastdiv() ? 2 : 0));
     if (warp_only) return;
-    if (mid256()) scale_mid256_kernel<<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, right, left, mid, cnt);
+    if (mid256() && fastdiv())
+        scale_mid256_kernel<true><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, right, left, mid, cnt);
+    else if (mid256())
+        scale_mid256_kernel<false><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, right, left, mid, cnt);
     else scale_mid_kernel<<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, right, left, mid, cnt);
 }
 void launch_gemm_sym(const DevTables& T, const SymGemm* tasks, int nt, const SymCon* con, int* mid, int* cnt,
