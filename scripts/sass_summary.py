@@ -29,7 +29,7 @@ for line in sass.splitlines():
         op = m.group(1)
         cur["_all"] += 1
         for k in MN:
-            if op == k or op.startswith(k + "."):
+            if op == k or op.startswith(k + ".") or op.startswith(k + "_"):
                 cur[k] += 1
 print("# SASS summary of `%s` (sm_100a)\n" % os.path.relpath(lib, ROOT))
 print("`cuobjdump -sass` of the shipped library, instruction counts per kernel (static code, not executed counts). "

@@ -1786,13 +1786,13 @@ bool mid256() {
     }
     return v != 0;
 }
-// SPAND_FASTDIV (default 0): divisions of the substitutions (blocks up to 64) as product + exact remainder + correction
+// SPAND_FASTDIV (default 1): divisions of the substitutions (blocks up to 64) as product + exact remainder + correction
 // with the reciprocal of the diagonal entry taken off the dependent chain (div_by)
 bool fastdiv() {
     static int v = -1;
     if (v < 0) {
         const char* e = std::getenv("SPAND_FASTDIV");
-        v = e ? std::atoi(e) : 0;
+        v = e ? std::atoi(e) : 1;
     }
     return v != 0;
 }

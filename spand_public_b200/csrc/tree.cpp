@@ -34,6 +34,11 @@ void cuda_check(cudaError_t e, const char* what) {
 // ------------------------------------------------------------------------------------------------
 // memory
 // ------------------------------------------------------------------------------------------------
+// device / pinned allocations of the process (first-call cost of a factorization), reported with SPAND_TIMING
+static double g_malloc_seconds = 0;
+static long g_malloc_calls = 0;
+static size_t g_malloc_bytes = 0;
+
 void* DeviceArena::alloc(size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
     if (bytes == 0) bytes = 256;
@@ -52,7 +57,11 @@ void* DeviceArena::alloc(size_t bytes) {
         Chunk c;
         c.cap = std::max(chunk_, bytes);
         c.top = 0;
+        const double t0 = wtime();
         CK(cudaMalloc((void**)&c.p, c.cap));
+        g_malloc_seconds += wtime() - t0;
+        g_malloc_calls++;
+        g_malloc_bytes += c.cap;
         chunks_.push_back(c);
     }
 }
@@ -80,7 +89,10 @@ void Stager::reserve(size_t bytes) {
     if (bytes <= cap_) return;
     if (pinned_) cudaFreeHost(pinned_);
     cap_ = bytes;
+    const double t0 = wtime();
     CK(cudaMallocHost((void**)&pinned_, cap_));
+    g_malloc_seconds += wtime() - t0;
+    g_malloc_calls++;
     top_ = 0;
 }
 void Stager::upload(void* dst, const void* src, size_t bytes, cudaStream_t st) {
@@ -134,7 +146,7 @@ void Tree::ensure_device() {
     arena_ = new DeviceArena((size_t)1 << 30);
     scratch_ = new DeviceArena((size_t)256 << 20);
     sym_arena_ = new DeviceArena((size_t)256 << 20);
-    stager_.reserve((size_t)256 << 20);
+    stager_.reserve((size_t)64 << 20);
     CK(cudaMalloc((void**)&d_err_, sizeof(int)));
     CK(cudaMalloc((void**)&d_cnt_, sizeof(int) * 64));
     for (int i = 0; i < kSide; i++) {
@@ -1287,7 +1299,7 @@ void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
     mg_barrier();  // a block needs the factor of its row cluster too, possibly from another rank
     if (scale_inv_mode_ < 0) {
         const char* e = std::getenv("SPAND_SCALE_INV");
-        scale_inv_mode_ = e ? std::atoi(e) : 1;
+        scale_inv_mode_ = e ? std::atoi(e) : 1;  // measured best that keeps rank parity
     }
     const int lmax = level_max_size();
     // blocks with a dimension above inv_dim go through the explicit-inverse GEMM path (0: none on this level)
@@ -1401,7 +1413,10 @@ void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
         yoff[q + 1] = yoff[q] + ((m * n + 31) & ~(size_t)31);
         prefix[q + 1] = prefix[q] + (int)(((m + 63) / 64) * ((n + 63) / 64));
     }
-    double* Ybase = scratch_->alloc_n<double>(yoff[nt]);
+    // one scratch block per product (bump allocations inside the arena's chunks, which later levels reuse: one
+    // allocation of the level's total would cost a multi-GB cudaMalloc at every level of the first factorization)
+    std::vector<double*> Yptr(nt);
+    for (size_t q = 0; q < nt; q++) Yptr[q] = scratch_->alloc_n<double>(yoff[q + 1] - yoff[q]);
     std::vector<GemmTask> g1(nt), g2(nt);
     std::vector<GemmContrib> c1(nt), c2(nt);
     std::vector<int> tile_task(prefix[nt]);
@@ -1414,7 +1429,7 @@ void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
             const Inv& w2 = inv.find(l.cn)->second;
             double* B = h_eptr_[r.eB];
             const int ldb = h_eld_[r.eB];
-            double* Y = Ybase + yoff[q];
+            double* Y = Yptr[q];
             g1[q] = GemmTask{Y, m, m, n, (int)q, 1, GEMM_ZERO_INIT | GEMM_POS | GEMM_TRIB};
             c1[q] = GemmContrib{B, w1.W, ldb, w1.ld, n};
             g2[q] = GemmTask{B, ldb, m, n, (int)q, 1, GEMM_NN | GEMM_ZERO_INIT | GEMM_POS | GEMM_TRIA};
@@ -2042,6 +2057,9 @@ void Tree::factorize() {
     }
     stager_.reset();
     scratch_->reset();
+    if (getenv("SPAND_TIMING"))
+        fprintf(stderr, "[spand] factorize: %.1f ms on the device; allocations of this process so far: %ld calls, %.2f GB, %.1f ms\n",
+                t_factorize_device * 1e3, g_malloc_calls, g_malloc_bytes / 1e9, g_malloc_seconds * 1e3);
     factorized_ = !stopped;
 }
 
