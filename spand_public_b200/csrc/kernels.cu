@@ -20,6 +20,15 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// a / d given rinv = RN(1 / d): product, exact remainder (one FMA), one correction (Markstein's division step). Three
+// dependent operations instead of the ~25-instruction IEEE division sequence on the substitution chain; the result is
+// the correctly rounded quotient except in rare cases that are off by one ulp.
+__device__ __forceinline__ double div_by(double a, double d, double rinv) {
+    const double q = a * rinv;
+    const double r = fma(-d, q, a);
+    return fma(r, rinv, q);
+}
+
 // ------------------------------------------------------------------------------------------------
 // POTRF, one 64x64 diagonal block per CTA (left-looking, one thread per row).
 // ------------------------------------------------------------------------------------------------
@@ -89,9 +98,10 @@ __device__ __forceinline__ void trsm_tile64(const double* T, int ldt, const doub
         if (tid < fw) {
             double* x = Xs + tid * LDS;
             for (int i = 0; i < nb; i++) {
+                const double d = Ts[i * LDS + i], rd = 1.0 / d;  // reciprocal off the dependent chain (div_by)
                 double v = x[i];
                 for (int p = 0; p < i; p++) v -= Ts[p * LDS + i] * x[p];
-                x[i] = v / Ts[i * LDS + i];
+                x[i] = div_by(v, d, rd);
             }
         }
         __syncthreads();
@@ -104,9 +114,10 @@ __device__ __forceinline__ void trsm_tile64(const double* T, int ldt, const doub
         __syncthreads();
         if (tid < fw) {
             for (int j = 0; j < nb; j++) {
+                const double d = Ts[j * LDS + j], rd = 1.0 / d;
                 double v = Xs[j * LDS + tid];
                 for (int p = 0; p < j; p++) v -= Xs[p * LDS + tid] * Ts[p * LDS + j];
-                Xs[j * LDS + tid] = v / Ts[j * LDS + j];
+                Xs[j * LDS + tid] = div_by(v, d, rd);
             }
             for (int j = 0; j < nb; j++) B[tid + (size_t)j * ldb] = Xs[j * LDS + tid];
         }
@@ -547,7 +558,8 @@ __global__ void __launch_bounds__(NB) trtri_kernel(const TrtriTask* __restrict__
 #pragma unroll
                 for (int p = 0; p < NB; p++)
                     if (p >= c && p < i) v -= S[p * LDS + i] * x[p];
-                x[i] = v / S[i * LDS + i];
+                const double d = S[i * LDS + i];
+                x[i] = div_by(v, d, 1.0 / d);  // the reciprocal does not depend on the chain
             }
         }
     }
@@ -722,10 +734,11 @@ __global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__
                     if (lane == j) dg = (j < nb) ? tr[j] : 1.0;
                 }
                 double xi = (lane < nb) ? x[j0 + lane] : 0.0;
+                const double rg = 1.0 / dg;
 #pragma unroll
                 for (int j = 0; j < SV_B; j++) {
                     if (j < nb) {
-                        double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                        double xj = div_by(__shfl_sync(0xffffffffu, xi, j), __shfl_sync(0xffffffffu, dg, j), __shfl_sync(0xffffffffu, rg, j));
                         if (lane == j) xi = xj;
                         if (lane > j && lane < nb) xi -= tr[j] * xj;
                     }
@@ -762,10 +775,11 @@ __global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__
                     if (lane == j) dg = (j < nb) ? tr[j] : 1.0;
                 }
                 double xi = (lane < nb) ? xb[lane] : 0.0;
+                const double rg = 1.0 / dg;
 #pragma unroll
                 for (int j = SV_B - 1; j >= 0; j--) {
                     if (j < nb) {
-                        double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                        double xj = div_by(__shfl_sync(0xffffffffu, xi, j), __shfl_sync(0xffffffffu, dg, j), __shfl_sync(0xffffffffu, rg, j));
                         if (lane == j) xi = xj;
                         if (lane < j) xi -= tr[j] * xj;
                     }
@@ -786,10 +800,11 @@ __global__ void __launch_bounds__(SV_T) trsv_kernel(const TrsvTask* __restrict__
                 }
                 if (t.diag && lane < nb) dg = t.diag[j0 + lane];
                 double xi = (lane < nb) ? x[j0 + lane] : 0.0;
+                const double rg = 1.0 / dg;
 #pragma unroll
                 for (int j = SV_B - 1; j >= 0; j--) {
                     if (j < nb) {
-                        double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                        double xj = div_by(__shfl_sync(0xffffffffu, xi, j), __shfl_sync(0xffffffffu, dg, j), __shfl_sync(0xffffffffu, rg, j));
                         if (lane == j) xi = xj;
                         if (lane < j) xi -= tr[j] * xj;
                     }
@@ -834,12 +849,13 @@ __global__ void __launch_bounds__(128) trsv_small_kernel(const TrsvTask* __restr
     for (int j = 0; j < 32; j++)
         if (lane == j) dg = tr[j];
     if (trans == 2 && t.diag != nullptr && lane < n) dg = t.diag[lane];
+    const double rg = 1.0 / dg;  // reciprocal of the own diagonal entry, off the substitution chain (div_by)
     __syncwarp();
     if (trans == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j++) {
             if (j < n) {
-                const double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                const double xj = div_by(__shfl_sync(0xffffffffu, xi, j), __shfl_sync(0xffffffffu, dg, j), __shfl_sync(0xffffffffu, rg, j));
                 if (lane == j) xi = xj;
                 if (lane > j) xi -= tr[j] * xj;
             }
@@ -848,7 +864,7 @@ __global__ void __launch_bounds__(128) trsv_small_kernel(const TrsvTask* __restr
 #pragma unroll
         for (int j = 31; j >= 0; j--) {
             if (j < n) {
-                const double xj = __shfl_sync(0xffffffffu, xi, j) / __shfl_sync(0xffffffffu, dg, j);
+                const double xj = div_by(__shfl_sync(0xffffffffu, xi, j), __shfl_sync(0xffffffffu, dg, j), __shfl_sync(0xffffffffu, rg, j));
                 if (lane == j) xi = xj;
                 if (lane < j) xi -= tr[j] * xj;
             }
@@ -1152,14 +1168,6 @@ __global__ void __launch_bounds__(NB) potrf_mid_kernel(DevTables T, const int* _
 
 // In-warp triangular solves on a tile Bs[col * WLD + row] (rows x cols); the triangle is read from global memory
 // (uniform addresses: one broadcast transaction per load, L1-resident).
-// a / d given rinv = RN(1 / d): product, exact remainder (one FMA), one correction (Markstein's division step). Three
-// dependent operations instead of the ~25-instruction IEEE division sequence on the substitution chain; the result is
-// the correctly rounded quotient except in rare cases that are off by one ulp.
-__device__ __forceinline__ double div_by(double a, double d, double rinv) {
-    const double q = a * rinv;
-    const double r = fma(-d, q, a);
-    return fma(r, rinv, q);
-}
 template <bool FASTDIV>
 __device__ __forceinline__ void warp_solve_right_lt(double* Bs, int rows, int cols, const double* L, int ldl, int lane) {
     // B <- B L^-T : lane = row of B
