@@ -1431,6 +1431,139 @@ __global__ void __launch_bounds__(256, 3) scale_mid256_kernel(DevTables T, const
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// GEN / PLU blocks up to 64 x 64, plan-driven (PluMode in kernels.cuh). The row permutation commutes with the right
+// solve (it acts on the other side), so it is applied while the block is loaded: tile row i <- block row perm[i].
+// ------------------------------------------------------------------------------------------------
+struct PluBlock {
+    double* B;
+    const double *U, *ud, *L;
+    const int* perm;
+    int ldb, ldu, ldl, rows, cols;
+    bool valid;
+};
+template <int MODE>
+__device__ __forceinline__ PluBlock plu_resolve(const DevTables& T, const SymTrsm* __restrict__ right,
+                                                const SymTrsm* __restrict__ left, int ti,
+                                                const double* const* __restrict__ ud,
+                                                const int* const* __restrict__ pperm) {
+    PluBlock b{};
+    b.valid = false;
+    int eB;
+    if (MODE == PLU_LEFT) {
+        const SymTrsm l = left[ti];  // B is |cn| x |cm|
+        eB = l.eB;
+        b.rows = T.csize[l.cn];
+        b.cols = T.csize[l.cm];
+        b.L = T.eptr[l.eT];
+        b.ldl = T.eld[l.eT];
+        b.perm = pperm[l.cn];
+    } else {
+        const SymTrsm r = right[ti];  // B is |cm| x |cn|
+        eB = r.eB;
+        b.rows = T.csize[r.cm];
+        b.cols = T.csize[r.cn];
+        b.U = T.eptr[r.eT];
+        b.ldu = T.eld[r.eT];
+        b.ud = ud[r.cn];
+        if (MODE == PLU_BOTH) {
+            const SymTrsm l = left[ti];
+            b.L = T.eptr[l.eT];
+            b.ldl = T.eld[l.eT];
+            b.perm = pperm[l.cn];
+        }
+    }
+    if (T.rank >= 0 && T.owner[T.en1[eB]] != T.rank) return b;
+    if (b.rows <= 0 || b.cols <= 0 || b.rows > SMALL_DIM || b.cols > SMALL_DIM) return b;
+    b.B = T.eptr[eB];
+    b.ldb = T.eld[eB];
+    b.valid = true;
+    return b;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) plu_sym_kernel(DevTables T, const SymTrsm* __restrict__ right,
+                                                      const SymTrsm* __restrict__ left, int nt,
+                                                      const double* const* __restrict__ ud,
+                                                      const int* const* __restrict__ pperm, int* mid, int* cnt) {
+    __shared__ double Sw[4][32 * WLD];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * 4 + w;
+    if (ti >= nt) return;
+    const PluBlock b = plu_resolve<MODE>(T, right, left, ti, ud, pperm);
+    if (!b.valid) return;
+    if (b.rows > 32 || b.cols > 32) {
+        if (lane == 0) push_mid(mid, cnt, ti);
+        return;
+    }
+    double* S = Sw[w];
+    const int rows = b.rows, cols = b.cols;
+    for (int x = lane; x < rows * cols; x += 32) {
+        const int i = x % rows, j = x / rows;
+        S[j * WLD + i] = b.B[(MODE == PLU_RIGHT ? i : b.perm[i]) + (size_t)j * b.ldb];
+    }
+    __syncwarp();
+    if (MODE != PLU_LEFT) {
+        // X U = B : lane = row; U(p, j) above the diagonal of the pivot block, diag(U) beside it
+        if (lane < rows)
+            for (int j = 0; j < cols; j++) {
+                const double d = b.ud[j], rd = 1.0 / d;
+                double v = S[j * WLD + lane];
+                for (int p = 0; p < j; p++) v -= S[p * WLD + lane] * b.U[p + (size_t)j * b.ldu];
+                S[j * WLD + lane] = div_by(v, d, rd);
+            }
+        __syncwarp();
+    }
+    if (MODE != PLU_RIGHT) {
+        warp_solve_left_ln<true>(S, rows, cols, b.L, b.ldl, lane);
+        __syncwarp();
+    }
+    warp_tile_store(S, b.B, b.ldb, rows, cols, lane);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 3) plu_mid256_kernel(DevTables T, const SymTrsm* __restrict__ right,
+                                                            const SymTrsm* __restrict__ left,
+                                                            const double* const* __restrict__ ud,
+                                                            const int* const* __restrict__ pperm,
+                                                            const int* __restrict__ mid, const int* __restrict__ cnt) {
+    extern __shared__ double trsm_smem[];
+    double* Bs = trsm_smem;
+    double* Ls = trsm_smem + NB * LDS;
+    const int nmid = *cnt;
+    for (int q = blockIdx.x; q < nmid; q += gridDim.x) {
+        const PluBlock b = plu_resolve<MODE>(T, right, left, mid[q], ud, pperm);
+        const int rows = b.rows, cols = b.cols;
+        for (int x = threadIdx.x; x < NB * NB; x += blockDim.x) {
+            const int i = x & (NB - 1), j = x >> 6;
+            Bs[j * LDS + i] =
+                (i < rows && j < cols) ? b.B[(MODE == PLU_RIGHT ? i : b.perm[i]) + (size_t)j * b.ldb] : 0.0;
+        }
+        if (MODE != PLU_LEFT) {
+            // U^T as the lower triangle of the right-looking solve: Ls[p * LDS + q] = U(p, q), diagonal from ud
+            for (int x = threadIdx.x; x < NB * NB; x += blockDim.x) {
+                const int i = x & (NB - 1), j = x >> 6;
+                double v = 0.0;
+                if (i < cols && j < i) v = b.U[j + (size_t)i * b.ldu];
+                else if (i == j && i < cols) v = b.ud[i];
+                Ls[j * LDS + i] = v;
+                if (i == j) Ls[j * LDS + NB] = (i < cols) ? 1.0 / v : 1.0;
+            }
+            __syncthreads();
+            tile_solve_rl<true, true>(Bs, Ls, cols, rows);  // B <- B U^-1
+            __syncthreads();
+        }
+        if (MODE != PLU_RIGHT) {
+            tile_load_l(Ls, b.L, b.ldl, rows);
+            __syncthreads();
+            tile_solve_rl<false, true>(Bs, Ls, rows, cols);  // B <- L^-1 (P^T B)
+            __syncthreads();
+        }
+        tile_store_b(Bs, b.B, b.ldb, rows, cols);
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ GemmContrib resolve_contrib(const DevTables& T, const SymCon c) {
     GemmContrib g;
     g.A = T.eptr[c.e1];
@@ -1856,6 +1989,26 @@ void launch_scale_sym(const DevTables& T, const SymTrsm* right, const SymTrsm* l
     else if (mid256())
         scale_mid256_kernel<false><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, right, left, mid, cnt);
     else scale_mid_kernel<<<std::min(nt, kMidGrid), NB, kTrsmSmem, st>>>(T, right, left, mid, cnt);
+}
+namespace {
+template <int MODE>
+void launch_plu_sym_mode(const DevTables& T, const SymTrsm* right, const SymTrsm* left, int nt, const double* const* ud,
+                         const int* const* pperm, int* mid, int* cnt, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(plu_mid256_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+        configured = true;
+    }
+    plu_sym_kernel<MODE><<<(nt + 3) / 4, 128, 0, st>>>(T, right, left, nt, ud, pperm, mid, cnt);
+    plu_mid256_kernel<MODE><<<std::min(nt, kMidGrid), 256, kTrsmSmem, st>>>(T, right, left, ud, pperm, mid, cnt);
+}
+}  // namespace
+void launch_plu_sym(int mode, const DevTables& T, const SymTrsm* right, const SymTrsm* left, int nt,
+                    const double* const* ud, const int* const* pperm, int* mid, int* cnt, cudaStream_t st) {
+    if (nt <= 0) return;
+    if (mode == PLU_BOTH) launch_plu_sym_mode<PLU_BOTH>(T, right, left, nt, ud, pperm, mid, cnt, st);
+    else if (mode == PLU_RIGHT) launch_plu_sym_mode<PLU_RIGHT>(T, right, left, nt, ud, pperm, mid, cnt, st);
+    else launch_plu_sym_mode<PLU_LEFT>(T, right, left, nt, ud, pperm, mid, cnt, st);
 }
 void launch_gemm_sym(const DevTables& T, const SymGemm* tasks, int nt, const SymCon* con, int* mid, int* cnt,
                      cudaStream_t st) {

@@ -256,6 +256,14 @@ void launch_scale_sym(const DevTables& T, const SymTrsm* right, const SymTrsm* l
                       cudaStream_t st, bool warp_only = false);
 void launch_gemm_sym(const DevTables& T, const SymGemm* tasks, int nt, const SymCon* con, int* mid, int* cnt,
                      cudaStream_t st);
+// GEN / PLU blocks with both dimensions <= 64 (src/tree.cpp:668-689, :838-853), plan-driven like the LLT batches.
+// ud[c] / pperm[c]: diag(U) and the row permutation of the current pivot of cluster c (device pointer tables).
+//   PLU_BOTH  (scale):           B <- L_row^-1 P_row^T (B U_col^-1); right[i] / left[i] describe the same block
+//   PLU_RIGHT (out-edge panels): B <- B U^-1                        (tasks in `right`, `left` unused)
+//   PLU_LEFT  (in-edge panels):  B <- L^-1 P^T B                    (tasks in `left`, `right` unused)
+enum PluMode { PLU_BOTH = 0, PLU_RIGHT = 1, PLU_LEFT = 2 };
+void launch_plu_sym(int mode, const DevTables& T, const SymTrsm* right, const SymTrsm* left, int nt,
+                    const double* const* ud, const int* const* pperm, int* mid, int* cnt, cudaStream_t st);
 void launch_copy_sym(const DevTables& T, const SymCopy* tasks, int nt, int pivots_identity, cudaStream_t st);
 void launch_expand_qsrc(const DevTables& T, const SymQrSrc* s, int n, QrSrc* out, cudaStream_t st);
 // recorded operations -> solve batches (sizes are captured now)

@@ -582,6 +582,8 @@ void Tree::assemble_impl(const SpMat* Afull, int n_in, const int* colptr, const 
     const size_t nedges = plan_.en1.size();
     d_pos_ = arena_->alloc_n<int>(ncl);
     d_xptr_ = arena_->alloc_n<double*>(ncl);
+    d_ud_ = arena_->alloc_n<double*>(ncl);
+    d_pperm_ = arena_->alloc_n<int*>(ncl);
     d_eptr_ = arena_->alloc_n<double*>(nedges);
     d_eld_ = arena_->alloc_n<int>(nedges);
     d_perm_ = arena_->alloc_n<int>(N);
@@ -1171,14 +1173,22 @@ void Tree::alloc_plu(int c) {
     h_pperm_[c] = reinterpret_cast<int*>(alloc_block(o, (n + 1) / 2));
 }
 
+// diag(U) / row permutation pointers of the pivots of the current level -> device tables read by the plan-driven kernels
+void Tree::upload_plu_tables() {
+    const std::vector<int>& bottom = bottoms_[current_bottom_];
+    if (bottom.empty()) return;
+    const int first = bottom.front(), span = bottom.back() - first + 1;
+    stager_.upload(d_ud_ + first, h_ud_.data() + first, sizeof(double*) * span, st_);
+    stager_.upload(d_pperm_ + first, h_pperm_.data() + first, sizeof(int*) * span, st_);
+}
+
 void Tree::phase_eliminate_plu(LevelLog& lg, SolveLevel& sl) {
     const SymLevel& L = plan_.lv[ilvl_];
     const DevLevel& D = dplan_[ilvl_];
     if (L.E.empty()) return;
+    const bool big = level_max_size() > SMALL_DIM;
     alloc_edges(L.fill0, L.fill1, false, lg);
     std::vector<GetrfTask> getrf;
-    std::vector<RowPermTask> rperm;
-    std::vector<TrsmTask> left, right;
     std::vector<TrsvTask> trsv;
     // Sharded over several GPUs: a pivot is factored by the owner of its cluster, a block is transformed / updated by
     // the owner of its column cluster (which reads the factor and the permutation of the row cluster through peer
@@ -1189,30 +1199,50 @@ void Tree::phase_eliminate_plu(LevelLog& lg, SolveLevel& sl) {
         if (mine(s)) getrf.push_back({h_eptr_[piv], h_eld_[piv], h_csize_[s], h_ud_[s], h_ipiv_[s], h_pperm_[s]});
         trsv.push_back({h_eptr_[piv], h_xptr_[s], h_eld_[piv], mine(s) ? h_csize_[s] : 0, h_ud_[s], h_pperm_[s]});
     }
-    for (const SymTrsm& t : L.e_in) {  // A[s,n] <- L^-1 P^T A[s,n]   (tree.cpp:668-676)
-        if (!mine(plan_.en1[t.eB])) continue;
-        rperm.push_back({h_eptr_[t.eB], h_eld_[t.eB], h_csize_[t.cn], h_csize_[t.cm], h_pperm_[t.cn]});
-        left.push_back(host_trsm(t, nullptr));
-    }
-    for (const SymTrsm& t : L.e_out)  // A[n,s] <- A[n,s] U^-1 (tree.cpp:681-689)
-        if (mine(plan_.en1[t.eB])) right.push_back(host_trsm(t, h_ud_[t.cn]));
     run_getrf(getrf, lg);
+    upload_plu_tables();
     mg_barrier();  // the in-edges of a pivot may belong to other ranks
-    run_rowperm(rperm, lg);
-    run_trsm(TRSM_LLN, left, lg);
-    run_trsm(TRSM_RUN, right, lg);
+    // panels with both dimensions <= 64: plan-driven (ids resolved on the device), the others through the blocked path
+    auto ev = fam_begin(F_TRSM);
+    launch_plu_sym(PLU_LEFT, tab_, nullptr, D.e_in, (int)L.e_in.size(), d_ud_, d_pperm_, d_mid_, next_counter(), st_);
+    launch_plu_sym(PLU_RIGHT, tab_, D.e_out, nullptr, (int)L.e_out.size(), d_ud_, d_pperm_, d_mid_, next_counter(), st_);
+    fam_end(F_TRSM, ev);
+    lg.launches += 4;
+    if (big) {
+        std::vector<RowPermTask> rperm;
+        std::vector<TrsmTask> left, right;
+        auto is_big = [&](const SymTrsm& t) {
+            const int m = h_csize_[t.cm], n = h_csize_[t.cn];
+            return (m > SMALL_DIM || n > SMALL_DIM) && m > 0 && n > 0 && mine(plan_.en1[t.eB]);
+        };
+        for (const SymTrsm& t : L.e_in) {  // A[s,n] <- L^-1 P^T A[s,n]   (tree.cpp:668-676)
+            if (!is_big(t)) continue;
+            rperm.push_back({h_eptr_[t.eB], h_eld_[t.eB], h_csize_[t.cn], h_csize_[t.cm], h_pperm_[t.cn]});
+            left.push_back(host_trsm(t, nullptr));
+        }
+        for (const SymTrsm& t : L.e_out)  // A[n,s] <- A[n,s] U^-1 (tree.cpp:681-689)
+            if (is_big(t)) right.push_back(host_trsm(t, h_ud_[t.cn]));
+        run_rowperm(rperm, lg);
+        run_trsm(TRSM_LLN, left, lg);
+        run_trsm(TRSM_RUN, right, lg);
+    }
     mg_barrier();  // a Schur target is updated by its owner, which reads the panels of other ranks
-    // Schur complement A[n1,n2] -= A[n1,s] A[s,n2] (tree.cpp:943-947)
-    {
+    // Schur complement A[n1,n2] -= A[n1,s] A[s,n2] (tree.cpp:943-947): targets up to 64 x 64 plan-driven
+    ev = fam_begin(F_GEMM);
+    launch_gemm_sym(tab_, D.e_gemm, (int)L.e_gemm.size(), D.e_con, d_mid_, next_counter(), st_);
+    fam_end(F_GEMM, ev);
+    lg.launches += 2;
+    if (big) {
         std::vector<GemmTask> tasks;
         std::vector<GemmContrib> con;
         for (const SymGemm& g : L.e_gemm) {
-            if (!mine(plan_.en1[g.target])) continue;
+            const int m = h_csize_[plan_.en2[g.target]], n = h_csize_[plan_.en1[g.target]];
+            if (!(m > SMALL_DIM || n > SMALL_DIM) || m == 0 || n == 0 || !mine(plan_.en1[g.target])) continue;
             GemmTask t;
             t.C = h_eptr_[g.target];
             t.ldc = h_eld_[g.target];
-            t.m = h_csize_[plan_.en2[g.target]];
-            t.n = h_csize_[plan_.en1[g.target]];
+            t.m = m;
+            t.n = n;
             t.c0 = (int)con.size();
             t.nc = g.nc;
             t.flags = g.flags;
@@ -1242,10 +1272,10 @@ void Tree::phase_eliminate_plu(LevelLog& lg, SolveLevel& sl) {
 
 void Tree::phase_scale_plu(LevelLog& lg, SolveLevel& sl) {
     const SymLevel& L = plan_.lv[ilvl_];
+    const DevLevel& D = dplan_[ilvl_];
     if (L.S.empty()) return;
+    const bool big = level_max_size() > SMALL_DIM;
     std::vector<GetrfTask> getrf;
-    std::vector<RowPermTask> rperm;
-    std::vector<TrsmTask> right, left;
     std::vector<TrsvTask> trsv;
     for (size_t i = 0; i < L.S.size(); i++) {
         const int c = L.S[i], piv = L.s_piv[i];
@@ -1253,20 +1283,32 @@ void Tree::phase_scale_plu(LevelLog& lg, SolveLevel& sl) {
         if (mine(c)) getrf.push_back({h_eptr_[piv], h_eld_[piv], h_csize_[c], h_ud_[c], h_ipiv_[c], h_pperm_[c]});
         trsv.push_back({h_eptr_[piv], h_xptr_[c], h_eld_[piv], mine(c) ? h_csize_[c] : 0, h_ud_[c], h_pperm_[c]});
     }
-    for (size_t i = 0; i < L.s_right.size(); i++) {
-        // block A[n2,n1] (|n2| x |n1|): out-edge of n1 -> B U_n1^-1 ; in-edge of n2 -> L_n2^-1 P_n2^T B
-        const SymTrsm& r = L.s_right[i];
-        const SymTrsm& l = L.s_left[i];
-        if (!mine(plan_.en1[r.eB])) continue;  // both transformations of a block run on the owner of its column cluster
-        right.push_back(host_trsm(r, h_ud_[r.cn]));
-        rperm.push_back({h_eptr_[l.eB], h_eld_[l.eB], h_csize_[l.cn], h_csize_[l.cm], h_pperm_[l.cn]});
-        left.push_back(host_trsm(l, nullptr));
-    }
     run_getrf(getrf, lg);
+    upload_plu_tables();
     mg_barrier();  // a block needs the factor and the permutation of its row cluster too, possibly from another rank
-    run_trsm(TRSM_RUN, right, lg);
-    run_rowperm(rperm, lg);
-    run_trsm(TRSM_LLN, left, lg);
+    // block A[n2,n1] (|n2| x |n1|): out-edge of n1 -> B U_n1^-1 ; in-edge of n2 -> L_n2^-1 P_n2^T B. Both
+    // transformations of a block run on the owner of its column cluster. Blocks up to 64 x 64: one fused plan-driven
+    // pass (permuted load, two substitutions, one store); larger ones through the blocked path.
+    auto ev = fam_begin(F_TRSM);
+    launch_plu_sym(PLU_BOTH, tab_, D.s_right, D.s_left, (int)L.s_right.size(), d_ud_, d_pperm_, d_mid_, next_counter(), st_);
+    fam_end(F_TRSM, ev);
+    lg.launches += 2;
+    if (big) {
+        std::vector<RowPermTask> rperm;
+        std::vector<TrsmTask> right, left;
+        for (size_t i = 0; i < L.s_right.size(); i++) {
+            const SymTrsm& r = L.s_right[i];
+            const SymTrsm& l = L.s_left[i];
+            const int m = h_csize_[r.cm], n = h_csize_[r.cn];
+            if (!((m > SMALL_DIM || n > SMALL_DIM) && m > 0 && n > 0 && mine(plan_.en1[r.eB]))) continue;
+            right.push_back(host_trsm(r, h_ud_[r.cn]));
+            rperm.push_back({h_eptr_[l.eB], h_eld_[l.eB], h_csize_[l.cn], h_csize_[l.cm], h_pperm_[l.cn]});
+            left.push_back(host_trsm(l, nullptr));
+        }
+        run_trsm(TRSM_RUN, right, lg);
+        run_rowperm(rperm, lg);
+        run_trsm(TRSM_LLN, left, lg);
+    }
     sl.s_trsv = to_device(trsv, arena_);
     sl.max_s = level_max_size();
     sl.n_s_trsv = (int)trsv.size();

@@ -246,6 +246,9 @@ class Tree {
     // PLU: diag(U), swap sequence and permutation of the current pivot of every cluster
     std::vector<double*> h_ud_;
     std::vector<int*> h_ipiv_, h_pperm_;
+    double** d_ud_ = nullptr;  // device tables of the two (plan-driven PLU kernels)
+    int** d_pperm_ = nullptr;
+    void upload_plu_tables();
     // cluster sizes before the elimination and after the sparsification of every level: the flop / byte / nnz
     // model is evaluated from these after the factorization (finalize_logs), off the critical path
     std::vector<std::vector<int>> size_pre_, size_post_;
