@@ -522,6 +522,18 @@ __global__ void __launch_bounds__(256) gemm_tiled_kernel(const GemmTask* __restr
     });
 }
 
+__global__ void __launch_bounds__(256) ut_kernel(const UtTask* __restrict__ tasks) {
+    const UtTask t = tasks[blockIdx.x];
+    const size_t total = (size_t)t.n * t.n;
+    for (size_t x = (size_t)blockIdx.y * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.y * blockDim.x) {
+        const int p = (int)(x % t.n), i = (int)(x / t.n);  // reads run down a column of U
+        double v = 0.0;
+        if (p < i) v = t.U[p + (size_t)i * t.ldu];
+        else if (p == i) v = t.ud[i];
+        t.Lt[i + (size_t)p * t.n] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) eye_kernel(const EyeTask* __restrict__ tasks) {
     const EyeTask t = tasks[blockIdx.x];
     const size_t total = (size_t)t.n * t.n;
@@ -1814,6 +1826,9 @@ void launch_trtri(const TrtriTask* t, int nt, int max_n, cudaStream_t st) {
     if (nt <= 0 || max_n <= 0) return;
     dim3 grid(nt, (max_n + NB - 1) / NB);
     trtri_kernel<<<grid, NB, 0, st>>>(t);
+}
+void launch_ut(const UtTask* t, int nt, cudaStream_t st) {
+    if (nt > 0) ut_kernel<<<dim3(nt, 8), 256, 0, st>>>(t);
 }
 void launch_eye(const EyeTask* t, int nt, cudaStream_t st) {
     if (nt > 0) eye_kernel<<<dim3(nt, 8), 256, 0, st>>>(t);

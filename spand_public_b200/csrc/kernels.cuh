@@ -53,6 +53,13 @@ struct TrtriTask {  // inverses of the diagonal blocks of one triangle
     int ldw;  // 0: 64 x 64 blocks of 4096 doubles each; > 0 (n <= 64 only): one n x n block with this leading dimension
 };
 
+struct UtTask {  // Lt (n x n, leading dimension n) <- U^T as a lower triangle: Lt(i, p) = U(p, i) for p < i, Lt(i, i) = ud[i]
+    const double* U;
+    const double* ud;
+    double* Lt;
+    int ldu, n;
+};
+
 struct EyeTask {  // W (n x n, leading dimension ld) <- I
     double* W;
     int n, ld;
@@ -167,6 +174,7 @@ void launch_trsm_step(int mode, const TrsmTask* t, int nt, int j0, int max_m, cu
 // prefix of ceil(m / 64).
 void launch_trtri(const TrtriTask* t, int nt, int max_n, cudaStream_t st);
 void launch_eye(const EyeTask* t, int nt, cudaStream_t st);
+void launch_ut(const UtTask* t, int nt, cudaStream_t st);
 void launch_trsm_strip(int mode, const TrsmTask* t, int nt, const int* strip_prefix, int total_strips, cudaStream_t st);
 // GETRF with partial pivoting. n <= 64: one launch does everything (factor, split_LU, perm). Larger: right-looking
 // over 64-wide panels: launch_getrf_panel (pivoting inside the panel) -> launch_getrf_laswp (row swaps outside the

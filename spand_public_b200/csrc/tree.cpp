@@ -1293,7 +1293,13 @@ void Tree::phase_scale_plu(LevelLog& lg, SolveLevel& sl) {
     launch_plu_sym(PLU_BOTH, tab_, D.s_right, D.s_left, (int)L.s_right.size(), d_ud_, d_pperm_, d_mid_, next_counter(), st_);
     fam_end(F_TRSM, ev);
     lg.launches += 2;
-    if (big) {
+    if (scale_inv_mode_ < 0) {
+        const char* e = std::getenv("SPAND_SCALE_INV");
+        scale_inv_mode_ = e ? std::atoi(e) : 1;
+    }
+    if (big && scale_inv_mode_ >= 1) {
+        run_scale_inv(SMALL_DIM, lg);  // explicit inverses + two grouped GEMM launches (row permutation in between)
+    } else if (big) {
         std::vector<RowPermTask> rperm;
         std::vector<TrsmTask> right, left;
         for (size_t i = 0; i < L.s_right.size(); i++) {
@@ -1381,6 +1387,7 @@ void Tree::phase_scale(LevelLog& lg, SolveLevel& sl) {
 // ones by the strip solve L X = I on top of the inverted diagonal blocks. When sharded, a rank inverts the pivots its
 // own blocks need (the factor of a remote row cluster is read through peer memory, after the barrier above).
 void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
+    const bool plu = scale_kind == PLU;
     const SymLevel& L = plan_.lv[ilvl_];
     const size_t nb_all = L.s_right.size();
     if (nb_all == 0) return;
@@ -1398,38 +1405,51 @@ void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
     for (int t = 0; t < nth; t++) idx.insert(idx.end(), part[t].begin(), part[t].end());
     const size_t nt = idx.size();
     if (nt == 0) return;
-    // 2. inverses of the pivots these blocks touch
+    // 2. inverses of the pivots these blocks touch. LLT: W = L^-1 for both sides. PLU: the row side uses L^-1 of the
+    // pivot (lower part of the block, its own diagonal), the column side (U^T)^-1 with U^T materialised as a lower
+    // triangle (strictly upper part of the block + diag(U) kept beside it), so that B U^-1 = B ((U^T)^-1)^T is the same
+    // NT product as in the LLT case.
     struct Inv {
         const double* W = nullptr;
         int ld = 0;
     };
-    std::unordered_map<int, Inv> inv;
+    std::unordered_map<long long, Inv> inv;  // key: 2 * cluster + (1: column side of a PLU pivot)
     std::vector<TrtriTask> tt;
+    std::vector<UtTask> ut;
     std::vector<EyeTask> eye;
     std::vector<TrsmTask> solve;
     std::vector<int> sprefix(1, 0);
     int max_n = 0;
-    auto need = [&](int c, int eT) {
-        if (inv.count(c)) return;
+    auto need = [&](int c, int eT, bool upper) {
+        const long long key = 2LL * c + (upper ? 1 : 0);
+        if (inv.count(key)) return;
         const int n = h_csize_[c];
+        const double* T = h_eptr_[eT];
+        int ldt = h_eld_[eT];
+        if (upper) {
+            double* Lt = scratch_->alloc_n<double>((size_t)n * n);
+            ut.push_back({T, h_ud_[c], Lt, ldt, n});
+            T = Lt;
+            ldt = n;
+        }
         Inv w;
         if (n <= NB) {
             const int ld = (n + 1) & ~1;
             double* W = scratch_->alloc_n<double>((size_t)ld * n);
-            tt.push_back({h_eptr_[eT], h_eld_[eT], n, W, ld});
+            tt.push_back({T, ldt, n, W, ld});
             w.W = W;
             w.ld = ld;
         } else {
             const int nblk = (n + NB - 1) / NB;
             double* blocks = scratch_->alloc_n<double>((size_t)nblk * NB * NB);
             double* W = scratch_->alloc_n<double>((size_t)n * n);
-            tt.push_back({h_eptr_[eT], h_eld_[eT], n, blocks, 0});
+            tt.push_back({T, ldt, n, blocks, 0});
             eye.push_back({W, n, n});
             TrsmTask s{};
             s.B = W;
             s.ldb = n;
-            s.T = h_eptr_[eT];
-            s.ldt = h_eld_[eT];
+            s.T = T;
+            s.ldt = ldt;
             s.m = n;
             s.n = n;
             s.inv = blocks;
@@ -1440,11 +1460,11 @@ void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
             w.ld = n;
         }
         max_n = std::max(max_n, n);
-        inv.emplace(c, w);
+        inv.emplace(key, w);
     };
     for (size_t q = 0; q < nt; q++) {
-        need(L.s_right[idx[q]].cn, L.s_right[idx[q]].eT);
-        need(L.s_left[idx[q]].cn, L.s_left[idx[q]].eT);
+        need(L.s_right[idx[q]].cn, L.s_right[idx[q]].eT, plu);
+        need(L.s_left[idx[q]].cn, L.s_left[idx[q]].eT, false);
     }
     // 3. the two grouped products
     std::vector<size_t> yoff(nt + 1, 0);
@@ -1461,14 +1481,15 @@ void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
     for (size_t q = 0; q < nt; q++) Yptr[q] = scratch_->alloc_n<double>(yoff[q + 1] - yoff[q]);
     std::vector<GemmTask> g1(nt), g2(nt);
     std::vector<GemmContrib> c1(nt), c2(nt);
+    std::vector<RowPermTask> rperm(plu ? nt : 0);
     std::vector<int> tile_task(prefix[nt]);
     parallel_chunks(nt, [&](int, size_t b, size_t e) {
         for (size_t q = b; q < e; q++) {
             const SymTrsm& r = L.s_right[idx[q]];
             const SymTrsm& l = L.s_left[idx[q]];
             const int m = h_csize_[r.cm], n = h_csize_[r.cn];
-            const Inv& w1 = inv.find(r.cn)->second;
-            const Inv& w2 = inv.find(l.cn)->second;
+            const Inv& w1 = inv.find(2LL * r.cn + (plu ? 1 : 0))->second;
+            const Inv& w2 = inv.find(2LL * l.cn)->second;
             double* B = h_eptr_[r.eB];
             const int ldb = h_eld_[r.eB];
             double* Y = Yptr[q];
@@ -1476,9 +1497,14 @@ void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
             c1[q] = GemmContrib{B, w1.W, ldb, w1.ld, n};
             g2[q] = GemmTask{B, ldb, m, n, (int)q, 1, GEMM_NN | GEMM_ZERO_INIT | GEMM_POS | GEMM_TRIA};
             c2[q] = GemmContrib{w2.W, Y, w2.ld, m, m};
+            if (plu) rperm[q] = RowPermTask{Y, m, m, n, h_pperm_[l.cn]};  // rows of Y <- rows perm[.] (P^T of the row pivot)
             for (int x = prefix[q]; x < prefix[q + 1]; x++) tile_task[x] = (int)q;
         }
     });
+    if (plu)
+        for (auto& t : rperm)
+            if (t.n > 6144) throw std::runtime_error("PLU pivot larger than 6144 is not supported by the row permutation kernel");
+    UtTask* dut = to_device(ut, scratch_);
     TrtriTask* dtt = to_device(tt, scratch_);
     EyeTask* deye = to_device(eye, scratch_);
     TrsmTask* dsolve = to_device(solve, scratch_);
@@ -1487,9 +1513,14 @@ void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
     GemmTask* dg2 = to_device(g2, scratch_);
     GemmContrib* dc1 = to_device(c1, scratch_);
     GemmContrib* dc2 = to_device(c2, scratch_);
+    RowPermTask* drp = to_device(rperm, scratch_);
     int* dp = to_device(prefix, scratch_);
     int* dtile = to_device(tile_task, scratch_);
     auto ev = fam_begin(F_TRSM);
+    if (!ut.empty()) {
+        launch_ut(dut, (int)ut.size(), st_);
+        lg.launches++;
+    }
     launch_trtri(dtt, (int)tt.size(), max_n, st_);
     if (!solve.empty()) {
         launch_eye(deye, (int)eye.size(), st_);
@@ -1497,6 +1528,10 @@ void Tree::run_scale_inv(int min_dim, LevelLog& lg) {
         lg.launches += 2;
     }
     launch_gemm_tiled(dg1, (int)nt, dc1, dp, prefix[nt], st_, dtile);
+    if (plu) {
+        launch_rowperm(drp, (int)nt, st_);
+        lg.launches++;
+    }
     launch_gemm_tiled(dg2, (int)nt, dc2, dp, prefix[nt], st_, dtile);
     fam_end(F_TRSM, ev);
     lg.launches += 3;
