@@ -142,16 +142,6 @@ __global__ void __launch_bounds__(NB) trsm_step_kernel(const TrsmTask* __restric
 // ------------------------------------------------------------------------------------------------
 // GETRF with partial pivoting (dgetrf semantics: first maximal |a| wins) + split_LU (src/util.cpp:213-227).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_entry(double* A, int ld, int i, int j, const double* d) {
-    // d = diag of the LAPACK factor. L(i,j) = l_ij |d_j|^1/2 ; U(i,j) = s_i (u_ij / d_i), s_i = sign(d_i) |d_i|^1/2
-    double a = A[i + (size_t)j * ld];
-    if (i > j) A[i + (size_t)j * ld] = a * sqrt(fabs(d[j]));
-    else if (i < j) {
-        double di = d[i];
-        double si = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sqrt(fabs(di));
-        A[i + (size_t)j * ld] = si * ((1.0 / di) * a);
-    } else A[i + (size_t)j * ld] = sqrt(fabs(a));
-}
 
 __global__ void __launch_bounds__(NB) getrf_small_kernel(const GetrfTask* __restrict__ tasks, int* err) {
     GetrfTask t = tasks[blockIdx.x];
@@ -211,26 +201,28 @@ __global__ void __launch_bounds__(NB) getrf_small_kernel(const GetrfTask* __rest
         }
         __syncthreads();
     }
+    // split_LU (src/util.cpp:213-227); the square roots and reciprocals once per row, not once per entry
+    double di = 1.0, sqi = 1.0;
     if (i < n) {
-        dd[i] = S[i * LDS + i];
+        di = S[i * LDS + i];
+        sqi = sqrt(fabs(di));
+        dd[i] = sqi;
         t.perm[i] = prm[i];
     }
     __syncthreads();
     if (i < n) {
-        double di = dd[i];
-        t.ud[i] = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sqrt(fabs(di));
-    }
-    for (int j = 0; j < n; j++)
-        if (i < n) {
-            double a = S[j * LDS + i], o;
-            if (i > j) o = a * sqrt(fabs(dd[j]));
-            else if (i < j) {
-                double di = dd[i];
-                double si = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sqrt(fabs(di));
-                o = si * ((1.0 / di) * a);
-            } else o = sqrt(fabs(a));
+        const double si = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sqi;
+        const double ri = 1.0 / di;
+        t.ud[i] = si;
+        for (int j = 0; j < n; j++) {
+            const double a = S[j * LDS + i];
+            double o;
+            if (i > j) o = a * dd[j];
+            else if (i < j) o = si * (ri * a);
+            else o = sqi;
             t.A[i + (size_t)j * t.ld] = o;
         }
+    }
 }
 
 // Panel [j0, j0 + nbp) x rows [j0, n) of every matrix with n > j0, factored in place (global memory / L2).
@@ -334,24 +326,48 @@ __global__ void __launch_bounds__(256) getrf_finish_kernel(const GetrfTask* __re
     GetrfTask t = tasks[blockIdx.x];
     const int n = t.n;
     if (n <= NB) return;  // small pivots were finished by getrf_small_kernel
-    extern __shared__ double dfin[];  // n: the LAPACK diagonal
+    // n: the LAPACK diagonal | n: |d|^1/2 | n: 1 / d | 2 n ints: permutation, swap sequence (32 n bytes = 128 KB at n = 4096)
+    extern __shared__ double dfin[];
+    double* sq = dfin + n;
+    double* rinv = sq + n;
+    int* prm = reinterpret_cast<int*>(rinv + n);
+    int* swp = prm + n;  // the LAPACK swap sequence (32 n bytes in all)
     const int tid = threadIdx.x;
-    for (int i = tid; i < n; i += 256) dfin[i] = t.A[i + (size_t)i * t.ld];
-    if (tid == 0) {  // swap2perm (src/util.cpp:76-88)
-        for (int i = 0; i < n; i++) t.perm[i] = i;
+    for (int i = tid; i < n; i += 256) {
+        const double di = t.A[i + (size_t)i * t.ld];
+        dfin[i] = di;
+        sq[i] = sqrt(fabs(di));
+        rinv[i] = 1.0 / di;
+        prm[i] = i;
+        swp[i] = t.ipiv[i];
+    }
+    __syncthreads();
+    if (tid == 0) {  // swap2perm (src/util.cpp:76-88), a serial chain: on shared memory, not on global
         for (int i = 0; i < n; i++) {
-            int p = t.ipiv[i];
-            int tmp = t.perm[p];
-            t.perm[p] = t.perm[i];
-            t.perm[i] = tmp;
+            const int p = swp[i];
+            const int tmp = prm[p];
+            prm[p] = prm[i];
+            prm[i] = tmp;
         }
     }
     __syncthreads();
     for (int i = tid; i < n; i += 256) {
-        double di = dfin[i];
-        t.ud[i] = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sqrt(fabs(di));
+        const double di = dfin[i];
+        t.ud[i] = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sq[i];
+        t.perm[i] = prm[i];
     }
-    for (size_t e = tid; e < (size_t)n * n; e += 256) split_entry(t.A, t.ld, (int)(e % n), (int)(e / n), dfin);
+    // split_LU (src/util.cpp:213-227): L(i,j) = l_ij |d_j|^1/2 ; U(i,j) = s_i ((1 / d_i) u_ij), s_i = sign(d_i) |d_i|^1/2
+    for (size_t e = tid; e < (size_t)n * n; e += 256) {
+        const int i = (int)(e % n), j = (int)(e / n);
+        double* p = t.A + i + (size_t)j * t.ld;
+        const double a = *p;
+        if (i > j) *p = a * sq[j];
+        else if (i < j) {
+            const double di = dfin[i];
+            const double si = (di > 0 ? 1.0 : (di < 0 ? -1.0 : 0.0)) * sq[i];
+            *p = si * (rinv[i] * a);
+        } else *p = sq[i];
+    }
 }
 
 __global__ void __launch_bounds__(128) rowperm_kernel(const RowPermTask* __restrict__ tasks) {
