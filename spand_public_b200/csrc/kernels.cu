@@ -291,12 +291,26 @@ __global__ void __launch_bounds__(GP_T) getrf_panel_kernel(const GetrfTask* __re
             if (tid == 0) atomicOr(err, 2);
             continue;
         }
-        const int nr = n - col - 1, ncc = nbp - c - 1;
-        for (int r = tid; r < nr; r += GP_T) A[col + 1 + r + col * ld] /= akk;
-        __syncthreads();
-        for (int e = tid; e < nr * ncc; e += GP_T) {
-            int r = e % nr, cc = e / nr;
-            A[col + 1 + r + (col + 1 + cc) * ld] -= A[col + 1 + r + col * ld] * rowk[c + 1 + cc];
+        // a thread owns rows: multiplier of the row, then its part of the rank-1 update of the panel (coalesced over
+        // the threads for every column, independent updates along the row, no index arithmetic in the loop)
+        const int ncc = nbp - c - 1;
+        const double* rk = rowk + c + 1;
+        for (int r = col + 1 + tid; r < n; r += GP_T) {
+            double* a = A + r + col * ld;
+            const double l = *a / akk;
+            *a = l;
+            a += ld;
+            int cc = 0;
+            for (; cc + 3 < ncc; cc += 4) {
+                const double x0 = a[0] - l * rk[cc], x1 = a[ld] - l * rk[cc + 1];
+                const double x2 = a[2 * ld] - l * rk[cc + 2], x3 = a[3 * ld] - l * rk[cc + 3];
+                a[0] = x0;
+                a[ld] = x1;
+                a[2 * ld] = x2;
+                a[3 * ld] = x3;
+                a += 4 * ld;
+            }
+            for (; cc < ncc; cc++, a += ld) *a -= l * rk[cc];
         }
         __syncthreads();
     }
@@ -376,7 +390,7 @@ __global__ void __launch_bounds__(128) rowperm_kernel(const RowPermTask* __restr
     const int n = t.n;
     if (n == 0 || t.m == 0) return;
     const int w = max(1, min(t.m, 6144 / n));
-    for (int c0 = 0; c0 < t.m; c0 += w) {
+    for (int c0 = blockIdx.y * w; c0 < t.m; c0 += gridDim.y * w) {  // column strips of a block over blockIdx.y
         const int cw = min(w, t.m - c0);
         for (int e = threadIdx.x; e < n * cw; e += 128) {
             int i = e % n, c = e / n;
@@ -1883,7 +1897,7 @@ void launch_rowperm(const RowPermTask* t, int nt, cudaStream_t st) {
         cudaFuncSetAttribute(rowperm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
-    rowperm_kernel<<<nt, 128, smem, st>>>(t);
+    rowperm_kernel<<<dim3(nt, nt >= 2048 ? 1 : (nt >= 256 ? 4 : 16)), 128, smem, st>>>(t);
 }
 
 void launch_gemm_tiled(const GemmTask* t, int nt, const GemmContrib* c, const int* tile_prefix, int total_tiles,
