@@ -13,11 +13,13 @@ for C in c3 c5s; do
   timeout 600 python bench.py --steps 3 --warmup 3 --config $C --no-cpu-baseline > gpurun_out/bench_${C}_$T.json 2> gpurun_out/bench_${C}_$T.err
   echo "bench $C rc=$?"
 done
+timeout 600 python bench.py --steps 2 --warmup 2 --config c5 --no-cpu-baseline > gpurun_out/bench_c5_$T.json 2> gpurun_out/bench_c5_$T.err
+echo "bench c5 rc=$?"
 timeout 300 python bench.py --steps 5 --warmup 3 --config c2 --algebraic > gpurun_out/bench_c2_algebraic_$T.json 2> gpurun_out/bench_c2_algebraic_$T.err
 echo "bench c2 algebraic rc=$?"
 python - <<PY
 import json
-for f in ("bench_c4_$T", "bench_c3_$T", "bench_c5s_$T", "bench_c2_algebraic_$T"):
+for f in ("bench_c4_$T", "bench_c3_$T", "bench_c5s_$T", "bench_c5_$T", "bench_c2_algebraic_$T"):
     try:
         d=json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
         print(f, round(d["ms_per_step"],2), "ms", round(d["value"],2), "Mdof/s e2e", round(d["e2e"]["value"],2), "cold", round(d["e2e_cold"]["seconds"],2),
