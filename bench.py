@@ -529,7 +529,7 @@ def main():
         # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel family, from the
         # ncu capture of this same command committed under profiles/ (scripts/ncu_traffic.py); averaged over the
         # launches of the family like `achieved`
-        cand = [os.path.join(ROOT, "profiles", f) for f in ("r2b_ncu_traffic.json", "r2_ncu_traffic.json")]
+        cand = [os.path.join(ROOT, "profiles", f) for f in ("r2c_ncu_traffic.json", "r2_ncu_traffic.json")]
         tr = json.load(open([f for f in cand if os.path.exists(f)][0]))
         if dom in tr.get("families", {}):
             roof["traffic"] = tr["families"][dom]["dram_bytes_per_launch"]
