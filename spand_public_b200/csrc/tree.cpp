@@ -1574,17 +1574,25 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
         std::vector<int> task_color(nq);
         size_t vtotal = 0, ttotal = 0;
         std::vector<size_t> voff(nq), toff(nq);
+        // sizes of every task (sum over its ~10-30 neighbours: the bulk of the planning time on the low levels): host threads
+        parallel_chunks(nq, [&](int, size_t b, size_t e) {
+            for (size_t i = b; i < e; i++) {
+                const SymQr& q = *own[i];
+                QrTask& t = tasks[i];
+                t.cluster = q.cluster;
+                t.rows = h_csize_[q.cluster];
+                t.src0 = q.src0;
+                t.nsrc = q.nsrc;
+                int maxcols = 0;
+                for (int k = 0; k < q.nsrc; k++) maxcols += h_csize_[L.qs[q.src0 + k].nbr];
+                t.maxcols = maxcols;
+                t.W = nullptr;
+            }
+        }, 16384);
         for (size_t i = 0; i < nq; i++) {
             const SymQr& q = *own[i];
             QrTask& t = tasks[i];
-            t.cluster = q.cluster;
-            t.rows = h_csize_[q.cluster];
-            t.src0 = q.src0;
-            t.nsrc = q.nsrc;
-            int maxcols = 0;
-            for (int k = 0; k < q.nsrc; k++) maxcols += h_csize_[L.qs[q.src0 + k].nbr];
-            t.maxcols = maxcols;
-            t.W = nullptr;
+            const int maxcols = t.maxcols;
             const size_t kmax = std::min(t.rows, maxcols);
             voff[i] = vtotal;
             toff[i] = ttotal;
