@@ -103,7 +103,10 @@ void Stager::upload(void* dst, const void* src, size_t bytes, cudaStream_t st) {
         if (bytes > cap_) reserve(std::max(bytes, 2 * cap_));
         top_ = 0;
     }
-    std::memcpy(pinned_ + top_, src, bytes);
+    // large descriptor arrays (tens of MB per level on the low levels): the staging copy on host threads
+    char* const stage = pinned_ + top_;
+    const char* const from = static_cast<const char*>(src);
+    parallel_chunks(bytes, [&](int, size_t b, size_t e) { std::memcpy(stage + b, from + b, e - b); }, (size_t)4 << 20);
     CK(cudaMemcpyAsync(dst, pinned_ + top_, bytes, cudaMemcpyHostToDevice, st));
     top_ += (bytes + 63) & ~(size_t)63;
 }
@@ -639,10 +642,12 @@ void Tree::assemble_impl(const SpMat* Afull, int n_in, const int* colptr, const 
         h_csize_[c] = cl_[c].size;
     }
     double* dblocks = leaf_base[mg() ? mg_rank : 0];
-    for (int e = 0; e < plan_.nleaf_edges; e++) {
-        h_eptr_[e] = leaf_base[mg() ? h_owner_[plan_.en1[e]] : 0] + leaf_off_[e];
-        h_eld_[e] = std::max(1, cl_[plan_.en2[e]].size);
-    }
+    parallel_chunks((size_t)plan_.nleaf_edges, [&](int, size_t b, size_t e1) {
+        for (size_t e = b; e < e1; e++) {
+            h_eptr_[e] = leaf_base[mg() ? h_owner_[plan_.en1[e]] : 0] + leaf_off_[e];
+            h_eld_[e] = std::max(1, cl_[plan_.en2[e]].size);
+        }
+    });
     lap("host tables");
     stager_.upload(d_perm_, ord.perm.data(), sizeof(int) * N, st_);
     stager_.upload(d_csize_, h_csize_.data(), sizeof(int) * ncl, st_);
@@ -1829,12 +1834,17 @@ void Tree::phase_sparsify(LevelLog& lg, SolveLevel& sl) {
             smem_need[i] = (int)nd;
         }
         // order tasks by (colour, class), stable
+        // (a stable counting sort: the keys are small integers, 10^5 tasks on the low levels)
         std::vector<int> idx(nq);
-        for (size_t i = 0; i < nq; i++) idx[i] = (int)i;
-        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
-            if (task_color[a] != task_color[b]) return task_color[a] < task_color[b];
-            return klass[a] < klass[b];
-        });
+        {
+            int kmax = 0;
+            for (size_t i = 0; i < nq; i++) kmax = std::max(kmax, klass[i]);
+            const size_t nk = (size_t)kmax + 1;
+            std::vector<size_t> start((size_t)std::max(1, ncolors) * nk + 1, 0);
+            for (size_t i = 0; i < nq; i++) start[(size_t)task_color[i] * nk + klass[i] + 1]++;
+            for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+            for (size_t i = 0; i < nq; i++) idx[start[(size_t)task_color[i] * nk + klass[i]]++] = (int)i;
+        }
         std::vector<QrTask> sorted(nq);
         for (size_t i = 0; i < nq; i++) sorted[i] = tasks[idx[i]];
         QrTask* dt = to_device(sorted, scratch_);
