@@ -50,7 +50,21 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
             if (en2[e] == n2) return e;
         return -1;
     };
-    // leaf edges (src/tree.cpp:505-575)
+    // leaf edges (src/tree.cpp:505-575); the adjacency lists are sized first (one allocation per list instead of the
+    // doubling sequence of push_back: 10^6 lists)
+    {
+        std::vector<int> od(ncl, 0), id(ncl, 0);
+        for (size_t i = 0; i < leaf_n1.size(); i++) {
+            od[leaf_n1[i]]++;
+            if (leaf_n1[i] != leaf_n2[i]) id[leaf_n2[i]]++;
+        }
+        parallel_chunks((size_t)ncl, [&](int, size_t b, size_t e) {
+            for (size_t c = b; c < e; c++) {
+                if (od[c]) out[c].reserve(od[c] + 8);  // + fill-in edges of the first levels
+                if (id[c]) in[c].reserve(id[c]);
+            }
+        }, 65536);
+    }
     for (size_t i = 0; i < leaf_n1.size(); i++) {
         int e = new_edge(leaf_n1[i], leaf_n2[i]);
         if (leaf_n1[i] == leaf_n2[i]) out[leaf_n1[i]].insert(out[leaf_n1[i]].begin(), e);
@@ -346,6 +360,18 @@ void build_symbolic(const std::vector<SymCluster>& cl, const std::vector<std::ve
                 pend_off[t + 1] = pend_off[t] + parts[t].pend.size();
             }
             npend = pend_off[nth];
+            {   // sizes of the parents' lists (pivot + one out-edge per neighbour, in-edges counted here)
+                for (int t = 0; t < nth; t++) {
+                    size_t k = 0;
+                    const auto& ne = parts[t].ne;
+                    while (k < ne.size()) {
+                        size_t k2 = k;
+                        while (k2 < ne.size() && ne[k2].n1 == ne[k].n1) k2++;
+                        out[ne[k].n1].reserve(k2 - k + 8);
+                        k = k2;
+                    }
+                }
+            }
             for (int t = 0; t < nth; t++)
                 for (auto& n : parts[t].ne) {
                     int e = new_edge(n.n1, n.n2);
